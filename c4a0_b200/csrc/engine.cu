@@ -1,0 +1,1161 @@
+// engine.cu — lockstep MCTS self-play on sm_100a: kernels + the C-ABI of include/c4a0_engine.h.
+//
+// What the reference does per game with a heap tree of Rc<RefCell<Node>> (rust/src/mcts.rs:332-355)
+// and a thread pool (rust/src/self_play.rs), this file does for thousands of games at once with
+// struct-of-arrays trees in HBM:
+//
+//   * A tree is a bump-allocated array of 160-byte BLOCKS.  A block belongs to one expanded node
+//     and holds the statistics of its 7 children column-wise (N[8], Qp[8], Qn[8], P[8], child[8]),
+//     i.e. exactly the fields UCT selection reads for one level (mcts.rs:359-388) as five 32-byte
+//     sectors.  Node positions are never stored: selection replays the moves on bitboards.
+//   * A game is served by 8 lanes (4 games per warp): lane c owns child c, argmax is a 3-step
+//     shuffle butterfly with the reference's last-maximum tie-break (Iterator::max_by_key).
+//   * Backup (mcts.rs:137-155) walks the path recorded by selection; the path nodes are
+//     independent read-modify-writes, so lanes update them in parallel, one f32 add per node per
+//     simulation in simulation order — the reference's accumulation order.
+//   * A move (mcts.rs:187-222) keeps the chosen child's subtree.  One CTA per moving game copies
+//     that subtree breadth-first into the other half of the game's arena (compaction), which is
+//     what bounds a game's memory to 2*(n_iterations+2) blocks regardless of game length.
+//
+// No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/c4a0_engine.h"
+#include "c4_math.cuh"
+#include "c4_rng.cuh"
+#include "c4_rules.cuh"
+
+namespace {
+
+using c4::Pos;
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(C4A0_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Data layout
+// ------------------------------------------------------------------------------------------------
+struct __align__(32) Block {
+  uint32_t N[8];      // visit_count of child c            (mcts.rs:335)
+  float Qp[8];        // q_sum_penalty of child c          (mcts.rs:336)
+  float Qn[8];        // q_sum_no_penalty of child c       (mcts.rs:337)
+  float P[8];         // initial_policy_value of child c   (mcts.rs:338)
+  uint32_t child[8];  // block index of child c's own block, 0 = child not expanded
+};
+static_assert(sizeof(Block) == 160, "block must be five 32-byte sectors");
+
+constexpr int PATH_STRIDE = 44;  // <= 42 levels below a root
+constexpr int MAXS = C4A0_MAX_SAMPLES;
+enum : uint32_t { ST_IDLE = 0, ST_WAIT_NN = 1, ST_CONTINUE = 2, ST_NEED_MOVE = 3 };
+
+struct Globals {  // one instance in device memory
+  uint32_t next_req;
+  uint32_t n_finished;
+  uint32_t n_running;
+  uint32_t n_movers;
+  uint32_t last_movers;
+  int32_t error;
+  unsigned long long skipped_root_sims;
+  unsigned long long moves;
+  unsigned long long samples;
+  unsigned long long compacted_blocks;
+};
+
+struct Dev {  // passed to kernels by value
+  uint32_t n_slots, n_iter, cap, n_req, max_inline, plane_bf16;
+  float c_expl, c_pen;
+  // per slot
+  uint64_t *root_mask, *root_value, *leaf_mask, *leaf_value;
+  uint32_t *root_N, *root_block, *half, *n_alloc, *state, *req, *n_moves, *path_len, *path;
+  float *root_Qp, *root_Qn;
+  unsigned long long *c_sims, *c_evals, *c_term, *c_depth;
+  Block* blocks;  // [n_slots][2][cap]
+  // per request
+  const uint64_t *game_id, *p0, *p1;
+  uint32_t* n_samples;
+  uint64_t *s_mask, *s_value;
+  float *s_policy, *s_qp, *s_qn;
+  // global
+  Globals* g;
+  uint32_t* movers;
+  // NN io
+  void* planes;
+  const float *logits, *qp, *qn;
+};
+
+__device__ __forceinline__ Block* arena_of(const Dev& D, uint32_t slot, uint32_t half) {
+  return D.blocks + ((size_t)slot * 2 + half) * D.cap;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 8-lane group helpers
+// ------------------------------------------------------------------------------------------------
+struct Group {
+  unsigned mask;  // the 8 lanes of this game within the warp
+  int l;          // 0..7 ; lanes 0..6 own children/columns 0..6
+};
+__device__ __forceinline__ Group make_group() {
+  Group g;
+  int lane = threadIdx.x & 31;
+  g.mask = 0xffu << (lane & 24);
+  g.l = lane & 7;
+  return g;
+}
+template <typename T>
+__device__ __forceinline__ T gshfl(const Group& g, T v, int src) {
+  return __shfl_sync(g.mask, v, src, 8);
+}
+template <typename T>
+__device__ __forceinline__ T gxor(const Group& g, T v, int m) {
+  return __shfl_xor_sync(g.mask, v, m, 8);
+}
+
+// NN input planes of `p` into row `row` (c4r.rs:378-392): 84 values, written by 8 lanes as
+// 16-byte (f32) or 8-byte (bf16) vectors.
+__device__ __forceinline__ void write_planes(const Dev& D, const Group& g, uint32_t row, Pos p) {
+  uint64_t mine = p.mask & p.value, theirs = p.mask & ~p.value;
+  if (D.plane_bf16) {
+    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(D.planes) + (size_t)row * 84);
+    for (int v = g.l; v < 21; v += 8) {
+      uint32_t w[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int i0 = v * 4 + h * 2, i1 = i0 + 1;
+        uint32_t b0 = (uint32_t)(((i0 < 42 ? mine >> i0 : theirs >> (i0 - 42))) & 1ull);
+        uint32_t b1 = (uint32_t)(((i1 < 42 ? mine >> i1 : theirs >> (i1 - 42))) & 1ull);
+        w[h] = (b0 ? 0x3f80u : 0u) | (b1 ? 0x3f800000u : 0u);  // bf16(1.0) = 0x3f80
+      }
+      dst[v] = make_uint2(w[0], w[1]);
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(D.planes) + (size_t)row * 84);
+    for (int v = g.l; v < 21; v += 8) {
+      float f[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int i = v * 4 + k;
+        f[k] = (float)(((i < 42 ? mine >> i : theirs >> (i - 42))) & 1ull);
+      }
+      dst[v] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-game working set held in registers by all 8 lanes (group-uniform values)
+// ------------------------------------------------------------------------------------------------
+struct Game {
+  uint32_t slot;
+  Pos root;
+  uint32_t rootN, root_block, n_alloc, len;
+  float rootQp, rootQn;
+  Block* arena;
+  uint32_t* path;
+  unsigned long long sims, evals, term, depth;
+};
+
+__device__ __forceinline__ void load_game(const Dev& D, uint32_t slot, Game& G) {
+  G.slot = slot;
+  G.root.mask = D.root_mask[slot];
+  G.root.value = D.root_value[slot];
+  G.rootN = D.root_N[slot];
+  G.rootQp = D.root_Qp[slot];
+  G.rootQn = D.root_Qn[slot];
+  G.root_block = D.root_block[slot];
+  G.n_alloc = D.n_alloc[slot];
+  G.len = D.path_len[slot];
+  G.arena = arena_of(D, slot, D.half[slot]);
+  G.path = D.path + (size_t)slot * PATH_STRIDE;
+  G.sims = G.evals = G.term = G.depth = 0;
+}
+__device__ __forceinline__ void store_game(const Dev& D, const Group& g, const Game& G, uint32_t state) {
+  if (g.l == 0) {
+    uint32_t s = G.slot;
+    D.root_N[s] = G.rootN;
+    D.root_Qp[s] = G.rootQp;
+    D.root_Qn[s] = G.rootQn;
+    D.root_block[s] = G.root_block;
+    D.n_alloc[s] = G.n_alloc;
+    D.path_len[s] = G.len;
+    D.state[s] = state;
+    if (G.sims) D.c_sims[s] += G.sims;
+    if (G.evals) D.c_evals[s] += G.evals;
+    if (G.term) D.c_term[s] += G.term;
+    if (G.depth) D.c_depth[s] += G.depth;
+  }
+}
+
+// mcts.rs:137-155 — add (qp, qn) at the leaf, alternate the sign towards the root.
+__device__ __forceinline__ void backup(const Group& g, Game& G, float qp, float qn) {
+  __syncwarp(g.mask);  // path[] written by lane 0 of this group
+  for (uint32_t j = g.l; j < G.len; j += 8) {
+    uint32_t e = G.path[j];
+    Block* B = G.arena + (e >> 3);
+    uint32_t c = e & 7u;
+    bool neg = ((G.len - 1 - j) & 1u) != 0;
+    B->N[c] += 1u;
+    B->Qp[c] += neg ? -qp : qp;
+    B->Qn[c] += neg ? -qn : qn;
+  }
+  bool neg = (G.len & 1u) != 0;
+  G.rootN += 1u;
+  G.rootQp += neg ? -qp : qp;
+  G.rootQn += neg ? -qn : qn;
+  __syncwarp(g.mask);  // statistics visible to the selection that follows
+}
+
+// mcts.rs:160-183 + 359-388 — walk from the root to a node without children.
+__device__ __forceinline__ Pos select_leaf(const Dev& D, const Group& g, Game& G) {
+  Pos pos = G.root;
+  uint32_t np = G.rootN, b = G.root_block, len = 0;
+  const float ninf = -c4::f32_inf();
+  while (b != 0u && len < 43u) {  // a tree is at most 42 plies deep
+    const Block* B = G.arena + b;
+    uint32_t n = B->N[g.l];
+    float qs = B->Qp[g.l];
+    float pr = B->P[g.l];
+    uint32_t ch = B->child[g.l];
+    unsigned legal = c4::legal_mask(pos.mask);
+    float lnp = c4::c4_logf((float)np);             // ln(parent visits), mcts.rs:378-379
+    float nf = (float)n + 1.0f;
+    float q = qs / nf;                              // mcts.rs:359-361
+    float ex = sqrtf(lnp / nf);
+    ex = ex * (pr + 1e-8f);                         // mcts.rs:380
+    float u = (-q) + (D.c_expl * ex);               // mcts.rs:386-388
+    bool ok = (g.l < 7) && ((legal >> g.l) & 1u);
+    float bu = ok ? u : ninf;
+    int bl = ok ? g.l : -1;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {               // max_by_key: the LAST maximum wins
+      float ou = gxor(g, bu, m);
+      int ol = gxor(g, bl, m);
+      bool take = (ol >= 0) && (bl < 0 || ou > bu || (ou == bu && ol > bl));
+      bu = take ? ou : bu;
+      bl = take ? ol : bl;
+    }
+    if (g.l == 0) G.path[len] = (b << 3) | (uint32_t)bl;
+    len++;
+    pos = c4::make_move(pos, bl);
+    np = gshfl(g, n, bl);
+    b = gshfl(g, ch, bl);
+  }
+  G.len = len;
+  return pos;
+}
+
+// Run simulations from "leaf unknown" until a leaf needs the network, the root needs to move, or
+// the per-step budget of in-kernel (terminal-leaf) simulations is spent.
+__device__ __forceinline__ uint32_t advance(const Dev& D, const Group& g, Game& G, uint32_t row) {
+  for (uint32_t it = 0;; it++) {
+    Pos leaf = select_leaf(D, g, G);
+    float tqp, tqn;
+    int t = c4::terminal_value(leaf, D.c_pen, &tqp, &tqn);
+    if (t == c4::NONE) {
+      write_planes(D, g, row, leaf);
+      if (g.l == 0) {
+        D.leaf_mask[G.slot] = leaf.mask;
+        D.leaf_value[G.slot] = leaf.value;
+      }
+      return ST_WAIT_NN;
+    }
+    // terminal leaf: mcts.rs:92-98 — no expansion, back up the objective value
+    G.depth += G.len;
+    backup(g, G, tqp, tqn);
+    G.sims++;
+    G.term++;
+    if (G.rootN >= D.n_iter) return ST_NEED_MOVE;   // self_play.rs:283
+    if (it + 1 >= D.max_inline) return ST_CONTINUE;
+  }
+}
+
+__device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
+  uint32_t i = atomicAdd(&D.g->n_movers, 1u);
+  D.movers[i] = slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_step: apply network outputs (expand + backup), then select the next leaf.  8 lanes per game.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_step(Dev D) {
+  uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (row >= D.n_slots) return;
+  Group g = make_group();
+  uint32_t slot = row;
+  uint32_t st = D.state[slot];
+  if (st == ST_IDLE) return;
+  if (st == ST_NEED_MOVE) {  // reached n_iterations inside k_move's own advance()
+    if (g.l == 0) push_mover(D, slot);
+    return;
+  }
+  Game G;
+  load_game(D, slot, G);
+  if (st == ST_WAIT_NN) {
+    // mask_policy + softmax (c4r.rs:272-286, mcts.rs:416-434) over the leaf's legal moves
+    unsigned legal = c4::legal_mask(D.leaf_mask[slot]);
+    bool ok = (g.l < 7) && ((legal >> g.l) & 1u);
+    float x = ok ? D.logits[(size_t)row * 7 + g.l] : -c4::f32_inf();
+    float mx = x;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) mx = fmaxf(mx, gxor(g, mx, m));
+    float e = ok ? c4::c4_expf(x - mx) : 0.0f;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) s = s + gshfl(g, e, i);  // left fold, as iter().sum()
+    float p = ok ? e / s : 0.0f;
+    // expand_leaf (mcts.rs:114-132): one new block holding the 7 children
+    uint32_t nb = G.n_alloc++;
+    if (nb >= D.cap) {
+      if (g.l == 0) D.g->error = C4A0_E_ENGINE;
+      return;
+    }
+    Block* B = G.arena + nb;
+    B->N[g.l] = 0u;
+    B->Qp[g.l] = 0.0f;
+    B->Qn[g.l] = 0.0f;
+    B->P[g.l] = p;
+    B->child[g.l] = 0u;
+    if (G.len == 0) {
+      G.root_block = nb;
+    } else if (g.l == 0) {
+      uint32_t e2 = G.path[G.len - 1];
+      G.arena[e2 >> 3].child[e2 & 7u] = nb;
+    }
+    G.depth += G.len;
+    backup(g, G, D.qp[row], D.qn[row]);
+    G.sims++;
+    G.evals++;
+    if (G.rootN >= D.n_iter) {  // self_play.rs:283-300: time to move (or finish)
+      store_game(D, g, G, ST_NEED_MOVE);
+      if (g.l == 0) push_mover(D, slot);
+      return;
+    }
+  }
+  uint32_t ns = advance(D, g, G, row);
+  store_game(D, g, G, ns);
+  if (ns == ST_NEED_MOVE && g.l == 0) push_mover(D, slot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_move: one CTA per game that has to move.
+// ------------------------------------------------------------------------------------------------
+constexpr int MOVE_THREADS = 128;
+
+__device__ void seat_game(const Dev& D, uint32_t slot, uint32_t r) {
+  D.root_mask[slot] = 0ull;
+  D.root_value[slot] = 0ull;
+  D.leaf_mask[slot] = 0ull;
+  D.leaf_value[slot] = 0ull;
+  D.root_N[slot] = 0u;
+  D.root_Qp[slot] = 0.0f;
+  D.root_Qn[slot] = 0.0f;
+  D.root_block[slot] = 0u;
+  D.half[slot] = 0u;
+  D.n_alloc[slot] = 1u;
+  D.req[slot] = r;
+  D.n_moves[slot] = 0u;
+  D.path_len[slot] = 0u;
+  D.state[slot] = ST_WAIT_NN;
+}
+
+__global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
+  __shared__ uint32_t sh_src, sh_next, sh_head, sh_tail, sh_mode;  // mode: 0 continue, 1 finished
+  __shared__ Pos sh_newpos;
+  __shared__ uint32_t sh_newN;
+  __shared__ float sh_newQp, sh_newQn, sh_tqp, sh_tqn;
+  const uint32_t n_movers = D.g->n_movers;
+  for (uint32_t m = blockIdx.x; m < n_movers; m += gridDim.x) {
+    const uint32_t slot = D.movers[m];
+    const uint32_t req = D.req[slot];
+    const uint32_t half = D.half[slot];
+    Block* src = arena_of(D, slot, half);
+    Block* dst = arena_of(D, slot, half ^ 1u);
+    if (threadIdx.x == 0) {
+      Pos root{D.root_mask[slot], D.root_value[slot]};
+      uint32_t rb = D.root_block[slot];
+      uint32_t nm = D.n_moves[slot];
+      // root_policy (mcts.rs:396-412): visit counts of the children, normalised
+      float pol[7], tempered[7];
+      const float uniform = 1.0f / 7.0f;
+      uint32_t cn[7] = {0, 0, 0, 0, 0, 0, 0};
+      if (rb) {
+        float cnt[7], sum = 0.0f;
+        for (int i = 0; i < 7; i++) {
+          cn[i] = src[rb].N[i];
+          cnt[i] = (float)cn[i];
+        }
+        for (int i = 0; i < 7; i++) sum = sum + cnt[i];
+        for (int i = 0; i < 7; i++) pol[i] = (sum == 0.0f) ? uniform : cnt[i] / sum;
+      } else {
+        for (int i = 0; i < 7; i++) pol[i] = uniform;
+      }
+      // self_play.rs:294-299 + mcts.rs:214-222
+      float T = c4::temperature_for_ply(c4::ply(root.mask));
+      c4::apply_temperature7(pol, T, tempered);
+      int col = c4::weighted_sample7(tempered, c4::move_seed(D.game_id[req], (int)nm));
+      unsigned legal = c4::legal_mask(root.mask);
+      if (col < 0 || !((legal >> col) & 1u) || rb == 0u || nm >= 42u) {
+        // the reference panics here (mcts.rs:190-197); park the game and report
+        D.g->error = C4A0_E_ENGINE;
+        D.state[slot] = ST_IDLE;
+        atomicSub(&D.g->n_running, 1u);
+        sh_mode = 2u;
+      } else {
+        // RecordedMove (mcts.rs:198-203) goes straight into the sample store
+        size_t si = (size_t)req * MAXS + nm;
+        D.s_mask[si] = root.mask;
+        D.s_value[si] = root.value;
+        for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = pol[i];
+        D.n_moves[slot] = nm + 1u;
+        Pos np = c4::make_move(root, col);
+        sh_newpos = np;
+        sh_newN = src[rb].N[col];
+        sh_newQp = src[rb].Qp[col];
+        sh_newQn = src[rb].Qn[col];
+        sh_src = src[rb].child[col];
+        float tqp, tqn;
+        int t = c4::terminal_value(np, D.c_pen, &tqp, &tqn);
+        sh_tqp = tqp;
+        sh_tqn = tqn;
+        sh_mode = (t != c4::NONE) ? 1u : 0u;
+        atomicAdd(&D.g->moves, 1ull);
+      }
+    }
+    __syncthreads();
+    const uint32_t mode = sh_mode;
+    if (mode == 1u) {
+      // to_result (mcts.rs:271-313): alternate the terminal value back through the moves
+      const uint32_t L = D.n_moves[slot];
+      const float tqp = sh_tqp, tqn = sh_tqn;
+      for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) {
+        bool neg = ((L - k) & 1u) != 0;
+        size_t si = (size_t)req * MAXS + k;
+        D.s_qp[si] = neg ? -tqp : tqp;
+        D.s_qn[si] = neg ? -tqn : tqn;
+      }
+      if (threadIdx.x == 0) {
+        size_t si = (size_t)req * MAXS + L;
+        D.s_mask[si] = sh_newpos.mask;
+        D.s_value[si] = sh_newpos.value;
+        for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = 1.0f / 7.0f;
+        D.s_qp[si] = tqp;
+        D.s_qn[si] = tqn;
+        D.n_samples[req] = L + 1u;
+        atomicAdd(&D.g->samples, (unsigned long long)(L + 1u));
+        atomicAdd(&D.g->n_finished, 1u);
+        // the reference keeps simulating the terminal root until N >= n
+        uint32_t nN = sh_newN;
+        if (nN < D.n_iter) atomicAdd(&D.g->skipped_root_sims, (unsigned long long)(D.n_iter - nN));
+        // seat the next waiting request in this slot (self_play.rs:55-58 queues them all up front)
+        uint32_t r = atomicAdd(&D.g->next_req, 1u);
+        if (r < D.n_req) {
+          seat_game(D, slot, r);
+        } else {
+          D.state[slot] = ST_IDLE;
+          atomicSub(&D.g->n_running, 1u);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 8 && D.state[slot] == ST_WAIT_NN) {
+        Group g = make_group();
+        write_planes(D, g, slot, Pos{0ull, 0ull});
+      }
+      __syncthreads();
+      continue;
+    }
+    if (mode == 2u) {
+      __syncthreads();
+      continue;
+    }
+    // ---- re-root: copy the kept subtree breadth-first into the other arena half -------------
+    if (threadIdx.x == 0) {
+      sh_head = 1u;
+      sh_next = sh_src ? 2u : 1u;
+    }
+    if (sh_src && threadIdx.x < 10) {
+      reinterpret_cast<uint4*>(dst + 1)[threadIdx.x] = reinterpret_cast<const uint4*>(src + sh_src)[threadIdx.x];
+    }
+    __syncthreads();
+    for (;;) {
+      const uint32_t head = sh_head, tail = sh_next;  // blocks [head, tail) form one tree level
+      __syncthreads();
+      if (head == tail) break;
+      if (tail > D.cap) {  // cannot happen for a well-formed tree; never run off the arena
+        if (threadIdx.x == 0) D.g->error = C4A0_E_ENGINE;
+        break;
+      }
+      const uint32_t nwork = (tail - head) * 8u;
+      for (uint32_t w = threadIdx.x; w < nwork; w += blockDim.x) {
+        uint32_t b = head + (w >> 3), c = w & 7u;
+        if (c == 7u) continue;
+        uint32_t s = dst[b].child[c];  // still an index into src
+        if (s) {
+          uint32_t j = atomicAdd(&sh_next, 1u);
+          const uint4* from = reinterpret_cast<const uint4*>(src + s);
+          uint4* to = reinterpret_cast<uint4*>(dst + j);
+#pragma unroll
+          for (int q = 0; q < 10; q++) to[q] = from[q];
+          dst[b].child[c] = j;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) sh_head = tail;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      D.root_mask[slot] = sh_newpos.mask;
+      D.root_value[slot] = sh_newpos.value;
+      D.root_N[slot] = sh_newN;
+      D.root_Qp[slot] = sh_newQp;
+      D.root_Qn[slot] = sh_newQn;
+      D.root_block[slot] = sh_src ? 1u : 0u;
+      D.half[slot] = half ^ 1u;
+      D.n_alloc[slot] = sh_next;
+      D.path_len[slot] = 0u;
+      atomicAdd(&D.g->compacted_blocks, (unsigned long long)(sh_next - 1u));
+    }
+    __syncthreads();
+    // mcts.rs:205: select the new leaf under the new root
+    if (threadIdx.x < 8) {
+      Group g = make_group();
+      Game G;
+      load_game(D, slot, G);
+      uint32_t ns = advance(D, g, G, slot);
+      store_game(D, g, G, ns);
+    }
+    __syncthreads();
+  }
+}
+
+// Resets the mover list after k_move consumed it (runs as the first thing of the next step).
+__global__ void k_begin_step(Dev D) {
+  D.g->last_movers = D.g->n_movers;
+  D.g->n_movers = 0u;
+}
+
+// Seat the first min(n_slots, n_req) games.
+__global__ void k_init(Dev D) {
+  uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (row >= D.n_slots) return;
+  Group g = make_group();
+  if (row < D.n_req) {
+    if (g.l == 0) {
+      seat_game(D, row, row);
+      D.c_sims[row] = D.c_evals[row] = D.c_term[row] = D.c_depth[row] = 0ull;
+    }
+    write_planes(D, g, row, Pos{0ull, 0ull});
+  } else if (g.l == 0) {
+    D.state[row] = ST_IDLE;
+    D.c_sims[row] = D.c_evals[row] = D.c_term[row] = D.c_depth[row] = 0ull;
+  }
+  if (row == 0 && g.l == 0) {
+    Globals z;
+    memset(&z, 0, sizeof(z));
+    z.next_req = D.n_req < D.n_slots ? D.n_req : D.n_slots;
+    z.n_running = z.next_req;
+    *D.g = z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic evaluators (parity tiers E0 / E1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float* qn) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= D.n_slots) return;
+  if (kind == C4A0_EVAL_UNIFORM) {
+    for (int k = 0; k < 7; k++) logits[(size_t)row * 7 + k] = 0.0f;
+    qp[row] = 0.0f;
+    qn[row] = 0.0f;
+    return;
+  }
+  uint64_t mask = D.leaf_mask[row], value = D.leaf_value[row];
+  uint32_t r = D.req[row];
+  uint64_t model = 0;
+  if (D.state[row] != ST_IDLE) model = (c4::ply(mask) % 2 == 0) ? D.p0[r] : D.p1[r];
+  uint64_t h = splitmix64(mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(value ^ model));
+  for (int k = 0; k < 7; k++) {
+    uint64_t hk = splitmix64(h + (uint64_t)k);
+    logits[(size_t)row * 7 + k] = (float)(uint32_t)(hk >> 48) * (1.0f / 8192.0f) - 4.0f;
+  }
+  uint64_t hq = splitmix64(h + 7);
+  qp[row] = ((float)(uint32_t)((hq >> 48) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * 0.75f;
+  qn[row] = ((float)(uint32_t)((hq >> 32) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * 0.75f;
+}
+
+__global__ void k_row_models(Dev D, uint64_t* out) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= D.n_slots) return;
+  uint64_t model = 0;
+  if (D.state[row] != ST_IDLE) {
+    uint32_t r = D.req[row];
+    model = (c4::ply(D.leaf_mask[row]) % 2 == 0) ? D.p0[r] : D.p1[r];  // mcts.rs:70-76
+  }
+  out[row] = model;
+}
+
+__global__ void k_sum_counters(Dev D, unsigned long long* out4) {
+  unsigned long long a = 0, b = 0, c = 0, d = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.n_slots; i += gridDim.x * blockDim.x) {
+    a += D.c_sims[i];
+    b += D.c_evals[i];
+    c += D.c_term[i];
+    d += D.c_depth[i];
+  }
+  atomicAdd(out4 + 0, a);
+  atomicAdd(out4 + 1, b);
+  atomicAdd(out4 + 2, c);
+  atomicAdd(out4 + 3, d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone batch kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_rules(const uint64_t* mask, const uint64_t* value, size_t n, float c_pen,
+                        int32_t* terminal, uint32_t* legal, int32_t* ply, float* qp, float* qn,
+                        uint64_t* cm, uint64_t* cv, float* planes, uint64_t* fm, uint64_t* fv) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Pos p{mask[i], value[i]};
+  float a, b;
+  int t = c4::terminal_value(p, c_pen, &a, &b);
+  if (terminal) terminal[i] = t;
+  unsigned lg = c4::legal_mask(p.mask);
+  if (legal) legal[i] = lg;
+  if (ply) ply[i] = c4::ply(p.mask);
+  if (qp) qp[i] = a;
+  if (qn) qn[i] = b;
+  if (cm && cv)
+    for (int c = 0; c < 7; c++) {
+      Pos ch{0ull, 0ull};
+      if ((lg >> c) & 1u) ch = c4::make_move(p, c);
+      cm[i * 7 + c] = ch.mask;
+      cv[i * 7 + c] = ch.value;
+    }
+  if (planes)
+    for (int k = 0; k < 84; k++) planes[i * 84 + k] = c4::plane_elem(p, k);
+  if (fm && fv) {
+    Pos f = c4::flip_h(p);
+    fm[i] = f.mask;
+    fv[i] = f.value;
+  }
+}
+__global__ void k_math(int op, const float* in, float* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = op == C4A0_MATH_LOGF ? c4::c4_logf(in[i]) : c4::c4_expf(in[i]);
+}
+__global__ void k_softmax(const float* logits, const uint32_t* legal, float* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x[7], o[7];
+  for (int k = 0; k < 7; k++) x[k] = ((legal[i] >> k) & 1u) ? logits[i * 7 + k] : -c4::f32_inf();
+  if (!c4::softmax7(x, o))
+    for (int k = 0; k < 7; k++) o[k] = c4::f32_nan();
+  for (int k = 0; k < 7; k++) out[i * 7 + k] = o[k];
+}
+__global__ void k_sample(const float* policy, const float* temperature, const uint64_t* seed,
+                         float* tempered, int32_t* column, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p[7], t[7];
+  for (int k = 0; k < 7; k++) p[k] = policy[i * 7 + k];
+  c4::apply_temperature7(p, temperature[i], t);
+  for (int k = 0; k < 7; k++) tempered[i * 7 + k] = t[k];
+  column[i] = c4::weighted_sample7(t, seed[i]);
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Engine object
+// ------------------------------------------------------------------------------------------------
+struct c4a0_engine {
+  c4a0_config cfg;
+  Dev D;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  bool io_bound = false, have_requests = false;
+  uint64_t steps = 0;
+  unsigned long long* scratch4 = nullptr;
+  uint64_t* row_models = nullptr;
+  Globals* h_globals = nullptr;  // pinned
+  float *b_logits = nullptr, *b_qp = nullptr, *b_qn = nullptr;  // writable aliases for eval_builtin
+};
+
+namespace {
+template <typename T>
+int dalloc(c4a0_engine* e, T** p, size_t n) {
+  size_t b = (n ? n : 1) * sizeof(T);
+  cudaError_t err = cudaMalloc((void**)p, b);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    return fail(err == cudaErrorMemoryAllocation ? C4A0_E_NOMEM : C4A0_E_CUDA,
+                "cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(err));
+  }
+  e->allocs.push_back(*p);
+  e->bytes += b;
+  return 0;
+}
+#define DA(ptr, n)                         \
+  do {                                     \
+    int _r = dalloc(e, &(ptr), (n));       \
+    if (_r) {                              \
+      c4a0_engine_destroy(e);              \
+      return _r;                           \
+    }                                      \
+  } while (0)
+
+int no_gpu_error() {
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(C4A0_E_CUDA, "no CUDA device available (%s): the engine has no CPU fallback",
+                err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+  }
+  return 0;
+}
+inline unsigned blocks_for(size_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+}  // namespace
+
+extern "C" {
+
+const char* c4a0_last_error(void) { return g_err.c_str(); }
+int c4a0_abi_version(void) { return C4A0_ABI_VERSION; }
+
+int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
+  if (!cfg || !out) return fail(C4A0_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_slots == 0 || cfg->n_mcts_iterations == 0 || cfg->max_requests == 0)
+    return fail(C4A0_E_INVALID, "n_slots, max_requests and n_mcts_iterations must be >= 1");
+  if (cfg->plane_dtype > C4A0_PLANES_BF16) return fail(C4A0_E_INVALID, "bad plane_dtype");
+  if (cfg->n_mcts_iterations > (1u << 24))
+    return fail(C4A0_E_INVALID, "n_mcts_iterations above 2^24 is not exactly representable in f32");
+  int r = no_gpu_error();
+  if (r) return r;
+  CK(cudaSetDevice(cfg->device));
+  c4a0_engine* e = new c4a0_engine();
+  e->cfg = *cfg;
+  Dev& D = e->D;
+  memset(&D, 0, sizeof(D));
+  D.n_slots = cfg->n_slots;
+  D.n_iter = cfg->n_mcts_iterations;
+  D.cap = cfg->n_mcts_iterations + 2;  // index 0 unused; at most n_iter expanded nodes per tree
+  D.n_req = 0;
+  D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : 8;
+  D.plane_bf16 = cfg->plane_dtype == C4A0_PLANES_BF16;
+  D.c_expl = cfg->c_exploration;
+  D.c_pen = cfg->c_ply_penalty;
+  size_t S = cfg->n_slots, R = cfg->max_requests;
+  DA(D.root_mask, S); DA(D.root_value, S); DA(D.leaf_mask, S); DA(D.leaf_value, S);
+  DA(D.root_N, S); DA(D.root_block, S); DA(D.half, S); DA(D.n_alloc, S); DA(D.state, S);
+  DA(D.req, S); DA(D.n_moves, S); DA(D.path_len, S); DA(D.path, S * PATH_STRIDE);
+  DA(D.root_Qp, S); DA(D.root_Qn, S);
+  DA(D.c_sims, S); DA(D.c_evals, S); DA(D.c_term, S); DA(D.c_depth, S);
+  DA(D.blocks, S * 2 * (size_t)D.cap);
+  uint64_t *gid, *p0, *p1;
+  DA(gid, R); DA(p0, R); DA(p1, R);
+  D.game_id = gid; D.p0 = p0; D.p1 = p1;
+  DA(D.n_samples, R); DA(D.s_mask, R * MAXS); DA(D.s_value, R * MAXS);
+  DA(D.s_policy, R * MAXS * 7); DA(D.s_qp, R * MAXS); DA(D.s_qn, R * MAXS);
+  DA(D.g, 1); DA(D.movers, S);
+  DA(e->scratch4, 4); DA(e->row_models, S);
+  cudaError_t err = cudaMemset(D.state, 0, S * sizeof(uint32_t));
+  if (err == cudaSuccess) err = cudaMemset(D.g, 0, sizeof(Globals));
+  if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_globals, sizeof(Globals));
+  if (err != cudaSuccess) {
+    c4a0_engine_destroy(e);
+    return fail(C4A0_E_CUDA, "engine init failed: %s", cudaGetErrorString(err));
+  }
+  *out = e;
+  return 0;
+}
+
+void c4a0_engine_destroy(c4a0_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->h_globals) cudaFreeHost(e->h_globals);
+  delete e;
+}
+
+size_t c4a0_engine_device_bytes(const c4a0_engine* e) { return e ? e->bytes : 0; }
+
+int c4a0_engine_bind_io(c4a0_engine* e, void* planes, const float* logits, const float* qp,
+                        const float* qn) {
+  if (!e || !planes || !logits || !qp || !qn) return fail(C4A0_E_INVALID, "null argument");
+  if (((uintptr_t)planes & 15u) != 0) return fail(C4A0_E_INVALID, "planes_dev must be 16-byte aligned");
+  e->D.planes = planes;
+  e->D.logits = logits;
+  e->D.qp = qp;
+  e->D.qn = qn;
+  e->b_logits = const_cast<float*>(logits);
+  e->b_qp = const_cast<float*>(qp);
+  e->b_qn = const_cast<float*>(qn);
+  e->io_bound = true;
+  return 0;
+}
+
+int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint64_t* p0,
+                             const uint64_t* p1, uint32_t n, void* stream) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if (!e->io_bound) return fail(C4A0_E_INVALID, "bind_io() must precede set_requests()");
+  if (n > e->cfg.max_requests) return fail(C4A0_E_INVALID, "%u requests exceed max_requests=%u", n, e->cfg.max_requests);
+  if (n && (!game_id || !p0 || !p1)) return fail(C4A0_E_INVALID, "null request arrays");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->cfg.device));
+  Dev& D = e->D;
+  if (n) {
+    CK(cudaMemcpyAsync((void*)D.game_id, game_id, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync((void*)D.p0, p0, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync((void*)D.p1, p1, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(D.n_samples, 0, n * sizeof(uint32_t), s));
+  }
+  D.n_req = n;
+  k_init<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));  // the host arrays may be freed by the caller after return
+  e->have_requests = true;
+  e->steps = 0;
+  return 0;
+}
+
+int c4a0_engine_step(c4a0_engine* e, void* stream) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if (!e->have_requests) return fail(C4A0_E_INVALID, "set_requests() must precede step()");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dev& D = e->D;
+  k_begin_step<<<1, 1, 0, s>>>(D);
+  k_step<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  unsigned grid = D.n_slots < 148u * 8u ? D.n_slots : 148u * 8u;
+  k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
+  CK(cudaGetLastError());
+  e->steps++;
+  return 0;
+}
+
+int c4a0_engine_eval_builtin(c4a0_engine* e, int kind, void* stream) {
+  if (!e || !e->io_bound) return fail(C4A0_E_INVALID, "engine not bound");
+  if (kind != C4A0_EVAL_UNIFORM && kind != C4A0_EVAL_HASH) return fail(C4A0_E_INVALID, "bad evaluator kind");
+  k_eval_builtin<<<blocks_for(e->D.n_slots, 256), 256, 0, (cudaStream_t)stream>>>(e->D, kind, e->b_logits, e->b_qp, e->b_qn);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int c4a0_engine_poll(c4a0_engine* e, c4a0_progress* out, void* stream) {
+  if (!e || !out) return fail(C4A0_E_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(e->h_globals, e->D.g, sizeof(Globals), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const Globals& g = *e->h_globals;
+  out->n_requests = e->D.n_req;
+  out->n_started = g.next_req < e->D.n_req ? g.next_req : e->D.n_req;
+  out->n_finished = g.n_finished;
+  out->n_running = g.n_running;
+  out->n_movers = g.n_movers;
+  out->error = g.error;
+  if (g.error) return fail(C4A0_E_ENGINE, "a game reached a state where the reference panics (illegal sampled move or arena overflow)");
+  return 0;
+}
+
+int c4a0_engine_stats(c4a0_engine* e, c4a0_stats* out, void* stream) {
+  if (!e || !out) return fail(C4A0_E_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(e->scratch4, 0, 4 * sizeof(unsigned long long), s));
+  k_sum_counters<<<64, 256, 0, s>>>(e->D, e->scratch4);
+  CK(cudaGetLastError());
+  unsigned long long h4[4];
+  CK(cudaMemcpyAsync(h4, e->scratch4, sizeof(h4), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(e->h_globals, e->D.g, sizeof(Globals), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const Globals& g = *e->h_globals;
+  out->sims = h4[0];
+  out->nn_evals = h4[1];
+  out->terminal_leaf_sims = h4[2];
+  out->select_depth_sum = h4[3];
+  out->expansions = h4[1];
+  out->skipped_root_sims = g.skipped_root_sims;
+  out->moves = g.moves;
+  out->samples = g.samples;
+  out->steps = e->steps;
+  out->compacted_blocks = g.compacted_blocks;
+  return 0;
+}
+
+int c4a0_engine_fetch_rows(c4a0_engine* e, uint32_t* state, uint64_t* leaf_mask, uint64_t* leaf_value,
+                           uint64_t* model_id, void* stream) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t S = e->D.n_slots;
+  if (model_id) {
+    k_row_models<<<blocks_for(S, 256), 256, 0, s>>>(e->D, e->row_models);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(model_id, e->row_models, S * 8, cudaMemcpyDeviceToHost, s));
+  }
+  if (state) CK(cudaMemcpyAsync(state, e->D.state, S * 4, cudaMemcpyDeviceToHost, s));
+  if (leaf_mask) CK(cudaMemcpyAsync(leaf_mask, e->D.leaf_mask, S * 8, cudaMemcpyDeviceToHost, s));
+  if (leaf_value) CK(cudaMemcpyAsync(leaf_value, e->D.leaf_value, S * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int c4a0_engine_fetch_results(c4a0_engine* e, uint32_t first, uint32_t n, uint32_t* n_samples,
+                              uint64_t* mask, uint64_t* value, float* policy, float* qp, float* qn,
+                              void* stream) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if ((uint64_t)first + n > e->D.n_req) return fail(C4A0_E_INVALID, "result range out of bounds");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dev& D = e->D;
+  size_t o = (size_t)first * MAXS, c = (size_t)n * MAXS;
+  if (n_samples) CK(cudaMemcpyAsync(n_samples, D.n_samples + first, n * 4, cudaMemcpyDeviceToHost, s));
+  if (mask) CK(cudaMemcpyAsync(mask, D.s_mask + o, c * 8, cudaMemcpyDeviceToHost, s));
+  if (value) CK(cudaMemcpyAsync(value, D.s_value + o, c * 8, cudaMemcpyDeviceToHost, s));
+  if (policy) CK(cudaMemcpyAsync(policy, D.s_policy + o * 7, c * 7 * 4, cudaMemcpyDeviceToHost, s));
+  if (qp) CK(cudaMemcpyAsync(qp, D.s_qp + o, c * 4, cudaMemcpyDeviceToHost, s));
+  if (qn) CK(cudaMemcpyAsync(qn, D.s_qn + o, c * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int c4a0_engine_results_dev(c4a0_engine* e, uint32_t** n_samples, uint64_t** mask, uint64_t** value,
+                            float** policy, float** qp, float** qn) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if (n_samples) *n_samples = e->D.n_samples;
+  if (mask) *mask = e->D.s_mask;
+  if (value) *value = e->D.s_value;
+  if (policy) *policy = e->D.s_policy;
+  if (qp) *qp = e->D.s_qp;
+  if (qn) *qn = e->D.s_qn;
+  return 0;
+}
+
+int c4a0_engine_slot_info(c4a0_engine* e, uint32_t slot, c4a0_slot_info* out, void* stream) {
+  if (!e || !out) return fail(C4A0_E_INVALID, "null argument");
+  if (slot >= e->D.n_slots) return fail(C4A0_E_INVALID, "slot out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dev& D = e->D;
+  uint32_t na;
+  CK(cudaMemcpyAsync(&out->state, D.state + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->request, D.req + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->n_moves, D.n_moves + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->root_visits, D.root_N + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->root_mask, D.root_mask + slot, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->root_value, D.root_value + slot, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->root_q_sum_penalty, D.root_Qp + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->root_q_sum_no_penalty, D.root_Qn + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&na, D.n_alloc + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  out->n_blocks = na ? na - 1 : 0;
+  return 0;
+}
+
+namespace {
+struct Dumper {
+  const Block* blocks;
+  uint32_t* buf;
+  size_t cap, w;
+  void put(uint32_t v) {
+    if (w < cap) buf[w] = v;
+    w++;
+  }
+  void children(uint32_t b, Pos pos) {
+    unsigned legal = c4::legal_mask(pos.mask);
+    const Block& B = blocks[b];
+    for (int c = 0; c < 7; c++) {
+      if (!((legal >> c) & 1u)) {
+        for (int k = 0; k < 5; k++) put(0);
+        continue;
+      }
+      put(B.child[c] ? 2u : 1u);
+      put(B.N[c]);
+      put(c4::f32_bits(B.Qp[c]));
+      put(c4::f32_bits(B.Qn[c]));
+      put(c4::f32_bits(B.P[c]));
+      if (B.child[c]) children(B.child[c], c4::make_move(pos, c));
+    }
+  }
+};
+}  // namespace
+
+int c4a0_engine_dump_tree(c4a0_engine* e, uint32_t slot, uint32_t* buf, size_t cap, size_t* needed,
+                          void* stream) {
+  if (!e || !needed) return fail(C4A0_E_INVALID, "null argument");
+  c4a0_slot_info info;
+  int r = c4a0_engine_slot_info(e, slot, &info, stream);
+  if (r) return r;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dev& D = e->D;
+  uint32_t half, rb;
+  CK(cudaMemcpyAsync(&half, D.half + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&rb, D.root_block + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  std::vector<Block> host(info.n_blocks + 1);
+  const Block* src = D.blocks + ((size_t)slot * 2 + half) * D.cap;
+  CK(cudaMemcpyAsync(host.data(), src, host.size() * sizeof(Block), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  Dumper d{host.data(), buf, buf ? cap : 0, 0};
+  d.put(rb ? 2u : 1u);
+  d.put(info.root_visits);
+  d.put(c4::f32_bits(info.root_q_sum_penalty));
+  d.put(c4::f32_bits(info.root_q_sum_no_penalty));
+  if (rb) d.children(rb, Pos{info.root_mask, info.root_value});
+  *needed = d.w;
+  return 0;
+}
+
+// ---- stand-alone batch entry points --------------------------------------------------------------
+#define BATCH_PROLOGUE()            \
+  do {                              \
+    int _r = no_gpu_error();        \
+    if (_r) return _r;              \
+    CK(cudaSetDevice(device));      \
+  } while (0)
+#define UP(dbuf, hptr, count)                                                              \
+  do {                                                                                     \
+    CK((dbuf).alloc(count));                                                               \
+    CK(cudaMemcpy((dbuf).p, hptr, (count) * sizeof(*(dbuf).p), cudaMemcpyHostToDevice));   \
+  } while (0)
+#define DOWN(hptr, dbuf, count) \
+  CK(cudaMemcpy(hptr, (dbuf).p, (count) * sizeof(*(dbuf).p), cudaMemcpyDeviceToHost))
+
+int c4a0_rules_batch(int device, const uint64_t* mask, const uint64_t* value, size_t n, float c_pen,
+                     int32_t* terminal, uint32_t* legal, int32_t* ply, float* qp, float* qn,
+                     uint64_t* cm, uint64_t* cv, float* planes, uint64_t* fm, uint64_t* fv) {
+  if (!mask || !value) return fail(C4A0_E_INVALID, "null positions");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<uint64_t> dm, dv, dcm, dcv, dfm, dfv;
+  DevBuf<int32_t> dt, dp;
+  DevBuf<uint32_t> dl;
+  DevBuf<float> dqp, dqn, dpl;
+  UP(dm, mask, n);
+  UP(dv, value, n);
+  if (terminal) CK(dt.alloc(n));
+  if (legal) CK(dl.alloc(n));
+  if (ply) CK(dp.alloc(n));
+  if (qp) CK(dqp.alloc(n));
+  if (qn) CK(dqn.alloc(n));
+  if (cm && cv) { CK(dcm.alloc(n * 7)); CK(dcv.alloc(n * 7)); }
+  if (planes) CK(dpl.alloc(n * 84));
+  if (fm && fv) { CK(dfm.alloc(n)); CK(dfv.alloc(n)); }
+  k_rules<<<blocks_for(n, 256), 256>>>(dm.p, dv.p, n, c_pen, dt.p, dl.p, dp.p, dqp.p, dqn.p, dcm.p, dcv.p,
+                                       dpl.p, dfm.p, dfv.p);
+  CK(cudaGetLastError());
+  if (terminal) DOWN(terminal, dt, n);
+  if (legal) DOWN(legal, dl, n);
+  if (ply) DOWN(ply, dp, n);
+  if (qp) DOWN(qp, dqp, n);
+  if (qn) DOWN(qn, dqn, n);
+  if (cm && cv) { DOWN(cm, dcm, n * 7); DOWN(cv, dcv, n * 7); }
+  if (planes) DOWN(planes, dpl, n * 84);
+  if (fm && fv) { DOWN(fm, dfm, n); DOWN(fv, dfv, n); }
+  return 0;
+}
+
+int c4a0_math_batch(int device, int op, const float* in, float* out, size_t n) {
+  if (!in || !out) return fail(C4A0_E_INVALID, "null argument");
+  if (op != C4A0_MATH_LOGF && op != C4A0_MATH_EXPF) return fail(C4A0_E_INVALID, "bad op");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<float> di, dout;
+  UP(di, in, n);
+  CK(dout.alloc(n));
+  k_math<<<blocks_for(n, 256), 256>>>(op, di.p, dout.p, n);
+  CK(cudaGetLastError());
+  DOWN(out, dout, n);
+  return 0;
+}
+
+int c4a0_softmax_batch(int device, const float* logits, const uint32_t* legal, float* out, size_t n) {
+  if (!logits || !legal || !out) return fail(C4A0_E_INVALID, "null argument");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<float> dl, dout;
+  DevBuf<uint32_t> dg;
+  UP(dl, logits, n * 7);
+  UP(dg, legal, n);
+  CK(dout.alloc(n * 7));
+  k_softmax<<<blocks_for(n, 128), 128>>>(dl.p, dg.p, dout.p, n);
+  CK(cudaGetLastError());
+  DOWN(out, dout, n * 7);
+  return 0;
+}
+
+int c4a0_sample_batch(int device, const float* policy, const float* temperature, const uint64_t* seed,
+                      float* tempered, int32_t* column, size_t n) {
+  if (!policy || !temperature || !seed || !tempered || !column) return fail(C4A0_E_INVALID, "null argument");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<float> dp, dt, dtemp;
+  DevBuf<uint64_t> ds;
+  DevBuf<int32_t> dc;
+  UP(dp, policy, n * 7);
+  UP(dt, temperature, n);
+  UP(ds, seed, n);
+  CK(dtemp.alloc(n * 7));
+  CK(dc.alloc(n));
+  k_sample<<<blocks_for(n, 128), 128>>>(dp.p, dt.p, ds.p, dtemp.p, dc.p, n);
+  CK(cudaGetLastError());
+  DOWN(tempered, dtemp, n * 7);
+  DOWN(column, dc, n);
+  return 0;
+}
+
+// ---- host builds of the shared math (CPU test-suite) ----------------------------------------------
+void c4a0_host_logf(const float* in, float* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = c4::c4_logf(in[i]);
+}
+void c4a0_host_expf(const float* in, float* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = c4::c4_expf(in[i]);
+}
+int c4a0_host_sample(const float* policy, float temperature, uint64_t seed, float* tempered) {
+  float t[7];
+  c4::apply_temperature7(policy, temperature, t);
+  if (tempered)
+    for (int i = 0; i < 7; i++) tempered[i] = t[i];
+  return c4::weighted_sample7(t, seed);
+}
+int c4a0_host_terminal_state(uint64_t mask, uint64_t value) { return c4::terminal_state(Pos{mask, value}); }
+void c4a0_host_make_move(uint64_t mask, uint64_t value, int col, uint64_t* om, uint64_t* ov) {
+  Pos r = c4::make_move(Pos{mask, value}, col);
+  *om = r.mask;
+  *ov = r.value;
+}
+
+}  // extern "C"

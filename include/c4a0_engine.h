@@ -1,0 +1,189 @@
+/*
+ * c4a0_engine.h — C-ABI of the B200-native self-play engine (libc4a0_engine.so).
+ *
+ * This is the drop-in boundary for the reference's batched MCTS self-play path.  In the reference
+ * the Python-facing function `c4a0_rust.play_games` (rust/src/pybridge.rs:20-53) calls
+ * `self_play::self_play` (rust/src/self_play.rs:39-129), which spawns one NN thread and ncpu-1 MCTS
+ * threads that push per-game pointer trees (rust/src/mcts.rs:27-32, 332-355) through channels.  Here
+ * the same work is a handle to a set of games resident in HBM that advance in lockstep: one call
+ * to c4a0_engine_step() performs, for every live game, what one trip through
+ * `MctsThread::loop_once` (self_play.rs:268-323) + `MctsGame::on_received_policy` (mcts.rs:83-108)
+ * does for one game.  The neural network stays outside (PyTorch): the engine writes the leaf
+ * positions as NN input planes (c4r.rs:378-392, pybridge.rs:202-221) into a caller-owned device
+ * buffer and reads the network's logits / q values from caller-owned device buffers, so both sides
+ * share memory with no copies.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative C4A0_E_* code
+ * and records a message retrievable with c4a0_last_error() (thread-local).  Nothing aborts the
+ * process (the reference panics: pybridge.rs:30, 182-188).  One host thread per handle; one handle
+ * per GPU (several handles per GPU are allowed and are how two half-batches ping-pong).  Pointers
+ * named *_dev are device pointers on the engine's GPU; all others are host pointers.  `stream` is a
+ * cudaStream_t passed as void* (0 = legacy default stream); step()/eval_builtin() only enqueue
+ * kernels and are safe to capture into a CUDA graph.
+ */
+#ifndef C4A0_ENGINE_H
+#define C4A0_ENGINE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C4A0_ABI_VERSION 1
+#define C4A0_N_ROWS 6               /* lib.rs:29 */
+#define C4A0_N_COLS 7               /* lib.rs:28 */
+#define C4A0_BUF_N_CHANNELS 2       /* lib.rs:30 */
+#define C4A0_PLANE_LEN 84           /* c4r.rs:50-52: 2*6*7 */
+#define C4A0_MAX_SAMPLES 43         /* 42 moves + the terminal position (mcts.rs:271-313) */
+
+enum {
+  C4A0_OK = 0,
+  C4A0_E_INVALID = -1,  /* bad argument / call order */
+  C4A0_E_CUDA = -2,     /* a CUDA runtime call failed; see c4a0_last_error() */
+  C4A0_E_NOMEM = -3,
+  C4A0_E_ENGINE = -4    /* device-side invariant violated (reference would panic) */
+};
+
+enum { C4A0_PLANES_F32 = 0, C4A0_PLANES_BF16 = 1 };
+
+/* Synthetic evaluators that stand in for the network in parity tests and kernel benchmarks
+ * (the reference's tests do the same: mcts.rs:469-485, self_play.rs:386-403). */
+enum { C4A0_EVAL_UNIFORM = 0, C4A0_EVAL_HASH = 1 };
+
+/* Row (= slot) states as reported by c4a0_engine_fetch_rows(). */
+enum { C4A0_ROW_IDLE = 0, C4A0_ROW_WAIT_NN = 1, C4A0_ROW_CONTINUE = 2, C4A0_ROW_NEED_MOVE = 3 };
+
+typedef struct c4a0_engine c4a0_engine;
+
+/* Arguments of self_play() (self_play.rs:39-46) plus the lockstep width. */
+typedef struct {
+  uint32_t n_slots;            /* games resident at once == rows of the NN batch (<= max_nn_batch_size) */
+  uint32_t max_requests;       /* capacity of set_requests() */
+  uint32_t n_mcts_iterations;  /* >= 1 */
+  float c_exploration;
+  float c_ply_penalty;
+  uint32_t plane_dtype;        /* C4A0_PLANES_F32 | C4A0_PLANES_BF16 */
+  uint32_t max_inline_sims;    /* terminal-leaf simulations a game may run inside one step (0 = 8) */
+  int32_t device;              /* CUDA device ordinal */
+} c4a0_config;
+
+typedef struct {
+  uint32_t n_requests;   /* games submitted */
+  uint32_t n_started;    /* games that have been given a slot */
+  uint32_t n_finished;   /* games whose samples are complete */
+  uint32_t n_running;    /* slots holding a live game */
+  uint32_t n_movers;     /* games that moved in the last step */
+  int32_t error;         /* 0, or C4A0_E_ENGINE if a game hit a state where the reference panics */
+} c4a0_progress;
+
+/* Counters in the reference's own units (self_play.rs:352-381 shows the same three live). */
+typedef struct {
+  uint64_t sims;               /* on_received_policy equivalents actually executed */
+  uint64_t nn_evals;           /* leaf positions handed to the network */
+  uint64_t terminal_leaf_sims; /* sims whose leaf was terminal (run inside the kernel, no NN row) */
+  uint64_t skipped_root_sims;  /* sims the reference would still spend on a terminal root */
+  uint64_t moves;
+  uint64_t samples;
+  uint64_t select_depth_sum;   /* sum over sims of the depth of the selected leaf */
+  uint64_t expansions;         /* nodes expanded (== non-terminal leaves applied) */
+  uint64_t steps;              /* c4a0_engine_step() calls since set_requests() */
+  uint64_t compacted_blocks;   /* tree blocks copied by re-rooting (mcts.rs:187-206 keeps the subtree) */
+} c4a0_stats;
+
+const char *c4a0_last_error(void);
+int c4a0_abi_version(void);
+
+/* ---- engine lifetime ------------------------------------------------------------------- */
+int c4a0_engine_create(const c4a0_config *cfg, c4a0_engine **out);
+void c4a0_engine_destroy(c4a0_engine *e);
+/* bytes of device memory the engine holds (arenas + state + sample store) */
+size_t c4a0_engine_device_bytes(const c4a0_engine *e);
+
+/* NN I/O buffers, caller-owned device memory (DLPack / torch tensors):
+ *   planes_dev : [n_slots][2][6][7] f32 or bf16 (cfg.plane_dtype)      <- pybridge.rs:202-221
+ *   logits_dev : [n_slots][7] f32, q_penalty_dev / q_no_penalty_dev : [n_slots] f32
+ *                                                                      <- pybridge.rs:175-196 */
+int c4a0_engine_bind_io(c4a0_engine *e, void *planes_dev, const float *logits_dev,
+                        const float *q_penalty_dev, const float *q_no_penalty_dev);
+
+/* The games to play: GameMetadata{game_id, player0_id, player1_id} (types.rs:36-48) as three host
+ * arrays.  Resets all state; games [0, min(n, n_slots)) are seated and their root planes written
+ * (self_play.rs:55-58).  Requires bind_io(). */
+int c4a0_engine_set_requests(c4a0_engine *e, const uint64_t *game_id, const uint64_t *player0_id,
+                             const uint64_t *player1_id, uint32_t n, void *stream);
+
+/* One lockstep tick: consume the network outputs for every row in WAIT_NN (mask+softmax, expand,
+ * negamax backup: mcts.rs:83-155), play the move of every game whose root reached
+ * n_mcts_iterations (temperature + seeded sample + re-root: self_play.rs:283-300,
+ * mcts.rs:187-222), emit finished games (mcts.rs:271-313) and seat waiting requests in their slots,
+ * then select every game's next leaf (mcts.rs:160-183) and write its planes. */
+int c4a0_engine_step(c4a0_engine *e, void *stream);
+
+/* Fill logits/q buffers for the current leaves with a synthetic evaluator (parity tiers E0/E1). */
+int c4a0_engine_eval_builtin(c4a0_engine *e, int kind, void *stream);
+
+/* Synchronises `stream` and reports progress. */
+int c4a0_engine_poll(c4a0_engine *e, c4a0_progress *out, void *stream);
+int c4a0_engine_stats(c4a0_engine *e, c4a0_stats *out, void *stream);
+
+/* Per-row view for the numpy-callback compatibility path and for tests: state, current leaf
+ * position and the model that has to evaluate it (mcts.rs:70-76).  Any pointer may be NULL. */
+int c4a0_engine_fetch_rows(c4a0_engine *e, uint32_t *state, uint64_t *leaf_mask,
+                           uint64_t *leaf_value, uint64_t *model_id, void *stream);
+
+/* Finished games [first, first+n) in request order: n_samples[i] (0 = not finished) and
+ * [n][43] sample fields (types.rs:104-110).  Any output pointer may be NULL. */
+int c4a0_engine_fetch_results(c4a0_engine *e, uint32_t first, uint32_t n, uint32_t *n_samples,
+                              uint64_t *mask, uint64_t *value, float *policy, float *q_penalty,
+                              float *q_no_penalty, void *stream);
+/* Device pointers of the same store ([max_requests][43]...), for zero-copy export to the trainer. */
+int c4a0_engine_results_dev(c4a0_engine *e, uint32_t **n_samples_dev, uint64_t **mask_dev,
+                            uint64_t **value_dev, float **policy_dev, float **q_penalty_dev,
+                            float **q_no_penalty_dev);
+
+/* ---- introspection used by the parity tests -------------------------------------------- */
+typedef struct {
+  uint32_t state, request, n_moves, root_visits;
+  uint64_t root_mask, root_value;
+  float root_q_sum_penalty, root_q_sum_no_penalty;
+  uint32_t n_blocks; /* expanded nodes currently allocated in the live arena half */
+} c4a0_slot_info;
+int c4a0_engine_slot_info(c4a0_engine *e, uint32_t slot, c4a0_slot_info *out, void *stream);
+/* Canonical pre-order dump of a slot's tree: 4 words {root kind, N, Qp bits, Qn bits}, then for
+ * every expanded node 7 child records of 5 words {kind (0 illegal, 1 leaf, 2 expanded), N, Qp bits,
+ * Qn bits, prior bits}, each expanded child followed by its own records.  *needed = words of the
+ * full dump; at most `cap` are written. */
+int c4a0_engine_dump_tree(c4a0_engine *e, uint32_t slot, uint32_t *buf, size_t cap, size_t *needed,
+                          void *stream);
+
+/* ---- stand-alone batch kernels (rules / math / sampling), host buffers in and out --------- */
+/* For n positions: terminal state (c4r.rs:228-238), legal-move bitmask (c4r.rs:266-269), ply,
+ * terminal values (c4r.rs:253-263), the 7 successor positions (c4r.rs:58-72; zeros when illegal),
+ * the NN planes (c4r.rs:378-392) and the mirrored position (c4r.rs:289-299).  NULL outputs skipped. */
+int c4a0_rules_batch(int device, const uint64_t *mask, const uint64_t *value, size_t n,
+                     float c_ply_penalty, int32_t *terminal, uint32_t *legal, int32_t *ply,
+                     float *q_penalty, float *q_no_penalty, uint64_t *child_mask,
+                     uint64_t *child_value, float *planes, uint64_t *flip_mask,
+                     uint64_t *flip_value);
+enum { C4A0_MATH_LOGF = 0, C4A0_MATH_EXPF = 1 };
+int c4a0_math_batch(int device, int op, const float *in, float *out, size_t n);
+/* softmax over legal moves (c4r.rs:272-286 + mcts.rs:416-434): logits [n][7], legal bitmask [n] */
+int c4a0_softmax_batch(int device, const float *logits, const uint32_t *legal, float *out, size_t n);
+/* apply_temperature (mcts.rs:439-454) then the seeded weighted draw (mcts.rs:214-222):
+ * policy [n][7], temperature [n], seed [n] -> tempered [n][7], column [n] (-1 = reference panics) */
+int c4a0_sample_batch(int device, const float *policy, const float *temperature,
+                      const uint64_t *seed, float *tempered, int32_t *column, size_t n);
+
+/* The same math compiled for the host (no GPU needed); used to pin the restated logf/expf and the
+ * sampler against libm / the oracle in the CPU test-suite. */
+void c4a0_host_logf(const float *in, float *out, size_t n);
+void c4a0_host_expf(const float *in, float *out, size_t n);
+int c4a0_host_sample(const float *policy, float temperature, uint64_t seed, float *tempered);
+int c4a0_host_terminal_state(uint64_t mask, uint64_t value);
+void c4a0_host_make_move(uint64_t mask, uint64_t value, int col, uint64_t *out_mask,
+                         uint64_t *out_value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

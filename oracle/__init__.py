@@ -152,6 +152,9 @@ def lib() -> C.CDLL:
     L.c4o_self_play_threaded.restype = C.c_int
     L.c4o_player0_score.argtypes = [C.POINTER(Sample), C.c_int]
     L.c4o_player0_score.restype = C.c_float
+    for ev in (L.c4o_eval_uniform, L.c4o_eval_hash):
+        ev.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Pos), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        ev.restype = None
     L.c4o_logf_array.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.c4o_expf_array.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = L
@@ -310,6 +313,15 @@ class Game:
         out = np.zeros(need, dtype=np.uint32)
         lib().c4o_game_dump_tree(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), need)
         return out
+
+
+def builtin_eval(name: str, pos: Pos, model_id: int = 0):
+    """One position through the 'uniform' (E0) or 'hash' (E1) synthetic evaluator."""
+    fn = lib().c4o_eval_uniform if name == "uniform" else lib().c4o_eval_hash
+    pol = (C.c_float * 7)()
+    qp, qn = C.c_float(), C.c_float()
+    fn(None, model_id, 1, C.byref(pos), pol, C.byref(qp), C.byref(qn))
+    return list(pol), qp.value, qn.value
 
 
 def run_mcts(pos: Pos, n_iterations: int, c_exploration: float = 4.0, c_ply_penalty: float = 0.01):
