@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — self-play positions/s (and MCTS sims/s) of the B200 engine, next to the reference's
+CPU self-play architecture timed on the same box.
+
+A *step* is one whole self-play job through the public API: `c4a0_rust.play_games(reqs, ...)` with
+HOST request objects in and HOST samples out (BASELINE.json configs[1]: 16,384 lockstep games x 600
+MCTS sims/move, default c4a0 ResNet with random init, per GPU).  From the same K steps:
+  value        positions/s over the device-timed search region (CUDA events, inputs resident in HBM)
+  e2e.value    positions/s over the wall clock of the API calls (H2D of the requests, engine set-up,
+               CUDA-graph capture, search, D2H of the samples)
+  roofline     the tree kernel `k_step` (apply + select): algorithmic bytes per launch / its average
+               device time, sampled with CUDA events on ticks inside the timed region
+  cpu_baseline the oracle's threaded restatement of rust/src/self_play.rs on the host cores
+               (rank 0, N=1 only), network evaluated through the numpy callback on cuda:0 as the
+               reference does
+
+`--impl reference` times that CPU implementation alone (the Rust crate cannot be built in this
+image: no cargo/rustc).
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "self-play positions/sec"
+UNIT = "positions/s"
+C_EXPLORATION, C_PLY_PENALTY = 6.6, 0.01  # src/c4a0/main.py:42-43
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--games", type=int, default=16384, help="lockstep games per GPU")
+    ap.add_argument("--sims", type=int, default=600, help="MCTS iterations per move")
+    ap.add_argument("--width", type=int, default=32, help="conv_filter_size of the ResNet")
+    ap.add_argument("--nn-dtype", choices=["bf16", "f32"], default="bf16")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-kernels-every", type=int, default=53)
+    return ap.parse_args()
+
+
+def make_model(width: int, dtype: torch.dtype, device):
+    from c4a0_b200.nn import ConnectFourNet, ModelConfig
+
+    torch.manual_seed(1337)  # tests/c4a0_tests/conftest.py:8 of the reference
+    cfg = ModelConfig(n_residual_blocks=1, conv_filter_size=width, n_policy_layers=4, n_value_layers=2)
+    return ConnectFourNet(cfg).to(device=device, dtype=dtype).eval()
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: oracle/selfplay_threads.cpp (the reference's thread/channel architecture)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_games: int, n_iter: int, width: int, nn_device: str):
+    """Returns dict(positions, sims, seconds, threads, nn_batches)."""
+    import oracle
+
+    model = make_model(width, torch.float32, nn_device)
+    L = oracle.lib()
+    bits = np.arange(42, dtype=np.uint64)[None, :]
+
+    def cb(_user, model_id, n, pos, policy, qp, qn):  # rust/src/pybridge.rs:170-198
+        arr = np.ctypeslib.as_array(C.cast(pos, C.POINTER(C.c_uint64)), shape=(n, 2))
+        mask, value = arr[:, 0], arr[:, 1]
+        mine = ((mask & value)[:, None] >> bits) & np.uint64(1)
+        theirs = ((mask & ~value)[:, None] >> bits) & np.uint64(1)
+        planes = np.concatenate([mine, theirs], axis=1).astype(np.float32).reshape(n, 2, 6, 7)
+        pol, a, b = model.forward_numpy(planes)
+        C.memmove(policy, pol.ctypes.data, 28 * n)
+        C.memmove(qp, a.ctypes.data, 4 * n)
+        C.memmove(qn, b.ctypes.data, 4 * n)
+
+    fn = oracle.EVAL_FN(cb)
+    md = (oracle.Metadata * n_games)(*[oracle.Metadata(i, 0, 0) for i in range(n_games)])
+    out = (oracle.Sample * (n_games * oracle.MAX_SAMPLES))()
+    out_n = (C.c_int * n_games)()
+    st = oracle.Stats()
+    nb = C.c_uint64(0)
+    threads = max(1, (os.cpu_count() or 2) - 1)  # self_play.rs:78
+    t0 = time.perf_counter()
+    rc = L.c4o_self_play_threaded(
+        md, n_games, 2000, n_iter, C_EXPLORATION, C_PLY_PENALTY, C.cast(fn, C.c_void_p), None, threads, out, out_n,
+        C.byref(st), C.byref(nb),
+    )
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        raise RuntimeError(f"CPU reference self-play failed rc={rc}")
+    return dict(positions=int(st.samples), sims=int(st.sims), seconds=dt, threads=threads + 1, nn_batches=int(nb.value))
+
+
+def cpu_baseline(args, budget_s: float) -> dict:
+    nn_device = "cuda:0" if torch.cuda.is_available() else "cpu"
+    probe_games = 16
+    probe = cpu_reference_run(probe_games, args.sims, args.width, nn_device)
+    rate = probe["sims"] / probe["seconds"]
+    sims_per_game = probe["sims"] / probe_games
+    n = int(max(32, min(1000, rate * budget_s / sims_per_game)))
+    run = cpu_reference_run(n, args.sims, args.width, nn_device)
+    return {
+        "value": run["positions"] / run["seconds"],
+        "unit": UNIT,
+        "cores": run["threads"],
+        "kind": "port",
+        "sample": f"{n} concurrent games x {args.sims} sims/move (game_id 0..{n - 1}) of the same workload, "
+                  f"threaded port of rust/src/self_play.rs, fp32 network via numpy callback on {nn_device}",
+        "sims_per_s": run["sims"] / run["seconds"],
+        "seconds": run["seconds"],
+        "host_cpus": os.cpu_count(),
+        "mean_nn_batch": (run["sims"] / run["nn_batches"]) if run["nn_batches"] else None,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(4.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_baseline(args, per_step / 4)
+    vals, last = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = cpu_baseline(args, per_step)
+        vals.append(last["value"])
+    dt = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1), "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sims_per_s": last["sims_per_s"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"gen-0 self-play, {args.games} lockstep games per GPU x {args.sims} MCTS sims/move, 7x6 board, "
+                    f"random-init c4a0 ResNet (1 block x {args.width} filters, 4 policy / 2 value layers), "
+                    f"c_exploration={C_EXPLORATION}, c_ply_penalty={C_PLY_PENALTY}",
+        "games_per_gpu": args.games, "sims_per_move": args.sims, "global_games": args.games * world,
+        "parallelism": f"games sharded over {world} GPU(s), no search-path collective",
+        "l2": "inputs larger than L2: live tree arenas ~1.5 GB per GPU vs 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from c4a0_b200 import dist as D
+    from c4a0_b200 import selfplay
+    from c4a0_b200.selfplay import DeviceEvaluator
+    import c4a0_rust
+
+    rank, world, local_rank = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dtype = torch.bfloat16 if args.nn_dtype == "bf16" else torch.float32
+    model = make_model(args.width, dtype, device)
+    evaluator = DeviceEvaluator(model, dtype)
+    selfplay.DEFAULTS["sample_kernels_every"] = args.sample_kernels_every
+    G = args.games
+    ids = range(rank * G, (rank + 1) * G)  # weak scaling: every rank plays its own G games
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        t0 = time.perf_counter()
+        D.broadcast_model(model)  # a generation's weights: rank 0 -> all (NCCL); no-op at N=1
+        reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
+        res = c4a0_rust.play_games(reqs, G, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
+        n_pos = int(res._soa.n_samples.sum())
+        checksum = float(res._soa.q_no_penalty.sum())  # touch the host result
+        return time.perf_counter() - t0, res._run_info, n_pos, checksum
+
+    for _ in range(args.warmup):
+        one_step()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t_start = time.perf_counter()
+    runs = [one_step() for _ in range(args.steps)]
+    barrier()
+    wall = time.perf_counter() - t_start
+    clk = clocks.stop() if rank == 0 else None
+
+    dev_s = sum(r[1].device_s for r in runs)
+    e2e_s = sum(r[0] for r in runs)
+    positions = sum(r[2] for r in runs)
+    sims = sum(r[1].stats["sims"] for r in runs)
+    evals = sum(r[1].stats["nn_evals"] for r in runs)
+    ticks = sum(r[1].ticks for r in runs)
+    depth = sum(r[1].stats["select_depth_sum"] for r in runs)
+    kms = [r[1].kernel_ms for r in runs if r[1].kernel_ms]
+    # max over ranks of the times, sum over ranks of the work
+    t = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device=device)
+    w = torch.tensor([positions, sims, evals], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(w, op=torch.distributed.ReduceOp.SUM)
+    dev_s_max, e2e_s_max, wall_max = t.tolist()
+    positions_all, sims_all, evals_all = w.tolist()
+    if rank != 0:
+        return
+
+    # roofline of the tree kernel (k_step): SURVEY.md §8(d) bytes per simulation
+    d = depth / max(1, sims)
+    e = evals / max(1, sims)
+    s = 2 if dtype == torch.bfloat16 else 4
+    bytes_per_sim = 92 * d + 24 * (d + 1) + 16 + 84 * s + 36 + 168 * e
+    sims_per_launch = sims / max(1, ticks)
+    peak, peak_src = measured_peak_gbs()
+    roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                "peak_source": peak_src, "kernel": "k_step (apply network outputs + backup + UCT select + plane pack)"}
+    if kms:
+        k_step_ms = float(np.mean([k["k_step"] for k in kms]))
+        k_move_ms = float(np.mean([k["k_move"] for k in kms]))
+        achieved = bytes_per_sim * sims_per_launch / (k_step_ms * 1e-3) / 1e9
+        roofline.update(
+            achieved=achieved, frac=achieved / peak, bytes_per_sim=bytes_per_sim, sims_per_launch=sims_per_launch,
+            avg_launch_ms=k_step_ms, k_move_avg_launch_ms=k_move_ms, launches_timed=int(sum(k["samples"] for k in kms)),
+            select_depth=d, expand_frac=e,
+        )
+        tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+        if os.path.exists(tp):
+            try:
+                roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+    flops = model.flops_per_position()
+    line = {
+        "metric": METRIC, "value": positions_all / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.nn_dtype, "data": "synthetic",
+        "config": workload_config(args, world),
+        "sims_per_s": sims_all / dev_s_max, "nn_evals_per_s": evals_all / dev_s_max,
+        "e2e": {
+            "value": positions_all / e2e_s_max, "unit": UNIT,
+            "h2d_bytes_per_step": 3 * 8 * G, "d2h_bytes_per_step": G * (4 + 43 * (8 + 8 + 28 + 4 + 4)),
+            "sims_per_s": sims_all / e2e_s_max, "api": "c4a0_rust.play_games(list[GameMetadata], ...) -> PlayGamesResult",
+            "wall_ms_per_step": 1e3 * wall_max / max(1, args.steps),
+        },
+        "gpu_launches": int(3 * ticks + 2 * args.steps),
+        "roofline": roofline,
+        "nn_roofline": {
+            "bound": "tensor", "unit": "TFLOP/s", "flops_per_eval": flops,
+            "achieved_whole_tick": evals_all / world * flops / dev_s_max / 1e12,
+            "note": "network FLOPs / whole search time on one GPU (library kernels: cuBLAS/cuDNN via PyTorch)",
+        },
+        "clocks": clk,
+        "ticks_per_step": ticks / max(1, args.steps),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
+        except Exception as exc:  # the number is a report, never a reason to lose the bench line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

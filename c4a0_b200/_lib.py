@@ -93,6 +93,7 @@ SIGNATURES = {
     "c4a0_engine_bind_io": (C.c_int, [_P, _P, _P, _P, _P]),
     "c4a0_engine_set_requests": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P]),
     "c4a0_engine_step": (C.c_int, [_P, _P]),
+    "c4a0_engine_step_timed": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "c4a0_engine_eval_builtin": (C.c_int, [_P, C.c_int, _P]),
     "c4a0_engine_poll": (C.c_int, [_P, C.POINTER(Progress), _P]),
     "c4a0_engine_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
@@ -110,6 +111,8 @@ SIGNATURES = {
     "c4a0_host_sample": (C.c_int, [_P, C.c_float, C.c_uint64, _P]),
     "c4a0_host_terminal_state": (C.c_int, [C.c_uint64, C.c_uint64]),
     "c4a0_host_make_move": (None, [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "c4a0_host_flip_h": (None, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "c4a0_host_shuffle": (None, [C.c_uint64, _P, C.c_size_t]),
 }
 
 _lib = None

@@ -70,6 +70,83 @@ C4_HD int weighted_sample7(const float w[7], uint64_t seed) {
   return idx;
 }
 
+// ---- host only: StdRng stream + SliceRandom::shuffle (rust/src/pybridge.rs:110-113) -----------
+// Same provenance note as above: rand 0.10.1's `shuffle` walks the slice upwards and swaps element
+// i with a uniform index in [0, i]; the indices come from `IncreasingUniform`, which draws one u32
+// below the largest product (i+1)(i+2)...(i+k) that fits 32 bits and peels k indices off it by
+// division.  Bounded u32 draws are widening multiplies with one bias-correction draw.
+struct StdRngStream {
+  uint32_t key[8];
+  uint32_t block[16];
+  uint64_t counter = 0;
+  int used = 16;
+  explicit StdRngStream(uint64_t seed) { seed_to_key(seed, key); }
+  void refill() {
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+    for (int i = 0; i < 8; i++) in[4 + i] = key[i];
+    in[12] = (uint32_t)counter;
+    in[13] = (uint32_t)(counter >> 32);
+    in[14] = in[15] = 0;
+    uint32_t x[16];
+    for (int i = 0; i < 16; i++) x[i] = in[i];
+    for (int r = 0; r < 6; r++) {
+      C4_QR(x[0], x[4], x[8], x[12]) C4_QR(x[1], x[5], x[9], x[13])
+      C4_QR(x[2], x[6], x[10], x[14]) C4_QR(x[3], x[7], x[11], x[15])
+      C4_QR(x[0], x[5], x[10], x[15]) C4_QR(x[1], x[6], x[11], x[12])
+      C4_QR(x[2], x[7], x[8], x[13]) C4_QR(x[3], x[4], x[9], x[14])
+    }
+    for (int i = 0; i < 16; i++) block[i] = x[i] + in[i];
+    counter++;
+    used = 0;
+  }
+  uint32_t next_u32() {
+    if (used >= 16) refill();
+    return block[used++];
+  }
+  // uniform in [0, bound) — bound == 0 means the full 32-bit range
+  uint32_t below(uint32_t bound) {
+    if (bound == 0) return next_u32();
+    uint64_t m = (uint64_t)next_u32() * bound;
+    uint32_t hi = (uint32_t)(m >> 32), lo = (uint32_t)m;
+    if (lo > (uint32_t)(0u - bound)) {
+      uint32_t hi2 = (uint32_t)(((uint64_t)next_u32() * bound) >> 32);
+      if ((uint32_t)(lo + hi2) < lo) hi++;
+    }
+    return hi;
+  }
+};
+
+inline void shuffle_indices(uint64_t seed, uint32_t* idx, size_t n) {
+  if (n < 2) return;
+  StdRngStream rng(seed);
+  uint32_t packed = 0;   // indices still packed in the last draw
+  uint32_t left = 1;     // how many indices `packed` still holds (the first, for i = 0, is free)
+  for (size_t i = 0; i < n; i++) {
+    uint32_t span = (uint32_t)i + 1;  // choose in [0, i]
+    if (left == 0) {
+      // largest run span*(span+1)*...*(span+k-1) that still fits in 32 bits
+      uint32_t prod = span, nxt = span + 1;
+      while ((uint64_t)prod * nxt <= 0xffffffffULL) {
+        prod *= nxt;
+        nxt++;
+      }
+      packed = rng.below(prod);
+      left = nxt - span;
+    }
+    left--;
+    uint32_t j;
+    if (left == 0) {
+      j = packed;
+    } else {
+      j = packed % span;
+      packed /= span;
+    }
+    uint32_t t = idx[i];
+    idx[i] = idx[j];
+    idx[j] = t;
+  }
+}
+
 C4_HD uint64_t move_seed(uint64_t game_id, int n_moves) { return game_id * (uint64_t)(42 + n_moves); }
 
 }  // namespace c4

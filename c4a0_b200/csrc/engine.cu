@@ -379,7 +379,7 @@ __device__ void seat_game(const Dev& D, uint32_t slot, uint32_t r) {
 }
 
 __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
-  __shared__ uint32_t sh_src, sh_next, sh_head, sh_tail, sh_mode;  // mode: 0 continue, 1 finished
+  __shared__ uint32_t sh_src, sh_next, sh_head, sh_mode;  // mode: 0 continue, 1 finished
   __shared__ Pos sh_newpos;
   __shared__ uint32_t sh_newN;
   __shared__ float sh_newQp, sh_newQn, sh_tqp, sh_tqn;
@@ -716,6 +716,7 @@ struct c4a0_engine {
   uint64_t* row_models = nullptr;
   Globals* h_globals = nullptr;  // pinned
   float *b_logits = nullptr, *b_qp = nullptr, *b_qn = nullptr;  // writable aliases for eval_builtin
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -812,6 +813,8 @@ void c4a0_engine_destroy(c4a0_engine* e) {
   cudaSetDevice(e->cfg.device);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_globals) cudaFreeHost(e->h_globals);
+  for (auto ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -866,6 +869,31 @@ int c4a0_engine_step(c4a0_engine* e, void* stream) {
   unsigned grid = D.n_slots < 148u * 8u ? D.n_slots : 148u * 8u;
   k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
   CK(cudaGetLastError());
+  e->steps++;
+  return 0;
+}
+
+int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* ms_move) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if (!e->have_requests) return fail(C4A0_E_INVALID, "set_requests() must precede step()");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!e->ev[0])
+    for (int i = 0; i < 3; i++) CK(cudaEventCreate(&e->ev[i]));
+  const Dev& D = e->D;
+  k_begin_step<<<1, 1, 0, s>>>(D);
+  CK(cudaEventRecord(e->ev[0], s));
+  k_step<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  CK(cudaEventRecord(e->ev[1], s));
+  unsigned grid = D.n_slots < 148u * 8u ? D.n_slots : 148u * 8u;
+  k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
+  CK(cudaEventRecord(e->ev[2], s));
+  CK(cudaGetLastError());
+  CK(cudaEventSynchronize(e->ev[2]));
+  float a = 0, b = 0;
+  CK(cudaEventElapsedTime(&a, e->ev[0], e->ev[1]));
+  CK(cudaEventElapsedTime(&b, e->ev[1], e->ev[2]));
+  if (ms_step) *ms_step = a;
+  if (ms_move) *ms_move = b;
   e->steps++;
   return 0;
 }
@@ -1157,5 +1185,12 @@ void c4a0_host_make_move(uint64_t mask, uint64_t value, int col, uint64_t* om, u
   *om = r.mask;
   *ov = r.value;
 }
+
+void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t* om, uint64_t* ov) {
+  Pos r = c4::flip_h(Pos{mask, value});
+  *om = r.mask;
+  *ov = r.value;
+}
+void c4a0_host_shuffle(uint64_t seed, uint32_t* idx, size_t n) { c4::shuffle_indices(seed, idx, n); }
 
 }  // extern "C"

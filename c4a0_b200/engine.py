@@ -86,6 +86,12 @@ class Engine:
     def step(self, stream: int = 0) -> None:
         L.check(self._lib.c4a0_engine_step(self._h, stream))
 
+    def step_timed(self, stream: int = 0) -> Tuple[float, float]:
+        """step() bracketed by CUDA events: (ms of the apply+select kernel, ms of the move kernel)."""
+        a, b = C.c_float(), C.c_float()
+        L.check(self._lib.c4a0_engine_step_timed(self._h, stream, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def eval_builtin(self, kind: int, stream: int = 0) -> None:
         L.check(self._lib.c4a0_engine_eval_builtin(self._h, kind, stream))
 
@@ -221,3 +227,19 @@ def host_sample(policy: Sequence[float], temperature: float, seed: int):
     t = np.empty(7, np.float32)
     col = L.lib().c4a0_host_sample(L.ptr(p), temperature, seed, L.ptr(t))
     return t, int(col)
+
+
+def host_flip_h(mask: int, value: int) -> Tuple[int, int]:
+    a, b = C.c_uint64(), C.c_uint64()
+    L.lib().c4a0_host_flip_h(mask, value, C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def host_shuffle(seed: int, n: int) -> np.ndarray:
+    idx = np.arange(n, dtype=np.uint32)
+    L.lib().c4a0_host_shuffle(seed & 0xFFFFFFFFFFFFFFFF, L.ptr(idx), n)
+    return idx
+
+
+def host_terminal_state(mask: int, value: int) -> int:
+    return int(L.lib().c4a0_host_terminal_state(mask, value))

@@ -119,6 +119,11 @@ int c4a0_engine_set_requests(c4a0_engine *e, const uint64_t *game_id, const uint
  * then select every game's next leaf (mcts.rs:160-183) and write its planes. */
 int c4a0_engine_step(c4a0_engine *e, void *stream);
 
+/* step() with CUDA events around its two kernels (synchronises): device milliseconds of the
+ * apply+select kernel and of the move/re-root kernel.  Used by bench.py to sample kernel time inside
+ * the timed region; not capturable. */
+int c4a0_engine_step_timed(c4a0_engine *e, void *stream, float *ms_step_kernel, float *ms_move_kernel);
+
 /* Fill logits/q buffers for the current leaves with a synthetic evaluator (parity tiers E0/E1). */
 int c4a0_engine_eval_builtin(c4a0_engine *e, int kind, void *stream);
 
@@ -182,6 +187,9 @@ int c4a0_host_sample(const float *policy, float temperature, uint64_t seed, floa
 int c4a0_host_terminal_state(uint64_t mask, uint64_t value);
 void c4a0_host_make_move(uint64_t mask, uint64_t value, int col, uint64_t *out_mask,
                          uint64_t *out_value);
+void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t *out_mask, uint64_t *out_value);
+/* idx[0..n) permuted like `results.shuffle(&mut StdRng::seed_from_u64(seed))` (pybridge.rs:110-113) */
+void c4a0_host_shuffle(uint64_t seed, uint32_t *idx, size_t n);
 
 #ifdef __cplusplus
 }
