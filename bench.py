@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sample-kernels-every", type=int, default=53)
+    ap.add_argument("--lanes", type=int, default=2, help="engines per GPU (2 = tree ticks overlap the other half's network)")
+    ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
+    ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")
     return ap.parse_args()
 
 
@@ -236,9 +239,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dtype = torch.bfloat16 if args.nn_dtype == "bf16" else torch.float32
-    model = make_model(args.width, dtype, device)
-    evaluator = DeviceEvaluator(model, dtype)
+    model = make_model(args.width, torch.float32, device)
     selfplay.DEFAULTS["sample_kernels_every"] = args.sample_kernels_every
+    selfplay.DEFAULTS["n_lanes"] = args.lanes
+    selfplay.DEFAULTS["dedup"] = not args.no_dedup
     G = args.games
     ids = range(rank * G, (rank + 1) * G)  # weak scaling: every rank plays its own G games
 
@@ -250,6 +254,7 @@ def run_ours(args):
     def one_step():
         t0 = time.perf_counter()
         D.broadcast_model(model)  # a generation's weights: rank 0 -> all (NCCL); no-op at N=1
+        evaluator = DeviceEvaluator.from_model(model, dtype, fold=not args.no_fold)  # weights -> inference form
         reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
         res = c4a0_rust.play_games(reqs, G, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
         n_pos = int(res._soa.n_samples.sum())
@@ -273,23 +278,25 @@ def run_ours(args):
     positions = sum(r[2] for r in runs)
     sims = sum(r[1].stats["sims"] for r in runs)
     evals = sum(r[1].stats["nn_evals"] for r in runs)
+    expansions = sum(r[1].stats["expansions"] for r in runs)
+    nn_rows_launched = sum(r[1].report.get("nn_rows_launched", 0) for r in runs)
     ticks = sum(r[1].ticks for r in runs)
     depth = sum(r[1].stats["select_depth_sum"] for r in runs)
     kms = [r[1].kernel_ms for r in runs if r[1].kernel_ms]
     # max over ranks of the times, sum over ranks of the work
     t = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device=device)
-    w = torch.tensor([positions, sims, evals], dtype=torch.float64, device=device)
+    w = torch.tensor([positions, sims, evals, expansions, nn_rows_launched], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(w, op=torch.distributed.ReduceOp.SUM)
     dev_s_max, e2e_s_max, wall_max = t.tolist()
-    positions_all, sims_all, evals_all = w.tolist()
+    positions_all, sims_all, evals_all, expansions_all, rows_launched_all = w.tolist()
     if rank != 0:
         return
 
     # roofline of the tree kernel (k_step): SURVEY.md §8(d) bytes per simulation
     d = depth / max(1, sims)
-    e = evals / max(1, sims)
+    e = expansions / max(1, sims)
     s = 2 if dtype == torch.bfloat16 else 4
     bytes_per_sim = 92 * d + 24 * (d + 1) + 16 + 84 * s + 36 + 168 * e
     sims_per_launch = sims / max(1, ticks)
@@ -324,12 +331,16 @@ def run_ours(args):
             "sims_per_s": sims_all / e2e_s_max, "api": "c4a0_rust.play_games(list[GameMetadata], ...) -> PlayGamesResult",
             "wall_ms_per_step": 1e3 * wall_max / max(1, args.steps),
         },
-        "gpu_launches": int(3 * ticks + 2 * args.steps),
+        "gpu_launches": int(5 * ticks + 4 * args.steps * args.lanes),
+        "leaf_evals_per_s": expansions_all / dev_s_max,
+        "dedup": {"enabled": not args.no_dedup, "leaf_requests": expansions_all, "unique_rows": evals_all,
+                  "rows_launched_incl_bucket_padding": rows_launched_all},
+        "lanes": args.lanes, "nn_form": "module" if args.no_fold else "GEMM-folded (c4a0_b200.nn.FoldedNet)",
         "roofline": roofline,
         "nn_roofline": {
             "bound": "tensor", "unit": "TFLOP/s", "flops_per_eval": flops,
-            "achieved_whole_tick": evals_all / world * flops / dev_s_max / 1e12,
-            "note": "network FLOPs / whole search time on one GPU (library kernels: cuBLAS/cuDNN via PyTorch)",
+            "achieved_whole_tick": rows_launched_all / world * flops / dev_s_max / 1e12,
+            "note": "reference-form network FLOPs x rows launched / whole search time on one GPU (library kernels: cuBLASLt via PyTorch)",
         },
         "clocks": clk,
         "ticks_per_step": ticks / max(1, args.steps),

@@ -18,6 +18,7 @@ EVAL_UNIFORM, EVAL_HASH = 0, 1
 ROW_IDLE, ROW_WAIT_NN, ROW_CONTINUE, ROW_NEED_MOVE = 0, 1, 2, 3
 MATH_LOGF, MATH_EXPF = 0, 1
 E_INVALID, E_CUDA, E_NOMEM, E_ENGINE = -1, -2, -3, -4
+FLAG_NO_DEDUP = 1
 
 
 class Config(C.Structure):
@@ -30,6 +31,8 @@ class Config(C.Structure):
         ("plane_dtype", C.c_uint32),
         ("max_inline_sims", C.c_uint32),
         ("device", C.c_int32),
+        ("plane_stride", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -40,6 +43,7 @@ class Progress(C.Structure):
         ("n_finished", C.c_uint32),
         ("n_running", C.c_uint32),
         ("n_movers", C.c_uint32),
+        ("n_rows", C.c_uint32),
         ("error", C.c_int32),
     ]
 
@@ -48,6 +52,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("sims", C.c_uint64),
         ("nn_evals", C.c_uint64),
+        ("leaf_requests", C.c_uint64),
         ("terminal_leaf_sims", C.c_uint64),
         ("skipped_root_sims", C.c_uint64),
         ("moves", C.c_uint64),
@@ -73,7 +78,28 @@ class SlotInfo(C.Structure):
         ("root_q_sum_penalty", C.c_float),
         ("root_q_sum_no_penalty", C.c_float),
         ("n_blocks", C.c_uint32),
+        ("nn_row", C.c_uint32),
     ]
+
+
+class NNGraph(C.Structure):
+    _fields_ = [("rows", C.c_uint32), ("graph_exec", C.c_void_p)]
+
+
+class RunReport(C.Structure):
+    _fields_ = [
+        ("ticks", C.c_uint64),
+        ("nn_launches", C.c_uint64),
+        ("nn_rows_launched", C.c_uint64),
+        ("device_ms", C.c_double),
+        ("wall_ms", C.c_double),
+        ("kernel_samples", C.c_uint32),
+        ("k_step_ms_sum", C.c_double),
+        ("k_move_ms_sum", C.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class EngineError(RuntimeError):
@@ -98,6 +124,7 @@ SIGNATURES = {
     "c4a0_engine_poll": (C.c_int, [_P, C.POINTER(Progress), _P]),
     "c4a0_engine_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
     "c4a0_engine_fetch_rows": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "c4a0_engine_run": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(RunReport)]),
     "c4a0_engine_fetch_results": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "c4a0_engine_results_dev": (C.c_int, [_P] + [C.POINTER(_P)] * 6),
     "c4a0_engine_slot_info": (C.c_int, [_P, C.c_uint32, C.POINTER(SlotInfo), _P]),

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libc4a0_engine.so")
 
-SOURCES = ["engine.cu"]
-HEADERS = ["c4_rules.cuh", "c4_math.cuh", "c4_rng.cuh"]
+SOURCES = ["engine.cu", "batch_ops.cu"]
+HEADERS = ["c4_rules.cuh", "c4_math.cuh", "c4_rng.cuh", "common.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

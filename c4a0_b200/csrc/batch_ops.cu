@@ -1,0 +1,236 @@
+// batch_ops.cu — stand-alone batch kernels (rules / math / sampling) and the host builds of the
+// shared math.  These entry points exist so that the parity tests can exercise every device
+// function of c4_rules.cuh / c4_math.cuh / c4_rng.cuh in isolation, on arbitrary inputs, through
+// the same C-ABI the engine uses.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "c4_math.cuh"
+#include "c4_rng.cuh"
+#include "c4_rules.cuh"
+#include "common.cuh"
+
+namespace c4host {
+static thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+const char* last_error() { return g_err.c_str(); }
+int no_gpu_error() {
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(C4A0_E_CUDA, "no CUDA device available (%s): the engine has no CPU fallback",
+                err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+  }
+  return 0;
+}
+}  // namespace c4host
+
+namespace {
+using c4::Pos;
+using c4host::blocks_for;
+using c4host::DevBuf;
+using c4host::fail;
+using c4host::no_gpu_error;
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone batch kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_rules(const uint64_t* mask, const uint64_t* value, size_t n, float c_pen,
+                        int32_t* terminal, uint32_t* legal, int32_t* ply, float* qp, float* qn,
+                        uint64_t* cm, uint64_t* cv, float* planes, uint64_t* fm, uint64_t* fv) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Pos p{mask[i], value[i]};
+  float a, b;
+  int t = c4::terminal_value(p, c_pen, &a, &b);
+  if (terminal) terminal[i] = t;
+  unsigned lg = c4::legal_mask(p.mask);
+  if (legal) legal[i] = lg;
+  if (ply) ply[i] = c4::ply(p.mask);
+  if (qp) qp[i] = a;
+  if (qn) qn[i] = b;
+  if (cm && cv)
+    for (int c = 0; c < 7; c++) {
+      Pos ch{0ull, 0ull};
+      if ((lg >> c) & 1u) ch = c4::make_move(p, c);
+      cm[i * 7 + c] = ch.mask;
+      cv[i * 7 + c] = ch.value;
+    }
+  if (planes)
+    for (int k = 0; k < 84; k++) planes[i * 84 + k] = c4::plane_elem(p, k);
+  if (fm && fv) {
+    Pos f = c4::flip_h(p);
+    fm[i] = f.mask;
+    fv[i] = f.value;
+  }
+}
+__global__ void k_math(int op, const float* in, float* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = op == C4A0_MATH_LOGF ? c4::c4_logf(in[i]) : c4::c4_expf(in[i]);
+}
+__global__ void k_softmax(const float* logits, const uint32_t* legal, float* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x[7], o[7];
+  for (int k = 0; k < 7; k++) x[k] = ((legal[i] >> k) & 1u) ? logits[i * 7 + k] : -c4::f32_inf();
+  if (!c4::softmax7(x, o))
+    for (int k = 0; k < 7; k++) o[k] = c4::f32_nan();
+  for (int k = 0; k < 7; k++) out[i * 7 + k] = o[k];
+}
+__global__ void k_sample(const float* policy, const float* temperature, const uint64_t* seed,
+                         float* tempered, int32_t* column, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p[7], t[7];
+  for (int k = 0; k < 7; k++) p[k] = policy[i * 7 + k];
+  c4::apply_temperature7(p, temperature[i], t);
+  for (int k = 0; k < 7; k++) tempered[i * 7 + k] = t[k];
+  column[i] = c4::weighted_sample7(t, seed[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* c4a0_last_error(void) { return c4host::last_error(); }
+int c4a0_abi_version(void) { return C4A0_ABI_VERSION; }
+
+// ---- stand-alone batch entry points --------------------------------------------------------------
+#define BATCH_PROLOGUE()            \
+  do {                              \
+    int _r = no_gpu_error();        \
+    if (_r) return _r;              \
+    CK(cudaSetDevice(device));      \
+  } while (0)
+#define UP(dbuf, hptr, count)                                                              \
+  do {                                                                                     \
+    CK((dbuf).alloc(count));                                                               \
+    CK(cudaMemcpy((dbuf).p, hptr, (count) * sizeof(*(dbuf).p), cudaMemcpyHostToDevice));   \
+  } while (0)
+#define DOWN(hptr, dbuf, count) \
+  CK(cudaMemcpy(hptr, (dbuf).p, (count) * sizeof(*(dbuf).p), cudaMemcpyDeviceToHost))
+
+int c4a0_rules_batch(int device, const uint64_t* mask, const uint64_t* value, size_t n, float c_pen,
+                     int32_t* terminal, uint32_t* legal, int32_t* ply, float* qp, float* qn,
+                     uint64_t* cm, uint64_t* cv, float* planes, uint64_t* fm, uint64_t* fv) {
+  if (!mask || !value) return fail(C4A0_E_INVALID, "null positions");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<uint64_t> dm, dv, dcm, dcv, dfm, dfv;
+  DevBuf<int32_t> dt, dp;
+  DevBuf<uint32_t> dl;
+  DevBuf<float> dqp, dqn, dpl;
+  UP(dm, mask, n);
+  UP(dv, value, n);
+  if (terminal) CK(dt.alloc(n));
+  if (legal) CK(dl.alloc(n));
+  if (ply) CK(dp.alloc(n));
+  if (qp) CK(dqp.alloc(n));
+  if (qn) CK(dqn.alloc(n));
+  if (cm && cv) { CK(dcm.alloc(n * 7)); CK(dcv.alloc(n * 7)); }
+  if (planes) CK(dpl.alloc(n * 84));
+  if (fm && fv) { CK(dfm.alloc(n)); CK(dfv.alloc(n)); }
+  k_rules<<<blocks_for(n, 256), 256>>>(dm.p, dv.p, n, c_pen, dt.p, dl.p, dp.p, dqp.p, dqn.p, dcm.p, dcv.p,
+                                       dpl.p, dfm.p, dfv.p);
+  CK(cudaGetLastError());
+  if (terminal) DOWN(terminal, dt, n);
+  if (legal) DOWN(legal, dl, n);
+  if (ply) DOWN(ply, dp, n);
+  if (qp) DOWN(qp, dqp, n);
+  if (qn) DOWN(qn, dqn, n);
+  if (cm && cv) { DOWN(cm, dcm, n * 7); DOWN(cv, dcv, n * 7); }
+  if (planes) DOWN(planes, dpl, n * 84);
+  if (fm && fv) { DOWN(fm, dfm, n); DOWN(fv, dfv, n); }
+  return 0;
+}
+
+int c4a0_math_batch(int device, int op, const float* in, float* out, size_t n) {
+  if (!in || !out) return fail(C4A0_E_INVALID, "null argument");
+  if (op != C4A0_MATH_LOGF && op != C4A0_MATH_EXPF) return fail(C4A0_E_INVALID, "bad op");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<float> di, dout;
+  UP(di, in, n);
+  CK(dout.alloc(n));
+  k_math<<<blocks_for(n, 256), 256>>>(op, di.p, dout.p, n);
+  CK(cudaGetLastError());
+  DOWN(out, dout, n);
+  return 0;
+}
+
+int c4a0_softmax_batch(int device, const float* logits, const uint32_t* legal, float* out, size_t n) {
+  if (!logits || !legal || !out) return fail(C4A0_E_INVALID, "null argument");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<float> dl, dout;
+  DevBuf<uint32_t> dg;
+  UP(dl, logits, n * 7);
+  UP(dg, legal, n);
+  CK(dout.alloc(n * 7));
+  k_softmax<<<blocks_for(n, 128), 128>>>(dl.p, dg.p, dout.p, n);
+  CK(cudaGetLastError());
+  DOWN(out, dout, n * 7);
+  return 0;
+}
+
+int c4a0_sample_batch(int device, const float* policy, const float* temperature, const uint64_t* seed,
+                      float* tempered, int32_t* column, size_t n) {
+  if (!policy || !temperature || !seed || !tempered || !column) return fail(C4A0_E_INVALID, "null argument");
+  BATCH_PROLOGUE();
+  if (n == 0) return 0;
+  DevBuf<float> dp, dt, dtemp;
+  DevBuf<uint64_t> ds;
+  DevBuf<int32_t> dc;
+  UP(dp, policy, n * 7);
+  UP(dt, temperature, n);
+  UP(ds, seed, n);
+  CK(dtemp.alloc(n * 7));
+  CK(dc.alloc(n));
+  k_sample<<<blocks_for(n, 128), 128>>>(dp.p, dt.p, ds.p, dtemp.p, dc.p, n);
+  CK(cudaGetLastError());
+  DOWN(tempered, dtemp, n * 7);
+  DOWN(column, dc, n);
+  return 0;
+}
+
+// ---- host builds of the shared math (CPU test-suite) ----------------------------------------------
+void c4a0_host_logf(const float* in, float* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = c4::c4_logf(in[i]);
+}
+void c4a0_host_expf(const float* in, float* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = c4::c4_expf(in[i]);
+}
+int c4a0_host_sample(const float* policy, float temperature, uint64_t seed, float* tempered) {
+  float t[7];
+  c4::apply_temperature7(policy, temperature, t);
+  if (tempered)
+    for (int i = 0; i < 7; i++) tempered[i] = t[i];
+  return c4::weighted_sample7(t, seed);
+}
+int c4a0_host_terminal_state(uint64_t mask, uint64_t value) { return c4::terminal_state(Pos{mask, value}); }
+void c4a0_host_make_move(uint64_t mask, uint64_t value, int col, uint64_t* om, uint64_t* ov) {
+  Pos r = c4::make_move(Pos{mask, value}, col);
+  *om = r.mask;
+  *ov = r.value;
+}
+
+void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t* om, uint64_t* ov) {
+  Pos r = c4::flip_h(Pos{mask, value});
+  *om = r.mask;
+  *ov = r.value;
+}
+void c4a0_host_shuffle(uint64_t seed, uint32_t* idx, size_t n) { c4::shuffle_indices(seed, idx, n); }
+
+}  // extern "C"

@@ -1,4 +1,5 @@
-// engine.cu — lockstep MCTS self-play on sm_100a: kernels + the C-ABI of include/c4a0_engine.h.
+// engine.cu — lockstep MCTS self-play on sm_100a: kernels + the engine half of the C-ABI
+// (include/c4a0_engine.h).
 //
 // What the reference does per game with a heap tree of Rc<RefCell<Node>> (rust/src/mcts.rs:332-355)
 // and a thread pool (rust/src/self_play.rs), this file does for thousands of games at once with
@@ -16,42 +17,32 @@
 //   * A move (mcts.rs:187-222) keeps the chosen child's subtree.  One CTA per moving game copies
 //     that subtree breadth-first into the other half of the game's arena (compaction), which is
 //     what bounds a game's memory to 2*(n_iterations+2) blocks regardless of game length.
+//   * The network batch is dense and de-duplicated, like the reference's NN thread builds it
+//     (self_play.rs:203-220: HashSet<Pos> per model): every selected leaf is inserted into an
+//     epoch-tagged hash table (smallest slot wins a key), a scan numbers the winners, and only they
+//     write input planes, to rows 0..n_rows-1.  Every game remembers the row that holds its answer.
 //
+// One tick = k_begin -> k_step -> k_move -> k_scan -> k_pack, then the network on rows [0, n_rows).
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
-#include <stdarg.h>
-#include <stdio.h>
+#include <string.h>
 
-#include <string>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <vector>
 
-#include "../../include/c4a0_engine.h"
 #include "c4_math.cuh"
 #include "c4_rng.cuh"
 #include "c4_rules.cuh"
+#include "common.cuh"
 
 namespace {
 
 using c4::Pos;
-
-thread_local std::string g_err;
-int fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  g_err = buf;
-  return code;
-}
-#define CK(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t _e = (call);                                                                  \
-    if (_e != cudaSuccess)                                                                    \
-      return fail(C4A0_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
-                  __LINE__);                                                                  \
-  } while (0)
+using c4host::blocks_for;
+using c4host::fail;
 
 // ------------------------------------------------------------------------------------------------
 // Data layout
@@ -67,30 +58,47 @@ static_assert(sizeof(Block) == 160, "block must be five 32-byte sectors");
 
 constexpr int PATH_STRIDE = 44;  // <= 42 levels below a root
 constexpr int MAXS = C4A0_MAX_SAMPLES;
+constexpr int SCAN_THREADS = 1024;
 enum : uint32_t { ST_IDLE = 0, ST_WAIT_NN = 1, ST_CONTINUE = 2, ST_NEED_MOVE = 3 };
 
 struct Globals {  // one instance in device memory
+  uint32_t tick;  // epoch of the hash table: leaves selected during tick t carry epoch t
+  uint32_t n_req;
   uint32_t next_req;
   uint32_t n_finished;
   uint32_t n_running;
   uint32_t n_movers;
-  uint32_t last_movers;
+  uint32_t n_rows;
   int32_t error;
   unsigned long long skipped_root_sims;
   unsigned long long moves;
   unsigned long long samples;
   unsigned long long compacted_blocks;
+  unsigned long long rows_total;   // sum over ticks of n_rows (positions actually evaluated)
+  unsigned long long leaves_total; // sum over ticks of games waiting for the network
+};
+
+struct HostStatus {  // mapped pinned host memory, written by k_scan at the end of every tick
+  volatile uint32_t tick;
+  volatile uint32_t n_rows;
+  volatile uint32_t n_finished;
+  volatile uint32_t n_running;
+  volatile uint32_t n_movers;
+  volatile int32_t error;
 };
 
 struct Dev {  // passed to kernels by value
-  uint32_t n_slots, n_iter, cap, n_req, max_inline, plane_bf16;
+  uint32_t n_slots, n_iter, cap, max_inline, plane_bf16, plane_stride, dedup, table_mask;
   float c_expl, c_pen;
   // per slot
-  uint64_t *root_mask, *root_value, *leaf_mask, *leaf_value;
+  uint64_t *root_mask, *root_value, *leaf_mask, *leaf_value, *leaf_model;
   uint32_t *root_N, *root_block, *half, *n_alloc, *state, *req, *n_moves, *path_len, *path;
+  uint32_t *bucket, *urow, *nn_row;
   float *root_Qp, *root_Qn;
   unsigned long long *c_sims, *c_evals, *c_term, *c_depth;
   Block* blocks;  // [n_slots][2][cap]
+  // per row
+  uint32_t* row_slot;
   // per request
   const uint64_t *game_id, *p0, *p1;
   uint32_t* n_samples;
@@ -98,7 +106,9 @@ struct Dev {  // passed to kernels by value
   float *s_policy, *s_qp, *s_qn;
   // global
   Globals* g;
+  HostStatus* status;  // device address of the mapped host struct
   uint32_t* movers;
+  unsigned long long* table;  // [table_mask+1] entries: epoch << 32 | leader slot
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
@@ -106,6 +116,13 @@ struct Dev {  // passed to kernels by value
 
 __device__ __forceinline__ Block* arena_of(const Dev& D, uint32_t slot, uint32_t half) {
   return D.blocks + ((size_t)slot * 2 + half) * D.cap;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -133,11 +150,11 @@ __device__ __forceinline__ T gxor(const Group& g, T v, int m) {
 
 // NN input planes of `p` into row `row` (c4r.rs:378-392): 84 values, written by 8 lanes as
 // 16-byte (f32) or 8-byte (bf16) vectors.
-__device__ __forceinline__ void write_planes(const Dev& D, const Group& g, uint32_t row, Pos p) {
+__device__ __forceinline__ void write_planes(const Dev& D, int l, uint32_t row, Pos p) {
   uint64_t mine = p.mask & p.value, theirs = p.mask & ~p.value;
   if (D.plane_bf16) {
-    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(D.planes) + (size_t)row * 84);
-    for (int v = g.l; v < 21; v += 8) {
+    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(D.planes) + (size_t)row * D.plane_stride);
+    for (int v = l; v < 21; v += 8) {
       uint32_t w[2];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
@@ -149,8 +166,8 @@ __device__ __forceinline__ void write_planes(const Dev& D, const Group& g, uint3
       dst[v] = make_uint2(w[0], w[1]);
     }
   } else {
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(D.planes) + (size_t)row * 84);
-    for (int v = g.l; v < 21; v += 8) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(D.planes) + (size_t)row * D.plane_stride);
+    for (int v = l; v < 21; v += 8) {
       float f[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -160,6 +177,42 @@ __device__ __forceinline__ void write_planes(const Dev& D, const Group& g, uint3
       dst[v] = make_float4(f[0], f[1], f[2], f[3]);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Leaf de-duplication (self_play.rs:203-208).  Called by ONE lane per game once its leaf is known.
+// Table entry = epoch << 32 | leader slot; an entry whose epoch is not the current tick is empty,
+// so the table never needs clearing.  Among games with equal (position, model) the smallest slot
+// becomes the leader (atomicMin) — deterministic whatever order the games arrive in.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, Pos leaf, uint32_t epoch) {
+  uint32_t r = D.req[slot];
+  uint64_t model = (c4::ply(leaf.mask) & 1) ? D.p1[r] : D.p0[r];  // mcts.rs:70-76
+  D.leaf_mask[slot] = leaf.mask;
+  D.leaf_value[slot] = leaf.value;
+  D.leaf_model[slot] = model;
+  if (!D.dedup) return;
+  __threadfence();  // the key must be visible before the slot can be found in the table
+  uint32_t h = (uint32_t)splitmix64(leaf.mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(leaf.value ^ model)) & D.table_mask;
+  const unsigned long long mine = ((unsigned long long)epoch << 32) | slot;
+  for (;;) {
+    unsigned long long* e = D.table + h;
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e);
+    if ((uint32_t)(cur >> 32) != epoch) {
+      unsigned long long prev = atomicCAS(e, cur, mine);
+      if (prev == cur) break;  // first game with this key in this tick
+      cur = prev;
+      if ((uint32_t)(cur >> 32) != epoch) continue;
+    }
+    uint32_t leader = (uint32_t)cur;
+    if (__ldcg(D.leaf_mask + leader) == leaf.mask && __ldcg(D.leaf_value + leader) == leaf.value &&
+        __ldcg(D.leaf_model + leader) == model) {
+      atomicMin(e, mine);
+      break;
+    }
+    h = (h + 1) & D.table_mask;  // another key lives here: linear probing
+  }
+  D.bucket[slot] = h;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -266,17 +319,13 @@ __device__ __forceinline__ Pos select_leaf(const Dev& D, const Group& g, Game& G
 
 // Run simulations from "leaf unknown" until a leaf needs the network, the root needs to move, or
 // the per-step budget of in-kernel (terminal-leaf) simulations is spent.
-__device__ __forceinline__ uint32_t advance(const Dev& D, const Group& g, Game& G, uint32_t row) {
+__device__ __forceinline__ uint32_t advance(const Dev& D, const Group& g, Game& G, uint32_t epoch) {
   for (uint32_t it = 0;; it++) {
     Pos leaf = select_leaf(D, g, G);
     float tqp, tqn;
     int t = c4::terminal_value(leaf, D.c_pen, &tqp, &tqn);
     if (t == c4::NONE) {
-      write_planes(D, g, row, leaf);
-      if (g.l == 0) {
-        D.leaf_mask[G.slot] = leaf.mask;
-        D.leaf_value[G.slot] = leaf.value;
-      }
+      if (g.l == 0) publish_leaf(D, G.slot, leaf, epoch);
       return ST_WAIT_NN;
     }
     // terminal leaf: mcts.rs:92-98 — no expansion, back up the objective value
@@ -298,20 +347,21 @@ __device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
 // K_step: apply network outputs (expand + backup), then select the next leaf.  8 lanes per game.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_step(Dev D) {
-  uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  if (row >= D.n_slots) return;
+  uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (slot >= D.n_slots) return;
   Group g = make_group();
-  uint32_t slot = row;
   uint32_t st = D.state[slot];
   if (st == ST_IDLE) return;
   if (st == ST_NEED_MOVE) {  // reached n_iterations inside k_move's own advance()
     if (g.l == 0) push_mover(D, slot);
     return;
   }
+  const uint32_t epoch = D.g->tick;
   Game G;
   load_game(D, slot, G);
   if (st == ST_WAIT_NN) {
     // mask_policy + softmax (c4r.rs:272-286, mcts.rs:416-434) over the leaf's legal moves
+    const uint32_t row = D.nn_row[slot];
     unsigned legal = c4::legal_mask(D.leaf_mask[slot]);
     bool ok = (g.l < 7) && ((legal >> g.l) & 1u);
     float x = ok ? D.logits[(size_t)row * 7 + g.l] : -c4::f32_inf();
@@ -351,7 +401,7 @@ __global__ void __launch_bounds__(256) k_step(Dev D) {
       return;
     }
   }
-  uint32_t ns = advance(D, g, G, row);
+  uint32_t ns = advance(D, g, G, epoch);
   store_game(D, g, G, ns);
   if (ns == ST_NEED_MOVE && g.l == 0) push_mover(D, slot);
 }
@@ -364,8 +414,6 @@ constexpr int MOVE_THREADS = 128;
 __device__ void seat_game(const Dev& D, uint32_t slot, uint32_t r) {
   D.root_mask[slot] = 0ull;
   D.root_value[slot] = 0ull;
-  D.leaf_mask[slot] = 0ull;
-  D.leaf_value[slot] = 0ull;
   D.root_N[slot] = 0u;
   D.root_Qp[slot] = 0.0f;
   D.root_Qn[slot] = 0.0f;
@@ -379,11 +427,13 @@ __device__ void seat_game(const Dev& D, uint32_t slot, uint32_t r) {
 }
 
 __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
-  __shared__ uint32_t sh_src, sh_next, sh_head, sh_mode;  // mode: 0 continue, 1 finished
+  __shared__ uint32_t sh_src, sh_next, sh_head, sh_mode;  // mode: 0 re-root, 1 game over, 2 error
   __shared__ Pos sh_newpos;
   __shared__ uint32_t sh_newN;
   __shared__ float sh_newQp, sh_newQn, sh_tqp, sh_tqn;
   const uint32_t n_movers = D.g->n_movers;
+  const uint32_t epoch = D.g->tick;
+  const uint32_t n_req = D.g->n_req;
   for (uint32_t m = blockIdx.x; m < n_movers; m += gridDim.x) {
     const uint32_t slot = D.movers[m];
     const uint32_t req = D.req[slot];
@@ -397,13 +447,9 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
       // root_policy (mcts.rs:396-412): visit counts of the children, normalised
       float pol[7], tempered[7];
       const float uniform = 1.0f / 7.0f;
-      uint32_t cn[7] = {0, 0, 0, 0, 0, 0, 0};
       if (rb) {
         float cnt[7], sum = 0.0f;
-        for (int i = 0; i < 7; i++) {
-          cn[i] = src[rb].N[i];
-          cnt[i] = (float)cn[i];
-        }
+        for (int i = 0; i < 7; i++) cnt[i] = (float)src[rb].N[i];
         for (int i = 0; i < 7; i++) sum = sum + cnt[i];
         for (int i = 0; i < 7; i++) pol[i] = (sum == 0.0f) ? uniform : cnt[i] / sum;
       } else {
@@ -468,17 +514,13 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
         if (nN < D.n_iter) atomicAdd(&D.g->skipped_root_sims, (unsigned long long)(D.n_iter - nN));
         // seat the next waiting request in this slot (self_play.rs:55-58 queues them all up front)
         uint32_t r = atomicAdd(&D.g->next_req, 1u);
-        if (r < D.n_req) {
+        if (r < n_req) {
           seat_game(D, slot, r);
+          publish_leaf(D, slot, Pos{0ull, 0ull}, epoch);
         } else {
           D.state[slot] = ST_IDLE;
           atomicSub(&D.g->n_running, 1u);
         }
-      }
-      __syncthreads();
-      if (threadIdx.x < 8 && D.state[slot] == ST_WAIT_NN) {
-        Group g = make_group();
-        write_planes(D, g, slot, Pos{0ull, 0ull});
       }
       __syncthreads();
       continue;
@@ -540,65 +582,139 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
       Group g = make_group();
       Game G;
       load_game(D, slot, G);
-      uint32_t ns = advance(D, g, G, slot);
+      uint32_t ns = advance(D, g, G, epoch);
       store_game(D, g, G, ns);
     }
     __syncthreads();
   }
 }
 
-// Resets the mover list after k_move consumed it (runs as the first thing of the next step).
+// First kernel of a tick: new epoch, empty mover list.
 __global__ void k_begin_step(Dev D) {
-  D.g->last_movers = D.g->n_movers;
+  D.g->tick += 1u;
   D.g->n_movers = 0u;
 }
 
-// Seat the first min(n_slots, n_req) games.
-__global__ void k_init(Dev D) {
-  uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  if (row >= D.n_slots) return;
-  Group g = make_group();
-  if (row < D.n_req) {
-    if (g.l == 0) {
-      seat_game(D, row, row);
-      D.c_sims[row] = D.c_evals[row] = D.c_term[row] = D.c_depth[row] = 0ull;
-    }
-    write_planes(D, g, row, Pos{0ull, 0ull});
-  } else if (g.l == 0) {
-    D.state[row] = ST_IDLE;
-    D.c_sims[row] = D.c_evals[row] = D.c_term[row] = D.c_depth[row] = 0ull;
-  }
-  if (row == 0 && g.l == 0) {
+// Seat the first min(n_slots, n_req) games (self_play.rs:55-58).
+__global__ void k_init(Dev D, uint32_t n_req) {
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot == 0) {
     Globals z;
     memset(&z, 0, sizeof(z));
-    z.next_req = D.n_req < D.n_slots ? D.n_req : D.n_slots;
+    z.tick = 1u;
+    z.n_req = n_req;
+    z.next_req = n_req < D.n_slots ? n_req : D.n_slots;
     z.n_running = z.next_req;
     *D.g = z;
+  }
+  if (slot >= D.n_slots) return;
+  D.c_sims[slot] = D.c_evals[slot] = D.c_term[slot] = D.c_depth[slot] = 0ull;
+  if (slot < n_req) {
+    seat_game(D, slot, slot);
+    publish_leaf(D, slot, Pos{0ull, 0ull}, 1u);
+  } else {
+    D.state[slot] = ST_IDLE;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Synthetic evaluators (parity tiers E0 / E1)
+// K_scan (one CTA): number the leaders in slot order -> urow[], n_rows; publish the tick's status
+// to the host.  K_pack: leaders write their planes to their row, every waiting game records the row
+// that will hold its answer.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ULL;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-  return x ^ (x >> 31);
+__device__ __forceinline__ bool is_leader(const Dev& D, uint32_t slot) {
+  if (D.state[slot] != ST_WAIT_NN) return false;
+  if (!D.dedup) return true;
+  return (uint32_t)D.table[D.bucket[slot]] == slot;
 }
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Dev D) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+  __shared__ uint32_t warp_wait[SCAN_THREADS / 32];
+  const uint32_t per = (D.n_slots + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t lo = threadIdx.x * per;
+  const uint32_t hi = min(lo + per, D.n_slots);
+  uint32_t cnt = 0, waiting = 0;
+  for (uint32_t s = lo; s < hi; s++) {
+    cnt += is_leader(D, s) ? 1u : 0u;
+    waiting += (D.state[s] == ST_WAIT_NN) ? 1u : 0u;
+  }
+  // block-wide exclusive scan of cnt
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  uint32_t wsum = waiting;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
+  if (lane == 31) warp_sums[warp] = incl;
+  if (lane == 0) warp_wait[warp] = wsum;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = warp_sums[lane];
+    uint32_t iv = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, iv, d);
+      if (lane >= d) iv += t;
+    }
+    warp_sums[lane] = iv - v;  // exclusive prefix of the warp totals
+    uint32_t ww = warp_wait[lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ww += __shfl_xor_sync(0xffffffffu, ww, d);
+    if (lane == 31) {
+      uint32_t total = iv;
+      Globals* G = D.g;
+      G->n_rows = total;
+      G->rows_total += total;
+      G->leaves_total += ww;
+      HostStatus* hs = D.status;
+      hs->n_rows = total;
+      hs->n_finished = G->n_finished;
+      hs->n_running = G->n_running;
+      hs->n_movers = G->n_movers;
+      hs->error = G->error;
+      __threadfence_system();
+      hs->tick = G->tick;  // written last: the host spins on it
+    }
+  }
+  __syncthreads();
+  uint32_t base = warp_sums[warp] + (incl - cnt);
+  for (uint32_t s = lo; s < hi; s++)
+    if (is_leader(D, s)) D.urow[s] = base++;
+}
+
+__global__ void __launch_bounds__(256) k_pack(Dev D) {
+  uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (slot >= D.n_slots) return;
+  if (D.state[slot] != ST_WAIT_NN) return;
+  const int l = threadIdx.x & 7;
+  uint32_t leader = D.dedup ? (uint32_t)D.table[D.bucket[slot]] : slot;
+  uint32_t row = D.urow[leader];
+  if (l == 0) D.nn_row[slot] = row;
+  if (leader == slot) {
+    if (l == 0) D.row_slot[row] = slot;
+    write_planes(D, l, row, Pos{D.leaf_mask[slot], D.leaf_value[slot]});
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic evaluators (parity tiers E0 / E1) and row views
+// ------------------------------------------------------------------------------------------------
 __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float* qn) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= D.n_slots) return;
+  if (row >= D.g->n_rows) return;
   if (kind == C4A0_EVAL_UNIFORM) {
     for (int k = 0; k < 7; k++) logits[(size_t)row * 7 + k] = 0.0f;
     qp[row] = 0.0f;
     qn[row] = 0.0f;
     return;
   }
-  uint64_t mask = D.leaf_mask[row], value = D.leaf_value[row];
-  uint32_t r = D.req[row];
-  uint64_t model = 0;
-  if (D.state[row] != ST_IDLE) model = (c4::ply(mask) % 2 == 0) ? D.p0[r] : D.p1[r];
+  uint32_t slot = D.row_slot[row];
+  uint64_t mask = D.leaf_mask[slot], value = D.leaf_value[slot], model = D.leaf_model[slot];
   uint64_t h = splitmix64(mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(value ^ model));
   for (int k = 0; k < 7; k++) {
     uint64_t hk = splitmix64(h + (uint64_t)k);
@@ -609,15 +725,13 @@ __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float*
   qn[row] = ((float)(uint32_t)((hq >> 32) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * 0.75f;
 }
 
-__global__ void k_row_models(Dev D, uint64_t* out) {
+__global__ void k_gather_rows(Dev D, uint64_t* mask, uint64_t* value, uint64_t* model) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= D.n_slots) return;
-  uint64_t model = 0;
-  if (D.state[row] != ST_IDLE) {
-    uint32_t r = D.req[row];
-    model = (c4::ply(D.leaf_mask[row]) % 2 == 0) ? D.p0[r] : D.p1[r];  // mcts.rs:70-76
-  }
-  out[row] = model;
+  if (row >= D.g->n_rows) return;
+  uint32_t slot = D.row_slot[row];
+  mask[row] = D.leaf_mask[slot];
+  value[row] = D.leaf_value[slot];
+  model[row] = D.leaf_model[slot];
 }
 
 __global__ void k_sum_counters(Dev D, unsigned long long* out4) {
@@ -634,72 +748,6 @@ __global__ void k_sum_counters(Dev D, unsigned long long* out4) {
   atomicAdd(out4 + 3, d);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Stand-alone batch kernels
-// ------------------------------------------------------------------------------------------------
-__global__ void k_rules(const uint64_t* mask, const uint64_t* value, size_t n, float c_pen,
-                        int32_t* terminal, uint32_t* legal, int32_t* ply, float* qp, float* qn,
-                        uint64_t* cm, uint64_t* cv, float* planes, uint64_t* fm, uint64_t* fv) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Pos p{mask[i], value[i]};
-  float a, b;
-  int t = c4::terminal_value(p, c_pen, &a, &b);
-  if (terminal) terminal[i] = t;
-  unsigned lg = c4::legal_mask(p.mask);
-  if (legal) legal[i] = lg;
-  if (ply) ply[i] = c4::ply(p.mask);
-  if (qp) qp[i] = a;
-  if (qn) qn[i] = b;
-  if (cm && cv)
-    for (int c = 0; c < 7; c++) {
-      Pos ch{0ull, 0ull};
-      if ((lg >> c) & 1u) ch = c4::make_move(p, c);
-      cm[i * 7 + c] = ch.mask;
-      cv[i * 7 + c] = ch.value;
-    }
-  if (planes)
-    for (int k = 0; k < 84; k++) planes[i * 84 + k] = c4::plane_elem(p, k);
-  if (fm && fv) {
-    Pos f = c4::flip_h(p);
-    fm[i] = f.mask;
-    fv[i] = f.value;
-  }
-}
-__global__ void k_math(int op, const float* in, float* out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  out[i] = op == C4A0_MATH_LOGF ? c4::c4_logf(in[i]) : c4::c4_expf(in[i]);
-}
-__global__ void k_softmax(const float* logits, const uint32_t* legal, float* out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float x[7], o[7];
-  for (int k = 0; k < 7; k++) x[k] = ((legal[i] >> k) & 1u) ? logits[i * 7 + k] : -c4::f32_inf();
-  if (!c4::softmax7(x, o))
-    for (int k = 0; k < 7; k++) o[k] = c4::f32_nan();
-  for (int k = 0; k < 7; k++) out[i * 7 + k] = o[k];
-}
-__global__ void k_sample(const float* policy, const float* temperature, const uint64_t* seed,
-                         float* tempered, int32_t* column, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float p[7], t[7];
-  for (int k = 0; k < 7; k++) p[k] = policy[i * 7 + k];
-  c4::apply_temperature7(p, temperature[i], t);
-  for (int k = 0; k < 7; k++) tempered[i * 7 + k] = t[k];
-  column[i] = c4::weighted_sample7(t, seed[i]);
-}
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-};
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -711,10 +759,12 @@ struct c4a0_engine {
   std::vector<void*> allocs;
   size_t bytes = 0;
   bool io_bound = false, have_requests = false;
+  uint32_t n_req = 0;
   uint64_t steps = 0;
   unsigned long long* scratch4 = nullptr;
-  uint64_t* row_models = nullptr;
-  Globals* h_globals = nullptr;  // pinned
+  uint64_t *row_mask = nullptr, *row_value = nullptr, *row_model = nullptr;
+  Globals* h_globals = nullptr;   // pinned
+  HostStatus* h_status = nullptr; // pinned + mapped
   float *b_logits = nullptr, *b_qp = nullptr, *b_qn = nullptr;  // writable aliases for eval_builtin
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
@@ -742,23 +792,28 @@ int dalloc(c4a0_engine* e, T** p, size_t n) {
     }                                      \
   } while (0)
 
-int no_gpu_error() {
-  int n = 0;
-  cudaError_t err = cudaGetDeviceCount(&n);
-  if (err != cudaSuccess || n == 0) {
-    cudaGetLastError();
-    return fail(C4A0_E_CUDA, "no CUDA device available (%s): the engine has no CPU fallback",
-                err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
-  }
+// Enqueue one tick.  `ev` (3 events) brackets k_step and k_move when given.
+int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
+  const Dev& D = e->D;
+  k_begin_step<<<1, 1, 0, s>>>(D);
+  if (ev) CK(cudaEventRecord(ev[0], s));
+  k_step<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  if (ev) CK(cudaEventRecord(ev[1], s));
+  unsigned grid = D.n_slots < 148u * 8u ? D.n_slots : 148u * 8u;
+  k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
+  if (ev) CK(cudaEventRecord(ev[2], s));
+  k_scan<<<1, SCAN_THREADS, 0, s>>>(D);
+  k_pack<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  CK(cudaGetLastError());
+  e->steps++;
   return 0;
 }
-inline unsigned blocks_for(size_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+const char* kEngineErr =
+    "a game reached a state where the reference panics (illegal sampled move or arena overflow)";
 }  // namespace
 
 extern "C" {
-
-const char* c4a0_last_error(void) { return g_err.c_str(); }
-int c4a0_abi_version(void) { return C4A0_ABI_VERSION; }
 
 int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   if (!cfg || !out) return fail(C4A0_E_INVALID, "null argument");
@@ -766,9 +821,12 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   if (cfg->n_slots == 0 || cfg->n_mcts_iterations == 0 || cfg->max_requests == 0)
     return fail(C4A0_E_INVALID, "n_slots, max_requests and n_mcts_iterations must be >= 1");
   if (cfg->plane_dtype > C4A0_PLANES_BF16) return fail(C4A0_E_INVALID, "bad plane_dtype");
+  if (cfg->plane_stride && (cfg->plane_stride < 84 || cfg->plane_stride % 4))
+    return fail(C4A0_E_INVALID, "plane_stride must be 0 or a multiple of 4 that is >= 84");
   if (cfg->n_mcts_iterations > (1u << 24))
     return fail(C4A0_E_INVALID, "n_mcts_iterations above 2^24 is not exactly representable in f32");
-  int r = no_gpu_error();
+  if (cfg->n_slots > (1u << 24)) return fail(C4A0_E_INVALID, "n_slots above 2^24 is not supported");
+  int r = c4host::no_gpu_error();
   if (r) return r;
   CK(cudaSetDevice(cfg->device));
   c4a0_engine* e = new c4a0_engine();
@@ -778,28 +836,40 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   D.n_slots = cfg->n_slots;
   D.n_iter = cfg->n_mcts_iterations;
   D.cap = cfg->n_mcts_iterations + 2;  // index 0 unused; at most n_iter expanded nodes per tree
-  D.n_req = 0;
   D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : 8;
   D.plane_bf16 = cfg->plane_dtype == C4A0_PLANES_BF16;
+  D.plane_stride = cfg->plane_stride ? cfg->plane_stride : 84;
+  D.dedup = (cfg->flags & C4A0_FLAG_NO_DEDUP) ? 0u : 1u;
   D.c_expl = cfg->c_exploration;
   D.c_pen = cfg->c_ply_penalty;
   size_t S = cfg->n_slots, R = cfg->max_requests;
-  DA(D.root_mask, S); DA(D.root_value, S); DA(D.leaf_mask, S); DA(D.leaf_value, S);
+  size_t T = 1;
+  while (T < 2 * S) T <<= 1;
+  D.table_mask = (uint32_t)(T - 1);
+  DA(D.root_mask, S); DA(D.root_value, S); DA(D.leaf_mask, S); DA(D.leaf_value, S); DA(D.leaf_model, S);
   DA(D.root_N, S); DA(D.root_block, S); DA(D.half, S); DA(D.n_alloc, S); DA(D.state, S);
   DA(D.req, S); DA(D.n_moves, S); DA(D.path_len, S); DA(D.path, S * PATH_STRIDE);
+  DA(D.bucket, S); DA(D.urow, S); DA(D.nn_row, S); DA(D.row_slot, S);
   DA(D.root_Qp, S); DA(D.root_Qn, S);
   DA(D.c_sims, S); DA(D.c_evals, S); DA(D.c_term, S); DA(D.c_depth, S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
+  DA(D.table, T);
   uint64_t *gid, *p0, *p1;
   DA(gid, R); DA(p0, R); DA(p1, R);
   D.game_id = gid; D.p0 = p0; D.p1 = p1;
   DA(D.n_samples, R); DA(D.s_mask, R * MAXS); DA(D.s_value, R * MAXS);
   DA(D.s_policy, R * MAXS * 7); DA(D.s_qp, R * MAXS); DA(D.s_qn, R * MAXS);
   DA(D.g, 1); DA(D.movers, S);
-  DA(e->scratch4, 4); DA(e->row_models, S);
+  DA(e->scratch4, 4); DA(e->row_mask, S); DA(e->row_value, S); DA(e->row_model, S);
   cudaError_t err = cudaMemset(D.state, 0, S * sizeof(uint32_t));
   if (err == cudaSuccess) err = cudaMemset(D.g, 0, sizeof(Globals));
+  if (err == cudaSuccess) err = cudaMemset(D.table, 0, T * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_globals, sizeof(Globals));
+  if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_status, sizeof(HostStatus), cudaHostAllocMapped);
+  if (err == cudaSuccess) {
+    memset((void*)e->h_status, 0, sizeof(HostStatus));
+    err = cudaHostGetDevicePointer((void**)&D.status, (void*)e->h_status, 0);
+  }
   if (err != cudaSuccess) {
     c4a0_engine_destroy(e);
     return fail(C4A0_E_CUDA, "engine init failed: %s", cudaGetErrorString(err));
@@ -811,8 +881,10 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
 void c4a0_engine_destroy(c4a0_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_globals) cudaFreeHost(e->h_globals);
+  if (e->h_status) cudaFreeHost((void*)e->h_status);
   for (auto ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   delete e;
@@ -850,10 +922,13 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
     CK(cudaMemcpyAsync((void*)D.p1, p1, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(D.n_samples, 0, n * sizeof(uint32_t), s));
   }
-  D.n_req = n;
-  k_init<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
+  k_init<<<blocks_for(D.n_slots, 256), 256, 0, s>>>(D, n);
+  k_scan<<<1, SCAN_THREADS, 0, s>>>(D);
+  k_pack<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));  // the host arrays may be freed by the caller after return
+  e->n_req = n;
   e->have_requests = true;
   e->steps = 0;
   return 0;
@@ -862,15 +937,7 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
 int c4a0_engine_step(c4a0_engine* e, void* stream) {
   if (!e) return fail(C4A0_E_INVALID, "null engine");
   if (!e->have_requests) return fail(C4A0_E_INVALID, "set_requests() must precede step()");
-  cudaStream_t s = (cudaStream_t)stream;
-  const Dev& D = e->D;
-  k_begin_step<<<1, 1, 0, s>>>(D);
-  k_step<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
-  unsigned grid = D.n_slots < 148u * 8u ? D.n_slots : 148u * 8u;
-  k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
-  CK(cudaGetLastError());
-  e->steps++;
-  return 0;
+  return launch_tick(e, (cudaStream_t)stream, nullptr);
 }
 
 int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* ms_move) {
@@ -879,22 +946,14 @@ int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* 
   cudaStream_t s = (cudaStream_t)stream;
   if (!e->ev[0])
     for (int i = 0; i < 3; i++) CK(cudaEventCreate(&e->ev[i]));
-  const Dev& D = e->D;
-  k_begin_step<<<1, 1, 0, s>>>(D);
-  CK(cudaEventRecord(e->ev[0], s));
-  k_step<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
-  CK(cudaEventRecord(e->ev[1], s));
-  unsigned grid = D.n_slots < 148u * 8u ? D.n_slots : 148u * 8u;
-  k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
-  CK(cudaEventRecord(e->ev[2], s));
-  CK(cudaGetLastError());
-  CK(cudaEventSynchronize(e->ev[2]));
+  int r = launch_tick(e, s, e->ev);
+  if (r) return r;
+  CK(cudaStreamSynchronize(s));
   float a = 0, b = 0;
   CK(cudaEventElapsedTime(&a, e->ev[0], e->ev[1]));
   CK(cudaEventElapsedTime(&b, e->ev[1], e->ev[2]));
   if (ms_step) *ms_step = a;
   if (ms_move) *ms_move = b;
-  e->steps++;
   return 0;
 }
 
@@ -912,13 +971,14 @@ int c4a0_engine_poll(c4a0_engine* e, c4a0_progress* out, void* stream) {
   CK(cudaMemcpyAsync(e->h_globals, e->D.g, sizeof(Globals), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   const Globals& g = *e->h_globals;
-  out->n_requests = e->D.n_req;
-  out->n_started = g.next_req < e->D.n_req ? g.next_req : e->D.n_req;
+  out->n_requests = g.n_req;
+  out->n_started = g.next_req < g.n_req ? g.next_req : g.n_req;
   out->n_finished = g.n_finished;
   out->n_running = g.n_running;
   out->n_movers = g.n_movers;
+  out->n_rows = g.n_rows;
   out->error = g.error;
-  if (g.error) return fail(C4A0_E_ENGINE, "a game reached a state where the reference panics (illegal sampled move or arena overflow)");
+  if (g.error) return fail(C4A0_E_ENGINE, "%s", kEngineErr);
   return 0;
 }
 
@@ -934,7 +994,8 @@ int c4a0_engine_stats(c4a0_engine* e, c4a0_stats* out, void* stream) {
   CK(cudaStreamSynchronize(s));
   const Globals& g = *e->h_globals;
   out->sims = h4[0];
-  out->nn_evals = h4[1];
+  out->nn_evals = g.rows_total;
+  out->leaf_requests = g.leaves_total;
   out->terminal_leaf_sims = h4[2];
   out->select_depth_sum = h4[3];
   out->expansions = h4[1];
@@ -946,19 +1007,20 @@ int c4a0_engine_stats(c4a0_engine* e, c4a0_stats* out, void* stream) {
   return 0;
 }
 
-int c4a0_engine_fetch_rows(c4a0_engine* e, uint32_t* state, uint64_t* leaf_mask, uint64_t* leaf_value,
+int c4a0_engine_fetch_rows(c4a0_engine* e, uint32_t* n_rows, uint64_t* leaf_mask, uint64_t* leaf_value,
                            uint64_t* model_id, void* stream) {
-  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if (!e || !n_rows) return fail(C4A0_E_INVALID, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   size_t S = e->D.n_slots;
-  if (model_id) {
-    k_row_models<<<blocks_for(S, 256), 256, 0, s>>>(e->D, e->row_models);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(model_id, e->row_models, S * 8, cudaMemcpyDeviceToHost, s));
-  }
-  if (state) CK(cudaMemcpyAsync(state, e->D.state, S * 4, cudaMemcpyDeviceToHost, s));
-  if (leaf_mask) CK(cudaMemcpyAsync(leaf_mask, e->D.leaf_mask, S * 8, cudaMemcpyDeviceToHost, s));
-  if (leaf_value) CK(cudaMemcpyAsync(leaf_value, e->D.leaf_value, S * 8, cudaMemcpyDeviceToHost, s));
+  k_gather_rows<<<blocks_for(S, 256), 256, 0, s>>>(e->D, e->row_mask, e->row_value, e->row_model);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->h_globals, e->D.g, sizeof(Globals), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  uint32_t n = e->h_globals->n_rows;
+  *n_rows = n;
+  if (n && leaf_mask) CK(cudaMemcpyAsync(leaf_mask, e->row_mask, n * 8, cudaMemcpyDeviceToHost, s));
+  if (n && leaf_value) CK(cudaMemcpyAsync(leaf_value, e->row_value, n * 8, cudaMemcpyDeviceToHost, s));
+  if (n && model_id) CK(cudaMemcpyAsync(model_id, e->row_model, n * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return 0;
 }
@@ -967,7 +1029,7 @@ int c4a0_engine_fetch_results(c4a0_engine* e, uint32_t first, uint32_t n, uint32
                               uint64_t* mask, uint64_t* value, float* policy, float* qp, float* qn,
                               void* stream) {
   if (!e) return fail(C4A0_E_INVALID, "null engine");
-  if ((uint64_t)first + n > e->D.n_req) return fail(C4A0_E_INVALID, "result range out of bounds");
+  if ((uint64_t)first + n > e->n_req) return fail(C4A0_E_INVALID, "result range out of bounds");
   cudaStream_t s = (cudaStream_t)stream;
   const Dev& D = e->D;
   size_t o = (size_t)first * MAXS, c = (size_t)n * MAXS;
@@ -1008,6 +1070,7 @@ int c4a0_engine_slot_info(c4a0_engine* e, uint32_t slot, c4a0_slot_info* out, vo
   CK(cudaMemcpyAsync(&out->root_q_sum_penalty, D.root_Qp + slot, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&out->root_q_sum_no_penalty, D.root_Qn + slot, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&na, D.n_alloc + slot, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&out->nn_row, D.nn_row + slot, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   out->n_blocks = na ? na - 1 : 0;
   return 0;
@@ -1067,130 +1130,156 @@ int c4a0_engine_dump_tree(c4a0_engine* e, uint32_t slot, uint32_t* buf, size_t c
   return 0;
 }
 
-// ---- stand-alone batch entry points --------------------------------------------------------------
-#define BATCH_PROLOGUE()            \
-  do {                              \
-    int _r = no_gpu_error();        \
-    if (_r) return _r;              \
-    CK(cudaSetDevice(device));      \
-  } while (0)
-#define UP(dbuf, hptr, count)                                                              \
-  do {                                                                                     \
-    CK((dbuf).alloc(count));                                                               \
-    CK(cudaMemcpy((dbuf).p, hptr, (count) * sizeof(*(dbuf).p), cudaMemcpyHostToDevice));   \
-  } while (0)
-#define DOWN(hptr, dbuf, count) \
-  CK(cudaMemcpy(hptr, (dbuf).p, (count) * sizeof(*(dbuf).p), cudaMemcpyDeviceToHost))
-
-int c4a0_rules_batch(int device, const uint64_t* mask, const uint64_t* value, size_t n, float c_pen,
-                     int32_t* terminal, uint32_t* legal, int32_t* ply, float* qp, float* qn,
-                     uint64_t* cm, uint64_t* cv, float* planes, uint64_t* fm, uint64_t* fv) {
-  if (!mask || !value) return fail(C4A0_E_INVALID, "null positions");
-  BATCH_PROLOGUE();
-  if (n == 0) return 0;
-  DevBuf<uint64_t> dm, dv, dcm, dcv, dfm, dfv;
-  DevBuf<int32_t> dt, dp;
-  DevBuf<uint32_t> dl;
-  DevBuf<float> dqp, dqn, dpl;
-  UP(dm, mask, n);
-  UP(dv, value, n);
-  if (terminal) CK(dt.alloc(n));
-  if (legal) CK(dl.alloc(n));
-  if (ply) CK(dp.alloc(n));
-  if (qp) CK(dqp.alloc(n));
-  if (qn) CK(dqn.alloc(n));
-  if (cm && cv) { CK(dcm.alloc(n * 7)); CK(dcv.alloc(n * 7)); }
-  if (planes) CK(dpl.alloc(n * 84));
-  if (fm && fv) { CK(dfm.alloc(n)); CK(dfv.alloc(n)); }
-  k_rules<<<blocks_for(n, 256), 256>>>(dm.p, dv.p, n, c_pen, dt.p, dl.p, dp.p, dqp.p, dqn.p, dcm.p, dcv.p,
-                                       dpl.p, dfm.p, dfv.p);
-  CK(cudaGetLastError());
-  if (terminal) DOWN(terminal, dt, n);
-  if (legal) DOWN(legal, dl, n);
-  if (ply) DOWN(ply, dp, n);
-  if (qp) DOWN(qp, dqp, n);
-  if (qn) DOWN(qn, dqn, n);
-  if (cm && cv) { DOWN(cm, dcm, n * 7); DOWN(cv, dcv, n * 7); }
-  if (planes) DOWN(planes, dpl, n * 84);
-  if (fm && fv) { DOWN(fm, dfm, n); DOWN(fv, dfv, n); }
-  return 0;
+// ------------------------------------------------------------------------------------------------
+// The host loop of self_play() (self_play.rs:60-129 spawns threads and waits for done_queue; here
+// the host only sequences two kinds of GPU work per engine):
+//     tree tick (our kernels)  ->  read n_rows from mapped host memory  ->  network graph for the
+//     smallest bucket >= n_rows (a cudaGraphExec_t the caller captured, e.g. with torch)
+// With two engines (two half-batches on two streams) one engine's tree tick and host round trip
+// hide under the other engine's network.
+// ------------------------------------------------------------------------------------------------
+int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_nn_graph* const* graphs,
+                    const uint32_t* n_graphs, void* const* streams, uint64_t max_ticks,
+                    uint32_t time_kernels_every, c4a0_run_report* out) {
+  if (!engines || !graphs || !n_graphs || !streams || !out || n_engines == 0 || n_engines > 8)
+    return fail(C4A0_E_INVALID, "bad argument");
+  memset(out, 0, sizeof(*out));
+  struct Lane {
+    c4a0_engine* e;
+    cudaStream_t s;
+    uint32_t expect;   // status tick the host waits for next
+    bool done;
+    cudaEvent_t t0, t1;
+  };
+  std::vector<Lane> lanes(n_engines);
+  std::vector<cudaEvent_t> kev;  // triples
+  for (uint32_t i = 0; i < n_engines; i++) {
+    c4a0_engine* e = engines[i];
+    if (!e || !e->have_requests) return fail(C4A0_E_INVALID, "engine %u has no requests", i);
+    if (n_graphs[i] == 0 || !graphs[i]) return fail(C4A0_E_INVALID, "engine %u has no network graphs", i);
+    for (uint32_t k = 0; k < n_graphs[i]; k++) {
+      if (!graphs[i][k].graph_exec) return fail(C4A0_E_INVALID, "null graph_exec");
+      if (k && graphs[i][k].rows <= graphs[i][k - 1].rows) return fail(C4A0_E_INVALID, "network graphs must be sorted by rows");
+    }
+    if (graphs[i][n_graphs[i] - 1].rows < e->D.n_slots)
+      return fail(C4A0_E_INVALID, "the largest network graph must cover n_slots rows");
+    lanes[i] = Lane{e, (cudaStream_t)streams[i], e->h_status->tick, e->n_req == 0, nullptr, nullptr};
+    CK(cudaEventCreate(&lanes[i].t0));
+    CK(cudaEventCreate(&lanes[i].t1));
+  }
+  auto cleanup = [&]() {
+    for (auto& L : lanes) {
+      if (L.t0) cudaEventDestroy(L.t0);
+      if (L.t1) cudaEventDestroy(L.t1);
+    }
+    for (auto ev : kev) cudaEventDestroy(ev);
+  };
+  auto wall0 = std::chrono::steady_clock::now();
+  int rc = 0;
+  // prime: the planes of the initial roots are already packed (set_requests) -> first network call
+  auto launch_nn = [&](uint32_t i) -> int {
+    Lane& L = lanes[i];
+    uint32_t rows = L.e->h_status->n_rows;
+    const c4a0_nn_graph* g = graphs[i];
+    uint32_t k = 0;
+    while (k + 1 < n_graphs[i] && g[k].rows < rows) k++;
+    CK(cudaGraphLaunch((cudaGraphExec_t)g[k].graph_exec, L.s));
+    out->nn_launches++;
+    out->nn_rows_launched += g[k].rows;
+    return 0;
+  };
+  auto launch_tree = [&](uint32_t i) -> int {
+    Lane& L = lanes[i];
+    cudaEvent_t* ev = nullptr;
+    if (time_kernels_every && (L.e->steps % time_kernels_every) == 0 && kev.size() < 3 * 4096) {
+      size_t b = kev.size();
+      for (int q = 0; q < 3; q++) {
+        cudaEvent_t x;
+        CK(cudaEventCreate(&x));
+        kev.push_back(x);
+      }
+      ev = &kev[b];
+    }
+    int r = launch_tick(L.e, L.s, ev);
+    if (r) return r;
+    L.expect++;
+    out->ticks++;
+    return 0;
+  };
+  for (uint32_t i = 0; i < n_engines && !rc; i++) {
+    Lane& L = lanes[i];
+    CK(cudaEventRecord(L.t0, L.s));
+    if (L.done) continue;
+    rc = launch_nn(i);
+    if (!rc) rc = launch_tree(i);
+  }
+  uint32_t remaining = 0;
+  for (auto& L : lanes) remaining += L.done ? 0 : 1;
+  uint32_t cur = 0;
+  while (remaining && !rc) {
+    Lane& L = lanes[cur];
+    if (!L.done) {
+      // wait for the tick's status (k_scan wrote it through mapped memory)
+      uint64_t spins = 0;
+      while (L.e->h_status->tick != L.expect) {
+        if (++spins > 2000) {
+          if (cudaStreamQuery(L.s) == cudaSuccess && L.e->h_status->tick != L.expect) {
+            rc = fail(C4A0_E_CUDA, "tick status never arrived (stream idle)");
+            break;
+          }
+          std::this_thread::yield();
+        }
+      }
+      if (rc) break;
+      std::atomic_thread_fence(std::memory_order_acquire);
+      if (L.e->h_status->error) {
+        rc = fail(C4A0_E_ENGINE, "%s", kEngineErr);
+        break;
+      }
+      if (L.e->h_status->n_finished >= L.e->n_req) {
+        L.done = true;
+        remaining--;
+        CK(cudaEventRecord(L.t1, L.s));
+      } else if (max_ticks && out->ticks >= max_ticks) {
+        rc = fail(C4A0_E_INVALID, "max_ticks reached before all games finished");
+        break;
+      } else {
+        rc = launch_nn(cur);
+        if (!rc) rc = launch_tree(cur);
+      }
+    }
+    cur = (cur + 1) % n_engines;
+  }
+  for (auto& L : lanes) {
+    if (rc) break;
+    if (L.e->n_req == 0) CK(cudaEventRecord(L.t1, L.s));
+  }
+  for (auto& L : lanes) cudaStreamSynchronize(L.s);
+  if (!rc) {
+    float mx = 0;
+    for (auto& L : lanes) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, L.t0, L.t1) == cudaSuccess && ms > mx) mx = ms;
+    }
+    out->device_ms = mx;
+    double a = 0, b = 0;
+    uint32_t n = 0;
+    for (size_t q = 0; q + 2 < kev.size(); q += 3) {
+      float x = 0, y = 0;
+      if (cudaEventElapsedTime(&x, kev[q], kev[q + 1]) == cudaSuccess &&
+          cudaEventElapsedTime(&y, kev[q + 1], kev[q + 2]) == cudaSuccess) {
+        a += x;
+        b += y;
+        n++;
+      }
+    }
+    out->kernel_samples = n;
+    out->k_step_ms_sum = a;
+    out->k_move_ms_sum = b;
+  }
+  out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  cleanup();
+  return rc;
 }
-
-int c4a0_math_batch(int device, int op, const float* in, float* out, size_t n) {
-  if (!in || !out) return fail(C4A0_E_INVALID, "null argument");
-  if (op != C4A0_MATH_LOGF && op != C4A0_MATH_EXPF) return fail(C4A0_E_INVALID, "bad op");
-  BATCH_PROLOGUE();
-  if (n == 0) return 0;
-  DevBuf<float> di, dout;
-  UP(di, in, n);
-  CK(dout.alloc(n));
-  k_math<<<blocks_for(n, 256), 256>>>(op, di.p, dout.p, n);
-  CK(cudaGetLastError());
-  DOWN(out, dout, n);
-  return 0;
-}
-
-int c4a0_softmax_batch(int device, const float* logits, const uint32_t* legal, float* out, size_t n) {
-  if (!logits || !legal || !out) return fail(C4A0_E_INVALID, "null argument");
-  BATCH_PROLOGUE();
-  if (n == 0) return 0;
-  DevBuf<float> dl, dout;
-  DevBuf<uint32_t> dg;
-  UP(dl, logits, n * 7);
-  UP(dg, legal, n);
-  CK(dout.alloc(n * 7));
-  k_softmax<<<blocks_for(n, 128), 128>>>(dl.p, dg.p, dout.p, n);
-  CK(cudaGetLastError());
-  DOWN(out, dout, n * 7);
-  return 0;
-}
-
-int c4a0_sample_batch(int device, const float* policy, const float* temperature, const uint64_t* seed,
-                      float* tempered, int32_t* column, size_t n) {
-  if (!policy || !temperature || !seed || !tempered || !column) return fail(C4A0_E_INVALID, "null argument");
-  BATCH_PROLOGUE();
-  if (n == 0) return 0;
-  DevBuf<float> dp, dt, dtemp;
-  DevBuf<uint64_t> ds;
-  DevBuf<int32_t> dc;
-  UP(dp, policy, n * 7);
-  UP(dt, temperature, n);
-  UP(ds, seed, n);
-  CK(dtemp.alloc(n * 7));
-  CK(dc.alloc(n));
-  k_sample<<<blocks_for(n, 128), 128>>>(dp.p, dt.p, ds.p, dtemp.p, dc.p, n);
-  CK(cudaGetLastError());
-  DOWN(tempered, dtemp, n * 7);
-  DOWN(column, dc, n);
-  return 0;
-}
-
-// ---- host builds of the shared math (CPU test-suite) ----------------------------------------------
-void c4a0_host_logf(const float* in, float* out, size_t n) {
-  for (size_t i = 0; i < n; i++) out[i] = c4::c4_logf(in[i]);
-}
-void c4a0_host_expf(const float* in, float* out, size_t n) {
-  for (size_t i = 0; i < n; i++) out[i] = c4::c4_expf(in[i]);
-}
-int c4a0_host_sample(const float* policy, float temperature, uint64_t seed, float* tempered) {
-  float t[7];
-  c4::apply_temperature7(policy, temperature, t);
-  if (tempered)
-    for (int i = 0; i < 7; i++) tempered[i] = t[i];
-  return c4::weighted_sample7(t, seed);
-}
-int c4a0_host_terminal_state(uint64_t mask, uint64_t value) { return c4::terminal_state(Pos{mask, value}); }
-void c4a0_host_make_move(uint64_t mask, uint64_t value, int col, uint64_t* om, uint64_t* ov) {
-  Pos r = c4::make_move(Pos{mask, value}, col);
-  *om = r.mask;
-  *ov = r.value;
-}
-
-void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t* om, uint64_t* ov) {
-  Pos r = c4::flip_h(Pos{mask, value});
-  *om = r.mask;
-  *ov = r.value;
-}
-void c4a0_host_shuffle(uint64_t seed, uint32_t* idx, size_t n) { c4::shuffle_indices(seed, idx, n); }
 
 }  // extern "C"

@@ -40,11 +40,14 @@ class Engine:
         plane_dtype: int = L.PLANES_F32,
         max_inline_sims: int = 0,
         device: int = 0,
+        plane_stride: int = 0,
+        flags: int = 0,
     ):
         self._lib = L.lib()
         self._h = C.c_void_p()
         self.cfg = L.Config(
-            n_slots, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, max_inline_sims, device
+            n_slots, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, max_inline_sims, device,
+            plane_stride, flags,
         )
         L.check(self._lib.c4a0_engine_create(C.byref(self.cfg), C.byref(self._h)))
         self.n_slots = n_slots
@@ -105,14 +108,16 @@ class Engine:
         L.check(self._lib.c4a0_engine_stats(self._h, C.byref(s), stream))
         return s.as_dict()
 
-    def fetch_rows(self, stream: int = 0, want_models: bool = True):
+    def fetch_rows(self, stream: int = 0):
+        """(n_rows, leaf_mask[n_rows], leaf_value[n_rows], model_id[n_rows]) of the live rows."""
         S = self.n_slots
-        state = np.empty(S, np.uint32)
+        n = C.c_uint32(0)
         mask = np.empty(S, np.uint64)
         value = np.empty(S, np.uint64)
-        model = np.empty(S, np.uint64) if want_models else None
-        L.check(self._lib.c4a0_engine_fetch_rows(self._h, L.ptr(state), L.ptr(mask), L.ptr(value), L.ptr(model), stream))
-        return state, mask, value, model
+        model = np.empty(S, np.uint64)
+        L.check(self._lib.c4a0_engine_fetch_rows(self._h, C.byref(n), L.ptr(mask), L.ptr(value), L.ptr(model), stream))
+        k = int(n.value)
+        return k, mask[:k], value[:k], model[:k]
 
     def fetch_results(self, first: int = 0, n: Optional[int] = None, stream: int = 0) -> GameSamples:
         if n is None:
@@ -152,6 +157,20 @@ class Engine:
         buf = np.zeros(need.value, np.uint32)
         L.check(self._lib.c4a0_engine_dump_tree(self._h, slot, L.ptr(buf), buf.size, C.byref(need), stream))
         return buf
+
+
+def run_engines(engines: Sequence["Engine"], graphs: Sequence[Sequence[Tuple[int, int]]], streams: Sequence[int],
+                max_ticks: int = 0, time_kernels_every: int = 0) -> dict:
+    """c4a0_engine_run(): graphs[i] = [(rows, cudaGraphExec_t as int), ...] sorted by rows."""
+    n = len(engines)
+    handles = (C.c_void_p * n)(*[e._h for e in engines])
+    arrays = [(L.NNGraph * len(g))(*[L.NNGraph(r, h) for r, h in g]) for g in graphs]
+    gptr = (C.c_void_p * n)(*[C.cast(a, C.c_void_p) for a in arrays])
+    counts = (C.c_uint32 * n)(*[len(g) for g in graphs])
+    st = (C.c_void_p * n)(*streams)
+    rep = L.RunReport()
+    L.check(L.lib().c4a0_engine_run(handles, n, gptr, counts, st, max_ticks, time_kernels_every, C.byref(rep)))
+    return rep.as_dict()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -107,3 +107,165 @@ class ConnectFourNet(nn.Module):
             elif isinstance(m, nn.Linear):
                 total += 2 * m.in_features * m.out_features
         return total
+
+
+# ------------------------------------------------------------------------------------------------
+# Inference form: the same function as a short chain of GEMMs
+# ------------------------------------------------------------------------------------------------
+def _conv_as_matrix(conv: nn.Conv2d):
+    """A 3x3/pad-1 convolution on the fixed 6x7 board is a linear map R^{Cin*42} -> R^{Cout*42}:
+    returns (M [Cin*42, Cout*42], bias [Cout*42]) in float64, exact (zero padding included)."""
+    cin, cout = conv.in_channels, conv.out_channels
+    w = conv.weight.detach().double()
+    eye = torch.eye(cin * 42, dtype=torch.float64, device=w.device).reshape(cin * 42, cin, N_ROWS, N_COLS)
+    m = torch.nn.functional.conv2d(eye, w, None, conv.stride, conv.padding).reshape(cin * 42, cout * 42)
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(cout, dtype=torch.float64, device=w.device)
+    return m, b.repeat_interleave(42)
+
+
+def _bn_scale_shift(bn, repeat: int = 1):
+    """Eval-mode BatchNorm as y = x * s + t (float64)."""
+    s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    t = bn.bias.detach().double() - bn.running_mean.detach().double() * s
+    return s.repeat_interleave(repeat), t.repeat_interleave(repeat)
+
+
+class FoldedNet(nn.Module):
+    """Inference-only restatement of a trained/initialised `ConnectFourNet` as dense GEMMs.
+
+    Same function, same weights, evaluated in an order that suits tensor cores:
+      * every convolution acts on a fixed 6x7 board, so it is a constant matrix; eval-mode
+        BatchNorm is an affine map and folds into the layer before it;
+      * the reference's residual block is x + relu(bn(conv(conv(x)))) with NO nonlinearity between
+        its two convolutions (src/c4a0/nn.py:184-195), so the pair is one matrix; for the first
+        block, whose input is itself affine in the 84 input planes, block-input and
+        block-preactivation come out of ONE [B,84(+pad)] x [84, 2*F] GEMM;
+      * the first hidden layers of the policy and value heads read the same activations and are
+        concatenated into one GEMM.
+    For the default net (1 block x 32 filters) a forward pass is 7 GEMMs, 4 of them 1344-wide.
+    Outputs match the module form to rounding (tests/test_nn_fold.py); PyTorch (cuBLASLt) stays
+    the runtime — this class only reorganises the weights at load time.
+    `in_features` is the padded input width (a multiple of 8 so bf16 rows are 16-byte aligned);
+    the engine writes its planes with that row stride.
+    """
+
+    IN_PAD = 96
+
+    def __init__(self, model: ConnectFourNet, dtype: torch.dtype = torch.bfloat16, device=None):
+        super().__init__()
+        model = model.eval()
+        device = device if device is not None else next(model.parameters()).device
+        F = model.fc_size
+        self.F, self.dtype = F, dtype
+        layers = list(model.conv.children())
+        stem, blocks = layers[0], layers[1:]
+        w_in, b_in = _conv_as_matrix(stem)  # x = planes @ w_in + b_in   [84 -> F]
+
+        def block_affine(blk):
+            ca, cb, bn, act = list(blk.block.children())
+            assert isinstance(ca, nn.Conv2d) and isinstance(cb, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d)
+            assert isinstance(act, nn.ReLU)
+            ma, ba = _conv_as_matrix(ca)
+            mb, bb = _conv_as_matrix(cb)
+            s, t = _bn_scale_shift(bn, 42)
+            return (ma @ mb) * s[None, :], (ba @ mb + bb) * s + t
+
+        def reg(name, t):
+            self.register_buffer(name, t.to(device=device, dtype=dtype).contiguous(), persistent=False)
+
+        self.n_blocks = len(blocks)
+        if blocks:
+            wb, bb_ = block_affine(blocks[0])
+            w0 = torch.cat([w_in @ wb, w_in], dim=1)  # [84, 2F]: block pre-activation | block input
+            b0 = torch.cat([b_in @ wb + bb_, b_in])
+        else:
+            w0, b0 = w_in, b_in
+        w0p = torch.zeros(self.IN_PAD, w0.shape[1], dtype=torch.float64, device=w0.device)
+        w0p[:84] = w0
+        reg("w0", w0p)
+        reg("b0", b0)
+        for j, blk in enumerate(blocks[1:], start=1):
+            wj, bj = block_affine(blk)
+            reg(f"wblk{j}", wj)
+            reg(f"bblk{j}", bj)
+
+        def head_layers(seq):
+            hidden, final = [], None
+            for m in seq.children():
+                if isinstance(m, nn.Sequential):
+                    lin, bn, act = list(m.children())
+                    s, t = _bn_scale_shift(bn)
+                    w = lin.weight.detach().double().t() * s[None, :]
+                    b = lin.bias.detach().double() * s + t
+                    hidden.append((w, b))
+                elif isinstance(m, nn.Linear):
+                    final = (m.weight.detach().double().t(), m.bias.detach().double())
+            return hidden, final
+
+        ph, pf = head_layers(model.fc_policy)
+        vh, vf = head_layers(model.fc_value)
+        self.joint_first = bool(ph) and bool(vh)
+        if self.joint_first:
+            reg("wh0", torch.cat([ph[0][0], vh[0][0]], dim=1))
+            reg("bh0", torch.cat([ph[0][1], vh[0][1]]))
+            ph, vh = ph[1:], vh[1:]
+        self.n_p, self.n_v = len(ph), len(vh)
+        for i, (w, b) in enumerate(ph):
+            reg(f"wp{i}", w)
+            reg(f"bp{i}", b)
+        for i, (w, b) in enumerate(vh):
+            reg(f"wv{i}", w)
+            reg(f"bv{i}", b)
+        # final layers, output width padded to 8 columns
+        dev0 = pf[0].device
+        wpf = torch.zeros(F, 8, dtype=torch.float64, device=dev0)
+        wpf[:, :7] = pf[0]
+        bpf = torch.zeros(8, dtype=torch.float64, device=dev0)
+        bpf[:7] = pf[1]
+        wvf = torch.zeros(F, 8, dtype=torch.float64, device=dev0)
+        wvf[:, :2] = vf[0]
+        bvf = torch.zeros(8, dtype=torch.float64, device=dev0)
+        bvf[:2] = vf[1]
+        reg("wpf", wpf)
+        reg("bpf", bpf)
+        reg("wvf", wvf)
+        reg("bvf", bvf)
+        self._flops = None
+
+    @staticmethod
+    def _lin_relu(x, w, b):
+        if x.is_cuda:
+            return torch._addmm_activation(b, x, w)  # cuBLASLt bias+ReLU epilogue
+        return torch.relu(torch.addmm(b, x, w))
+
+    def forward(self, planes: torch.Tensor):
+        """planes: [B, IN_PAD] (engine layout, zero padded) or [B,2,6,7]."""
+        if planes.dim() == 4:
+            x0 = planes.new_zeros(planes.shape[0], self.IN_PAD)
+            x0[:, :84] = planes.reshape(planes.shape[0], 84)
+        else:
+            x0 = planes
+        F = self.F
+        z = torch.addmm(self.b0, x0, self.w0)
+        h = torch.relu(z[:, :F]) + z[:, F:] if self.n_blocks else z
+        for j in range(1, self.n_blocks):
+            h = self._lin_relu(h, getattr(self, f"wblk{j}"), getattr(self, f"bblk{j}")) + h
+        if self.joint_first:
+            y = self._lin_relu(h, self.wh0, self.bh0)
+            hp, hv = y[:, :F], y[:, F:]
+        else:
+            hp = hv = h
+        for i in range(self.n_p):
+            hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
+        for i in range(self.n_v):
+            hv = self._lin_relu(hv, getattr(self, f"wv{i}"), getattr(self, f"bv{i}"))
+        logits = torch.addmm(self.bpf, hp, self.wpf)[:, :7].float()
+        q = torch.tanh(torch.addmm(self.bvf, hv, self.wvf)[:, :2].float())
+        return torch.log_softmax(logits, dim=1), q[:, 0], q[:, 1]
+
+    def flops_per_position(self) -> int:
+        total = 0
+        for name, t in self.named_buffers():
+            if name.startswith("w"):
+                total += 2 * t.shape[0] * t.shape[1]
+        return total

@@ -1,49 +1,71 @@
-"""Lockstep self-play driver: the engine's tree kernels + a PyTorch network on one CUDA stream.
+"""Lockstep self-play driver: the engine's tree kernels + a PyTorch network on CUDA streams.
 
 This is the B200 replacement for the thread/channel machinery of rust/src/self_play.rs:39-246
-(`self_play`, `NNThread`).  There the NN thread collects leaf positions from a queue, builds a
-numpy batch, calls Python, and fans results back through another queue; here a *tick* is
+(`self_play`, `NNThread`).  There the NN thread collects leaf positions from a queue, de-duplicates
+them, builds a numpy batch, calls Python, and fans results back through another queue; here a
+*tick* is
 
-    network(planes) -> logits, q_penalty, q_no_penalty        (PyTorch, bf16 or fp32)
-    engine.step()   -> expand + backup + move + select, writes the next planes   (our kernels)
+    network(planes[:B]) -> logits, q_penalty, q_no_penalty     (PyTorch, bf16 or fp32, CUDA graph)
+    engine tick         -> expand + backup + move + select + dedup/pack the next planes (our kernels)
 
-on the same device buffers, captured once into a CUDA graph and replayed until every game has
-finished.  The host only polls a progress counter every `poll_every` ticks.
+on the same device buffers.  The network is captured once per batch-size bucket into CUDA graphs;
+the C++ host loop (`c4a0_engine_run`) then alternates tree ticks and the smallest graph that covers
+the tick's live rows until every game has finished — no Python in the loop.  With `n_lanes=2` the
+games are split over two engines on two streams, so one half's tree tick hides under the other
+half's network.
 
 Two evaluator contracts are supported:
-  * device evaluators (fast path): `fn(planes: cuda Tensor[B,2,6,7]) -> (policy[B,7], qp[B], qn[B])`
-    cuda tensors — e.g. a `c4a0_b200.nn.ConnectFourNet` wrapped in `DeviceEvaluator`;
+  * device evaluators (fast path): `fn(planes: cuda Tensor[B, stride]) -> (policy[B,7], qp[B], qn[B])`
+    cuda tensors — `DeviceEvaluator.from_model(ConnectFourNet)` builds the GEMM-folded form;
   * the reference's numpy callback `cb(model_id, ndarray[B,2,6,7]) -> (policy, qp, qn)`
-    (rust/src/pybridge.rs:161-199), served by `run_callback` with host copies every tick.
+    (rust/src/pybridge.rs:161-199), served by `play_callback` with host copies every tick.
 """
 
 from __future__ import annotations
 
 import time
 from dataclasses import dataclass, field
-from typing import Callable, Dict, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import Engine, GameSamples
-
+from .engine import Engine, GameSamples, run_engines
 
 # process-wide defaults, overridable by tools (bench.py turns kernel sampling on)
-DEFAULTS = {"use_cuda_graph": True, "poll_every": 64, "sample_kernels_every": 0}
+DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 2, "dedup": True}
+
+BUCKETS = (128, 256, 512, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072)
 
 
 class DeviceEvaluator:
-    """Marks a callable as device-capable: planes (cuda tensor) in, three cuda tensors out."""
+    """A network the engine can call without leaving the GPU.
 
-    def __init__(self, module_or_fn, dtype: torch.dtype = torch.float32):
+    fn(planes) receives a cuda tensor [B, plane_stride] (plane_stride == 84: viewed as [B,2,6,7])
+    of dtype `dtype` and returns (policy [B,7], q_penalty [B], q_no_penalty [B]) cuda tensors.
+    """
+
+    def __init__(self, module_or_fn, dtype: torch.dtype = torch.float32, plane_stride: int = 84):
         self.fn = module_or_fn
         self.dtype = dtype
+        self.plane_stride = plane_stride
         if isinstance(module_or_fn, torch.nn.Module):
             module_or_fn.eval()
 
+    @classmethod
+    def from_model(cls, model, dtype: torch.dtype = torch.bfloat16, fold: bool = True) -> "DeviceEvaluator":
+        """ConnectFourNet -> evaluator.  fold=True uses the GEMM-folded inference form (nn.FoldedNet)."""
+        from .nn import ConnectFourNet, FoldedNet
+
+        if fold and isinstance(model, ConnectFourNet):
+            return cls(FoldedNet(model, dtype=dtype), dtype, FoldedNet.IN_PAD)
+        p = next(model.parameters(), None)
+        return cls(model, p.dtype if p is not None else dtype, 84)
+
     def __call__(self, planes: torch.Tensor):
+        if self.plane_stride == 84 and planes.dim() == 2:
+            planes = planes.view(-1, 2, 6, 7)
         return self.fn(planes)
 
 
@@ -51,14 +73,71 @@ class DeviceEvaluator:
 class RunInfo:
     ticks: int = 0
     wall_s: float = 0.0
-    device_s: float = 0.0  # CUDA-event time of the tick loop (first tick .. all games finished)
+    device_s: float = 0.0  # CUDA-event time of the search (first network launch .. last game finished)
     stats: dict = field(default_factory=dict)
     kernel_ms: dict = field(default_factory=dict)  # sampled k_step / k_move durations
     engine_bytes: int = 0
+    report: dict = field(default_factory=dict)
+    n_lanes: int = 1
+
+
+def _sum_stats(stats: List[dict]) -> dict:
+    out = {}
+    for s in stats:
+        for k, v in s.items():
+            out[k] = out.get(k, 0) + v
+    return out
+
+
+class _Lane:
+    """One engine + its NN I/O tensors + its stream."""
+
+    def __init__(self, n_slots, max_requests, n_iter, c_expl, c_pen, plane_dtype, device, max_inline, stride, flags):
+        self.n_slots = n_slots
+        self.engine = Engine(
+            n_slots, max(1, max_requests), n_iter, c_expl, c_pen,
+            L.PLANES_BF16 if plane_dtype == torch.bfloat16 else L.PLANES_F32, max_inline, device.index, stride, flags,
+        )
+        self.planes = torch.zeros(n_slots, stride, dtype=plane_dtype, device=device)
+        self.logits = torch.zeros(n_slots, 7, dtype=torch.float32, device=device)
+        self.qp = torch.zeros(n_slots, dtype=torch.float32, device=device)
+        self.qn = torch.zeros(n_slots, dtype=torch.float32, device=device)
+        self.engine.bind_io(self.planes.data_ptr(), self.logits.data_ptr(), self.qp.data_ptr(), self.qn.data_ptr())
+        self.stream = torch.cuda.Stream(device=device)
+        self.graphs = {}  # rows -> torch.cuda.CUDAGraph
+        self.graph_key = None
+        self.pool = None
+
+    def evaluate(self, evaluator, rows: int) -> None:
+        with torch.no_grad():
+            pol, a, b = evaluator(self.planes[:rows])
+            self.logits[:rows].copy_(pol.reshape(rows, 7))
+            self.qp[:rows].copy_(a.reshape(rows))
+            self.qn[:rows].copy_(b.reshape(rows))
+
+    def capture(self, evaluator) -> List[Tuple[int, int]]:
+        key = id(evaluator)
+        if self.graph_key != key:
+            self.graphs, self.graph_key = {}, key
+            self.pool = torch.cuda.graph_pool_handle()
+            sizes = [b for b in BUCKETS if b < self.n_slots] + [self.n_slots]
+            with torch.cuda.stream(self.stream):
+                for rows in reversed(sizes):  # largest first: the shared pool is sized once
+                    self.evaluate(evaluator, rows)  # eager warm-up (cuBLAS handles, heuristics)
+                    self.stream.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=self.pool, stream=self.stream):
+                        self.evaluate(evaluator, rows)
+                    self.graphs[rows] = g
+        return [(rows, self.graphs[rows].raw_cuda_graph_exec()) for rows in sorted(self.graphs)]
+
+    def close(self):
+        self.graphs = {}
+        self.engine.close()
 
 
 class SelfPlaySession:
-    """Owns one engine + its NN I/O tensors on one GPU; reusable across play() calls."""
+    """Owns the engine(s) + NN I/O tensors on one GPU; reusable across play() calls."""
 
     def __init__(
         self,
@@ -70,107 +149,151 @@ class SelfPlaySession:
         plane_dtype: torch.dtype = torch.float32,
         device: int = 0,
         max_inline_sims: int = 0,
+        plane_stride: int = 84,
+        n_lanes: Optional[int] = None,
+        dedup: Optional[bool] = None,
     ):
         if not torch.cuda.is_available():
             raise RuntimeError("c4a0_b200 needs a CUDA device: there is no CPU fallback")
         if plane_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("plane_dtype must be float32 or bfloat16")
+        n_lanes = DEFAULTS["n_lanes"] if n_lanes is None else n_lanes
+        dedup = DEFAULTS["dedup"] if dedup is None else dedup
+        if n_slots < 2 * 256:
+            n_lanes = 1  # tiny batches: nothing to overlap
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.n_slots = n_slots
         self.plane_dtype = plane_dtype
-        self.engine = Engine(
-            n_slots, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty,
-            L.PLANES_BF16 if plane_dtype == torch.bfloat16 else L.PLANES_F32, max_inline_sims, device,
-        )
-        self.planes = torch.zeros(n_slots, 2, 6, 7, dtype=plane_dtype, device=self.device)
-        self.logits = torch.zeros(n_slots, 7, dtype=torch.float32, device=self.device)
-        self.qp = torch.zeros(n_slots, dtype=torch.float32, device=self.device)
-        self.qn = torch.zeros(n_slots, dtype=torch.float32, device=self.device)
-        self.engine.bind_io(self.planes.data_ptr(), self.logits.data_ptr(), self.qp.data_ptr(), self.qn.data_ptr())
-        self.stream = torch.cuda.Stream(device=self.device)
-        self._graph = None
-        self._graph_key = None
+        self.plane_stride = plane_stride
+        flags = 0 if dedup else L.FLAG_NO_DEDUP
+        per = [(n_slots + i) // n_lanes for i in range(n_lanes)][::-1]
+        self.lanes = [
+            _Lane(s, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, self.device,
+                  max_inline_sims, plane_stride, flags)
+            for s in per if s > 0
+        ]
+
+    # single-lane conveniences used by tests
+    @property
+    def engine(self) -> Engine:
+        return self.lanes[0].engine
+
+    @property
+    def planes(self):
+        return self.lanes[0].planes
+
+    @property
+    def logits(self):
+        return self.lanes[0].logits
+
+    @property
+    def qp(self):
+        return self.lanes[0].qp
+
+    @property
+    def qn(self):
+        return self.lanes[0].qn
+
+    @property
+    def stream(self):
+        return self.lanes[0].stream
 
     def close(self):
-        self._graph = None
-        self.engine.close()
+        for ln in self.lanes:
+            ln.close()
+
+    def _split(self, n_req: int) -> List[Tuple[int, int]]:
+        """Contiguous request ranges per lane, proportional to the lanes' slot counts."""
+        total = sum(ln.n_slots for ln in self.lanes)
+        out, lo = [], 0
+        for i, ln in enumerate(self.lanes):
+            hi = n_req if i == len(self.lanes) - 1 else lo + (n_req * ln.n_slots) // total
+            out.append((lo, hi))
+            lo = hi
+        return out
 
     # ------------------------------------------------------------------------------------------
-    def _tick(self, evaluator) -> None:
-        with torch.no_grad():
-            pol, a, b = evaluator(self.planes)
-            self.logits.copy_(pol.reshape(self.n_slots, 7))
-            self.qp.copy_(a.reshape(self.n_slots))
-            self.qn.copy_(b.reshape(self.n_slots))
-        self.engine.step(torch.cuda.current_stream().cuda_stream)
-
     def play(
         self,
         game_id: Sequence[int],
         player0_id: Sequence[int],
         player1_id: Sequence[int],
         evaluator: Callable,
-        use_cuda_graph: Optional[bool] = None,
+        host_loop: Optional[str] = None,
         poll_every: Optional[int] = None,
         sample_kernels_every: Optional[int] = None,
         fetch: bool = True,
     ) -> Tuple[Optional[GameSamples], RunInfo]:
-        """Play all requested games; returns host samples (request order) and run information."""
-        use_cuda_graph = DEFAULTS["use_cuda_graph"] if use_cuda_graph is None else use_cuda_graph
+        """Play all requested games; returns host samples (request order) and run information.
+
+        host_loop = "native": bucketed CUDA graphs driven by the C++ loop (c4a0_engine_run);
+                    "python": eager network calls and engine.step() from Python (any callable)."""
+        host_loop = DEFAULTS["host_loop"] if host_loop is None else host_loop
         poll_every = DEFAULTS["poll_every"] if poll_every is None else poll_every
         sample_kernels_every = DEFAULTS["sample_kernels_every"] if sample_kernels_every is None else sample_kernels_every
-        info = RunInfo(engine_bytes=self.engine.device_bytes)
-        n_req = len(game_id)
+        gid = np.ascontiguousarray(game_id, dtype=np.uint64)
+        p0 = np.ascontiguousarray(player0_id, dtype=np.uint64)
+        p1 = np.ascontiguousarray(player1_id, dtype=np.uint64)
+        n_req = len(gid)
+        info = RunInfo(engine_bytes=sum(ln.engine.device_bytes for ln in self.lanes), n_lanes=len(self.lanes))
         t0 = time.perf_counter()
-        with torch.cuda.stream(self.stream):
-            s = self.stream.cuda_stream
-            self.engine.set_requests(game_id, player0_id, player1_id, s)
+        ranges = self._split(n_req)
+        for ln, (lo, hi) in zip(self.lanes, ranges):
+            ln.engine.set_requests(gid[lo:hi], p0[lo:hi], p1[lo:hi], ln.stream.cuda_stream)
+        if host_loop == "native":
+            graphs = [ln.capture(evaluator) for ln in self.lanes]
+            rep = run_engines(
+                [ln.engine for ln in self.lanes], graphs, [ln.stream.cuda_stream for ln in self.lanes], 0,
+                sample_kernels_every,
+            )
+            info.report = rep
+            info.ticks = int(rep["ticks"])
+            info.device_s = rep["device_ms"] / 1e3
+            if rep["kernel_samples"]:
+                n = rep["kernel_samples"]
+                info.kernel_ms = {"k_step": rep["k_step_ms_sum"] / n, "k_move": rep["k_move_ms_sum"] / n, "samples": n}
+        elif host_loop == "python":
             ev0 = torch.cuda.Event(enable_timing=True)
             ev1 = torch.cuda.Event(enable_timing=True)
-            ev0.record(self.stream)
-            ticks = 0
-            finished = n_req == 0
-            graph = None
-            if use_cuda_graph and not finished:
-                key = id(evaluator)
-                if self._graph is None or self._graph_key != key:
-                    for _ in range(3):  # real ticks; also warms cuBLAS/cuDNN before capture
-                        self._tick(evaluator)
+            ev0.record(self.lanes[0].stream)
+            ks, km, kn, ticks = 0.0, 0.0, 0, 0
+            live = [hi > lo for lo, hi in ranges]
+            while any(live):
+                for _ in range(poll_every):
+                    for ln, alive in zip(self.lanes, live):
+                        if not alive:
+                            continue
+                        with torch.cuda.stream(ln.stream):
+                            ln.evaluate(evaluator, ln.n_slots)
+                            if sample_kernels_every and ticks % sample_kernels_every == 0:
+                                x, y = ln.engine.step_timed(ln.stream.cuda_stream)
+                                ks, km, kn = ks + x, km + y, kn + 1
+                            else:
+                                ln.engine.step(ln.stream.cuda_stream)
                         ticks += 1
-                    self.stream.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=self.stream):
-                        self._tick(evaluator)
-                    self._graph, self._graph_key = g, key
-                graph = self._graph
-            ks, km, kn = 0.0, 0.0, 0
-            while not finished:
-                for i in range(poll_every):
-                    if sample_kernels_every and (ticks % sample_kernels_every) == 0:
-                        # an eager tick whose two engine kernels are bracketed by CUDA events
-                        with torch.no_grad():
-                            pol, a, b = evaluator(self.planes)
-                            self.logits.copy_(pol.reshape(self.n_slots, 7))
-                            self.qp.copy_(a.reshape(self.n_slots))
-                            self.qn.copy_(b.reshape(self.n_slots))
-                        x, y = self.engine.step_timed(s)
-                        ks, km, kn = ks + x, km + y, kn + 1
-                    elif graph is not None:
-                        graph.replay()
-                    else:
-                        self._tick(evaluator)
-                    ticks += 1
-                p = self.engine.poll(s)
-                finished = p.n_finished >= n_req
-            ev1.record(self.stream)
-            self.stream.synchronize()
+                for i, ln in enumerate(self.lanes):
+                    if live[i]:
+                        p = ln.engine.poll(ln.stream.cuda_stream)
+                        live[i] = p.n_finished < p.n_requests
+            for ln in self.lanes:
+                ln.stream.synchronize()
+            ev1.record(self.lanes[0].stream)
+            ev1.synchronize()
             info.device_s = ev0.elapsed_time(ev1) / 1e3
             info.ticks = ticks
-            info.stats = self.engine.stats(s)
             if kn:
                 info.kernel_ms = {"k_step": ks / kn, "k_move": km / kn, "samples": kn}
-            out = self.engine.fetch_results(0, n_req, s) if fetch else None
+        else:
+            raise ValueError("host_loop must be 'native' or 'python'")
+        info.stats = _sum_stats([ln.engine.stats(ln.stream.cuda_stream) for ln in self.lanes])
+        out = None
+        if fetch:
+            parts = [ln.engine.fetch_results(0, hi - lo, ln.stream.cuda_stream) for ln, (lo, hi) in zip(self.lanes, ranges)]
+            out = GameSamples(*[
+                np.concatenate([getattr(p, f) for p in parts])
+                for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty")
+            ])
         info.wall_s = time.perf_counter() - t0
         return out, info
 
@@ -183,58 +306,52 @@ class SelfPlaySession:
         cb: Callable,
         max_nn_batch_size: int,
     ) -> Tuple[GameSamples, RunInfo]:
-        """The reference's numpy-callback contract (pybridge.rs:161-199): every tick the waiting
-        leaf positions are grouped by model id, de-duplicated (self_play.rs:203-208), cut into
-        batches of at most max_nn_batch_size and handed to `cb` on the host."""
+        """The reference's numpy-callback contract (pybridge.rs:161-199).  The engine has already
+        de-duplicated the waiting leaves per (position, model) (self_play.rs:203-208); every tick
+        the live rows are grouped by model id, cut into batches of at most max_nn_batch_size and
+        handed to `cb` on the host."""
         if self.plane_dtype != torch.float32:
             raise ValueError("the numpy callback path needs float32 planes")
-        info = RunInfo(engine_bytes=self.engine.device_bytes)
+        if len(self.lanes) != 1:
+            raise ValueError("the numpy callback path runs on one lane (n_lanes=1)")
+        ln = self.lanes[0]
+        info = RunInfo(engine_bytes=ln.engine.device_bytes)
         n_req = len(game_id)
         t0 = time.perf_counter()
-        S = self.n_slots
+        S = ln.n_slots
         h_logits = torch.zeros(S, 7, dtype=torch.float32).pin_memory()
         h_qp = torch.zeros(S, dtype=torch.float32).pin_memory()
         h_qn = torch.zeros(S, dtype=torch.float32).pin_memory()
-        with torch.cuda.stream(self.stream):
-            s = self.stream.cuda_stream
-            self.engine.set_requests(game_id, player0_id, player1_id, s)
+        with torch.cuda.stream(ln.stream):
+            s = ln.stream.cuda_stream
+            ln.engine.set_requests(game_id, player0_id, player1_id, s)
             ticks = 0
             while n_req:
-                state, mask, value, model = self.engine.fetch_rows(s)
-                waiting = np.nonzero(state == L.ROW_WAIT_NN)[0]
-                if waiting.size:
-                    planes = self.planes.cpu().numpy()
+                n_rows, _, _, model = ln.engine.fetch_rows(s)
+                if n_rows:
+                    planes = ln.planes[:n_rows, :84].cpu().numpy().reshape(n_rows, 2, 6, 7)
                     lg, a, b = h_logits.numpy(), h_qp.numpy(), h_qn.numpy()
-                    for mid in np.unique(model[waiting]):
-                        rows = waiting[model[waiting] == mid]
-                        keys = np.stack([mask[rows], value[rows]], axis=1)
-                        _, first, inverse = np.unique(keys, axis=0, return_index=True, return_inverse=True)
-                        inverse = inverse.reshape(-1)
-                        u_pol = np.empty((first.size, 7), np.float32)
-                        u_a = np.empty(first.size, np.float32)
-                        u_b = np.empty(first.size, np.float32)
-                        for lo in range(0, first.size, max_nn_batch_size):
-                            sel = first[lo : lo + max_nn_batch_size]
-                            batch = np.ascontiguousarray(planes[rows[sel]])
+                    for mid in np.unique(model):
+                        rows = np.nonzero(model == mid)[0]
+                        for lo in range(0, rows.size, max_nn_batch_size):
+                            sel = rows[lo : lo + max_nn_batch_size]
+                            batch = np.ascontiguousarray(planes[sel])
                             pol, qa, qb = cb(int(mid), batch)
                             pol = np.asarray(pol, dtype=np.float32)
                             if pol.shape != (sel.size, 7):
                                 raise ValueError(f"callback returned policy of shape {pol.shape}, expected {(sel.size, 7)}")
-                            u_pol[lo : lo + sel.size] = pol
-                            u_a[lo : lo + sel.size] = np.asarray(qa, dtype=np.float32).reshape(sel.size)
-                            u_b[lo : lo + sel.size] = np.asarray(qb, dtype=np.float32).reshape(sel.size)
-                        lg[rows] = u_pol[inverse]
-                        a[rows] = u_a[inverse]
-                        b[rows] = u_b[inverse]
-                    self.logits.copy_(h_logits, non_blocking=True)
-                    self.qp.copy_(h_qp, non_blocking=True)
-                    self.qn.copy_(h_qn, non_blocking=True)
-                self.engine.step(s)
+                            lg[sel] = pol
+                            a[sel] = np.asarray(qa, dtype=np.float32).reshape(sel.size)
+                            b[sel] = np.asarray(qb, dtype=np.float32).reshape(sel.size)
+                    ln.logits[:n_rows].copy_(h_logits[:n_rows], non_blocking=True)
+                    ln.qp[:n_rows].copy_(h_qp[:n_rows], non_blocking=True)
+                    ln.qn[:n_rows].copy_(h_qn[:n_rows], non_blocking=True)
+                ln.engine.step(s)
                 ticks += 1
-                if self.engine.poll(s).n_finished >= n_req:
+                if ln.engine.poll(s).n_finished >= n_req:
                     break
             info.ticks = ticks
-            info.stats = self.engine.stats(s)
-            out = self.engine.fetch_results(0, n_req, s)
+            info.stats = ln.engine.stats(s)
+            out = ln.engine.fetch_results(0, n_req, s)
         info.wall_s = time.perf_counter() - t0
         return out, info

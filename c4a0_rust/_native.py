@@ -336,18 +336,21 @@ def play_games(
     meta = np.array([(r.game_id, r.player0_id, r.player1_id) for r in reqs], dtype=np.uint64)
     n_slots = min(len(reqs), int(max_nn_batch_size))
     fast = isinstance(py_eval_pos_cb, (DeviceEvaluator, torch.nn.Module))
-    plane_dtype = torch.float32
     if fast:
         if isinstance(py_eval_pos_cb, torch.nn.Module):
             p = next(py_eval_pos_cb.parameters(), None)
-            py_eval_pos_cb = DeviceEvaluator(py_eval_pos_cb, p.dtype if p is not None else torch.float32)
-        plane_dtype = py_eval_pos_cb.dtype
+            py_eval_pos_cb = DeviceEvaluator.from_model(py_eval_pos_cb, p.dtype if p is not None else torch.float32)
         if len(np.unique(meta[:, 1:])) != 1:
             raise ValueError("the device fast path plays one model against itself; use the numpy callback for tournaments")
-    sess = SelfPlaySession(
-        n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
-        plane_dtype=plane_dtype, device=torch.cuda.current_device(),
-    )
+        sess = SelfPlaySession(
+            n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
+            plane_dtype=py_eval_pos_cb.dtype, device=torch.cuda.current_device(), plane_stride=py_eval_pos_cb.plane_stride,
+        )
+    else:
+        sess = SelfPlaySession(
+            n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
+            plane_dtype=torch.float32, device=torch.cuda.current_device(), n_lanes=1,
+        )
     try:
         if fast:
             soa, info = sess.play(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb)

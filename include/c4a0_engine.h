@@ -65,7 +65,14 @@ typedef struct {
   uint32_t plane_dtype;        /* C4A0_PLANES_F32 | C4A0_PLANES_BF16 */
   uint32_t max_inline_sims;    /* terminal-leaf simulations a game may run inside one step (0 = 8) */
   int32_t device;              /* CUDA device ordinal */
+  uint32_t plane_stride;       /* elements between consecutive rows of planes_dev (0 = 84; a multiple of
+                                  4, >= 84; elements 84.. of a row are never written) */
+  uint32_t flags;              /* C4A0_FLAG_* */
 } c4a0_config;
+
+/* Evaluate every waiting leaf even when several games wait on the same (position, model); by default
+ * equal leaves share one network row, as the reference's NN thread does (self_play.rs:203-208). */
+#define C4A0_FLAG_NO_DEDUP 1u
 
 typedef struct {
   uint32_t n_requests;   /* games submitted */
@@ -73,13 +80,15 @@ typedef struct {
   uint32_t n_finished;   /* games whose samples are complete */
   uint32_t n_running;    /* slots holding a live game */
   uint32_t n_movers;     /* games that moved in the last step */
+  uint32_t n_rows;       /* network rows the last step packed: rows [0, n_rows) of planes_dev are live */
   int32_t error;         /* 0, or C4A0_E_ENGINE if a game hit a state where the reference panics */
 } c4a0_progress;
 
 /* Counters in the reference's own units (self_play.rs:352-381 shows the same three live). */
 typedef struct {
   uint64_t sims;               /* on_received_policy equivalents actually executed */
-  uint64_t nn_evals;           /* leaf positions handed to the network */
+  uint64_t nn_evals;           /* rows handed to the network (unique leaf positions per tick) */
+  uint64_t leaf_requests;      /* games that waited for a network answer, summed over ticks */
   uint64_t terminal_leaf_sims; /* sims whose leaf was terminal (run inside the kernel, no NN row) */
   uint64_t skipped_root_sims;  /* sims the reference would still spend on a terminal root */
   uint64_t moves;
@@ -100,9 +109,13 @@ void c4a0_engine_destroy(c4a0_engine *e);
 size_t c4a0_engine_device_bytes(const c4a0_engine *e);
 
 /* NN I/O buffers, caller-owned device memory (DLPack / torch tensors):
- *   planes_dev : [n_slots][2][6][7] f32 or bf16 (cfg.plane_dtype)      <- pybridge.rs:202-221
+ *   planes_dev : [n_slots][plane_stride] f32 or bf16 (cfg.plane_dtype); the first 84 elements of a
+ *                row are the [2][6][7] planes                          <- pybridge.rs:202-221
  *   logits_dev : [n_slots][7] f32, q_penalty_dev / q_no_penalty_dev : [n_slots] f32
- *                                                                      <- pybridge.rs:175-196 */
+ *                                                                      <- pybridge.rs:175-196
+ * Rows are dense: after set_requests()/step() rows [0, n_rows) hold the distinct leaf positions that
+ * wait for an answer (n_rows <= n_slots, reported by poll()); the network must fill the same rows of
+ * the three output buffers before the next step().  Rows >= n_rows are ignored. */
 int c4a0_engine_bind_io(c4a0_engine *e, void *planes_dev, const float *logits_dev,
                         const float *q_penalty_dev, const float *q_no_penalty_dev);
 
@@ -131,10 +144,42 @@ int c4a0_engine_eval_builtin(c4a0_engine *e, int kind, void *stream);
 int c4a0_engine_poll(c4a0_engine *e, c4a0_progress *out, void *stream);
 int c4a0_engine_stats(c4a0_engine *e, c4a0_stats *out, void *stream);
 
-/* Per-row view for the numpy-callback compatibility path and for tests: state, current leaf
- * position and the model that has to evaluate it (mcts.rs:70-76).  Any pointer may be NULL. */
-int c4a0_engine_fetch_rows(c4a0_engine *e, uint32_t *state, uint64_t *leaf_mask,
+/* Per-row view for the numpy-callback compatibility path and for tests: *n_rows, and for each live
+ * row the leaf position and the model that has to evaluate it (mcts.rs:70-76).  The arrays must hold
+ * n_slots entries; any of them may be NULL. */
+int c4a0_engine_fetch_rows(c4a0_engine *e, uint32_t *n_rows, uint64_t *leaf_mask,
                            uint64_t *leaf_value, uint64_t *model_id, void *stream);
+
+/* ---- the host loop ------------------------------------------------------------------------
+ * A network evaluator as CUDA graphs: graph_exec (a cudaGraphExec_t) reads rows [0, rows) of the
+ * engine's planes buffer and writes the same rows of its logits / q buffers.  Pass several sizes,
+ * sorted ascending, the largest covering n_slots; every tick the smallest one that covers n_rows is
+ * launched. */
+typedef struct {
+  uint32_t rows;
+  void *graph_exec;
+} c4a0_nn_graph;
+
+typedef struct {
+  uint64_t ticks;            /* tree ticks launched, all engines */
+  uint64_t nn_launches;      /* network graphs launched */
+  uint64_t nn_rows_launched; /* sum of their row counts (>= nn_evals: bucket padding) */
+  double device_ms;          /* CUDA-event time, first network launch .. last game finished (max over engines) */
+  double wall_ms;
+  uint32_t kernel_samples;   /* ticks whose kernels were bracketed by events */
+  double k_step_ms_sum;      /* summed device time of the apply+select kernel over those ticks */
+  double k_move_ms_sum;      /* ... of the move / re-root kernel */
+} c4a0_run_report;
+
+/* Plays every engine's requests to completion: what self_play() does between spawning its threads
+ * and collecting done_queue (self_play.rs:60-129).  engines[i] runs on streams[i] with graphs[i]
+ * (n_graphs[i] entries).  With two engines the tree tick and host round trip of one overlap the
+ * network of the other.  time_kernels_every = k > 0 brackets the tree kernels of every k-th tick
+ * with CUDA events (no synchronisation).  max_ticks = 0 means no limit. */
+int c4a0_engine_run(c4a0_engine *const *engines, uint32_t n_engines,
+                    const c4a0_nn_graph *const *graphs, const uint32_t *n_graphs,
+                    void *const *streams, uint64_t max_ticks, uint32_t time_kernels_every,
+                    c4a0_run_report *out);
 
 /* Finished games [first, first+n) in request order: n_samples[i] (0 = not finished) and
  * [n][43] sample fields (types.rs:104-110).  Any output pointer may be NULL. */
@@ -152,6 +197,7 @@ typedef struct {
   uint64_t root_mask, root_value;
   float root_q_sum_penalty, root_q_sum_no_penalty;
   uint32_t n_blocks; /* expanded nodes currently allocated in the live arena half */
+  uint32_t nn_row;   /* network row holding this game's answer (valid in C4A0_ROW_WAIT_NN) */
 } c4a0_slot_info;
 int c4a0_engine_slot_info(c4a0_engine *e, uint32_t slot, c4a0_slot_info *out, void *stream);
 /* Canonical pre-order dump of a slot's tree: 4 words {root kind, N, Qp bits, Qn bits}, then for

@@ -227,3 +227,84 @@ def test_stats_match_oracle_counts():
     assert st["moves"] == o.stats["moves"]
     assert st["samples"] == o.stats["samples"]
     e.close()
+
+
+def test_dedup_changes_network_rows_not_results():
+    """Equal leaves share a network row (self_play.rs:203-208); game records must not change."""
+    _need_gpu()
+    from c4a0_b200 import _lib as L
+
+    n_games, n_iter, c_expl, c_pen = 96, 40, 6.6, 0.01
+    ids = [5 * i for i in range(n_games)]
+    outs, stats = [], []
+    for flags in (0, L.FLAG_NO_DEDUP):
+        e, io = _make_engine(n_games, n_games, n_iter, c_expl, c_pen, flags=flags)
+        e.set_requests(ids, [0] * n_games, [0] * n_games)
+        p = e.poll()
+        assert p.n_rows == (1 if flags == 0 else n_games)  # every game starts from the empty board
+        _run_builtin(e, 1)
+        outs.append(e.fetch_results())
+        stats.append(e.stats())
+        e.close()
+    for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
+        assert np.array_equal(getattr(outs[0], f), getattr(outs[1], f)), f
+    assert stats[0]["sims"] == stats[1]["sims"] and stats[0]["leaf_requests"] == stats[1]["leaf_requests"]
+    assert stats[1]["nn_evals"] == stats[1]["leaf_requests"]
+    assert stats[0]["nn_evals"] < stats[0]["leaf_requests"]
+
+
+def test_rows_are_dense_distinct_and_in_slot_order():
+    _need_gpu()
+    n_games = 200
+    e, io = _make_engine(n_games, n_games, 30, 6.6, 0.01)
+    e.set_requests(list(range(n_games)), [0] * n_games, [1] * n_games)
+    for tick in range(400):
+        e.eval_builtin(1)
+        e.step()
+        if tick % 25 == 0:
+            n_rows, mask, value, model = e.fetch_rows()
+            keys = list(zip(mask.tolist(), value.tolist(), model.tolist()))
+            assert len(set(keys)) == n_rows
+            # the row of a key is decided by its smallest slot: rows ascend with leader slot
+            leaders = {}
+            for s in range(n_games):
+                info = e.slot_info(s)
+                if info.state == 1:
+                    leaders.setdefault(info.nn_row, s)
+                    assert info.nn_row < n_rows
+            assert sorted(leaders) == list(range(n_rows))
+            assert [leaders[r] for r in range(n_rows)] == sorted(leaders.values())
+    e.close()
+
+
+def test_native_host_loop_two_lanes_equals_python_loop_one_lane():
+    """c4a0_engine_run (bucketed CUDA graphs, two engines on two streams) plays the same games as
+    the Python loop on one engine, for an evaluator whose per-row output does not depend on the
+    batch it is computed in."""
+    _need_gpu()
+    from c4a0_b200.selfplay import DeviceEvaluator, SelfPlaySession
+
+    g = torch.Generator().manual_seed(3)
+    W = (torch.randn(84, generator=g) * 2).cuda()
+    V = torch.randn(84, generator=g).cuda()
+
+    def net(planes):
+        x = planes[:, :84].float()
+        pol = (x * W).view(-1, 7, 12).sum(2)
+        q = torch.tanh((x * V).sum(1))
+        return pol, q, q * 0.5
+
+    ev = DeviceEvaluator(net, torch.float32, 96)
+    n_games, n_iter = 1500, 24
+    ids = np.arange(n_games) * 3 + 1
+    z = np.zeros(n_games, np.uint64)
+    res = []
+    for lanes, loop, slots in ((2, "native", 1100), (1, "python", 700)):
+        sess = SelfPlaySession(slots, n_games, n_iter, 6.6, 0.01, plane_dtype=torch.float32, plane_stride=96, n_lanes=lanes)
+        out, info = sess.play(ids, z, z, ev, host_loop=loop, poll_every=16, sample_kernels_every=7)
+        assert info.stats["samples"] == int(out.n_samples.sum()) and (out.n_samples >= 8).all()
+        assert info.kernel_ms["samples"] > 0 and info.device_s > 0
+        res.append(out)
+        sess.close()
+    for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
+        assert np.array_equal(getattr(res[0], f), getattr(res[1], f)), f
