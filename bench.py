@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--sample-kernels-every", type=int, default=53)
     ap.add_argument("--lanes", type=int, default=2, help="engines per GPU (2 = tree ticks overlap the other half's network)")
     ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
+    ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
     ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")
     return ap.parse_args()
 
@@ -243,6 +244,7 @@ def run_ours(args):
     selfplay.DEFAULTS["sample_kernels_every"] = args.sample_kernels_every
     selfplay.DEFAULTS["n_lanes"] = args.lanes
     selfplay.DEFAULTS["dedup"] = not args.no_dedup
+    selfplay.DEFAULTS["max_inline_sims"] = args.max_inline
     G = args.games
     ids = range(rank * G, (rank + 1) * G)  # weak scaling: every rank plays its own G games
 
@@ -343,6 +345,7 @@ def run_ours(args):
             "note": "reference-form network FLOPs x rows launched / whole search time on one GPU (library kernels: cuBLASLt via PyTorch)",
         },
         "clocks": clk,
+        "bucket_launches": [int(sum(r[1].report.get("bucket_launches", [0] * 32)[i] for r in runs)) for i in range(20)],
         "ticks_per_step": ticks / max(1, args.steps),
     }
     if world == 1 and not args.no_cpu_baseline:

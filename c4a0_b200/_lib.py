@@ -96,10 +96,13 @@ class RunReport(C.Structure):
         ("kernel_samples", C.c_uint32),
         ("k_step_ms_sum", C.c_double),
         ("k_move_ms_sum", C.c_double),
+        ("bucket_launches", C.c_uint64 * 32),
     ]
 
     def as_dict(self) -> dict:
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["bucket_launches"] = list(self.bucket_launches)
+        return d
 
 
 class EngineError(RuntimeError):

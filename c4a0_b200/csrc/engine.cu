@@ -921,6 +921,12 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
     CK(cudaMemcpyAsync((void*)D.p0, p0, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync((void*)D.p1, p1, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(D.n_samples, 0, n * sizeof(uint32_t), s));
+    // unused sample cells read back as zeros
+    CK(cudaMemsetAsync(D.s_mask, 0, (size_t)n * MAXS * 8, s));
+    CK(cudaMemsetAsync(D.s_value, 0, (size_t)n * MAXS * 8, s));
+    CK(cudaMemsetAsync(D.s_policy, 0, (size_t)n * MAXS * 28, s));
+    CK(cudaMemsetAsync(D.s_qp, 0, (size_t)n * MAXS * 4, s));
+    CK(cudaMemsetAsync(D.s_qn, 0, (size_t)n * MAXS * 4, s));
   }
   CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
   k_init<<<blocks_for(D.n_slots, 256), 256, 0, s>>>(D, n);
@@ -1185,6 +1191,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     while (k + 1 < n_graphs[i] && g[k].rows < rows) k++;
     CK(cudaGraphLaunch((cudaGraphExec_t)g[k].graph_exec, L.s));
     out->nn_launches++;
+    out->bucket_launches[k < 31 ? k : 31]++;
     out->nn_rows_launched += g[k].rows;
     return 0;
   };

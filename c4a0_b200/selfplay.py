@@ -34,7 +34,8 @@ from . import _lib as L
 from .engine import Engine, GameSamples, run_engines
 
 # process-wide defaults, overridable by tools (bench.py turns kernel sampling on)
-DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 2, "dedup": True}
+DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 2, "dedup": True,
+            "max_inline_sims": 0}
 
 BUCKETS = (128, 256, 512, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072)
 
@@ -158,6 +159,7 @@ class SelfPlaySession:
         if plane_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("plane_dtype must be float32 or bfloat16")
         n_lanes = DEFAULTS["n_lanes"] if n_lanes is None else n_lanes
+        max_inline_sims = max_inline_sims or DEFAULTS["max_inline_sims"]
         dedup = DEFAULTS["dedup"] if dedup is None else dedup
         if n_slots < 2 * 256:
             n_lanes = 1  # tiny batches: nothing to overlap

@@ -169,6 +169,7 @@ typedef struct {
   uint32_t kernel_samples;   /* ticks whose kernels were bracketed by events */
   double k_step_ms_sum;      /* summed device time of the apply+select kernel over those ticks */
   double k_move_ms_sum;      /* ... of the move / re-root kernel */
+  uint64_t bucket_launches[32]; /* network launches per graph index (all engines) */
 } c4a0_run_report;
 
 /* Plays every engine's requests to completion: what self_play() does between spawning its threads

@@ -248,6 +248,8 @@ def test_dedup_changes_network_rows_not_results():
         e.close()
     for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
         assert np.array_equal(getattr(outs[0], f), getattr(outs[1], f)), f
+    valid = np.arange(43)[None, :] < outs[0].n_samples[:, None]
+    assert not outs[0].mask[~valid].any() and not outs[0].policy[~valid].any()  # unused cells are zero
     assert stats[0]["sims"] == stats[1]["sims"] and stats[0]["leaf_requests"] == stats[1]["leaf_requests"]
     assert stats[1]["nn_evals"] == stats[1]["leaf_requests"]
     assert stats[0]["nn_evals"] < stats[0]["leaf_requests"]
