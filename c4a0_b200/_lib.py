@@ -33,6 +33,7 @@ class Config(C.Structure):
         ("device", C.c_int32),
         ("plane_stride", C.c_uint32),
         ("flags", C.c_uint32),
+        ("arena_blocks", C.c_uint32),
     ]
 
 
@@ -61,6 +62,7 @@ class Stats(C.Structure):
         ("expansions", C.c_uint64),
         ("steps", C.c_uint64),
         ("compacted_blocks", C.c_uint64),
+        ("compactions", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -7,23 +7,29 @@
 //
 //   * A tree is a bump-allocated array of 160-byte BLOCKS.  A block belongs to one expanded node
 //     and holds the statistics of its 7 children column-wise (N[8], Qp[8], Qn[8], P[8], child[8]),
-//     i.e. exactly the fields UCT selection reads for one level (mcts.rs:359-388) as five 32-byte
-//     sectors.  Node positions are never stored: selection replays the moves on bitboards.
-//   * A game is served by 8 lanes (4 games per warp): lane c owns child c, argmax is a 3-step
-//     shuffle butterfly with the reference's last-maximum tie-break (Iterator::max_by_key).
-//   * Backup (mcts.rs:137-155) walks the path recorded by selection; the path nodes are
-//     independent read-modify-writes, so lanes update them in parallel, one f32 add per node per
-//     simulation in simulation order — the reference's accumulation order.
-//   * A move (mcts.rs:187-222) keeps the chosen child's subtree.  One CTA per moving game copies
-//     that subtree breadth-first into the other half of the game's arena (compaction), which is
-//     what bounds a game's memory to 2*(n_iterations+2) blocks regardless of game length.
+//     i.e. exactly the fields UCT selection reads for one level (mcts.rs:359-388), fetched as
+//     16-byte vectors.  Node positions are never stored: selection replays the moves on bitboards.
+//   * One THREAD owns one game for a whole tick (k_step): it consumes the network's answer
+//     (mask + softmax + expand + backup, mcts.rs:83-155), plays the move when the root reached
+//     n_iterations (temperature + seeded sample + re-root, self_play.rs:283-300, mcts.rs:187-222),
+//     finishes / re-seats the game, and selects the next leaf (mcts.rs:160-183).  The work of one
+//     tick is a short dependent chain per game, so what matters is the length of that chain, not
+//     lanes per game; 32 independent games per warp give the memory system 32x the requests.
+//   * Backup walks the path recorded by selection: one f32 add per node per simulation in
+//     simulation order — the reference's accumulation order.
+//   * Re-rooting keeps the chosen child's subtree and drops the siblings.  Nothing is copied while
+//     the arena has room (root_block simply becomes the child's block); when a half fills up, one
+//     CTA per game (k_move) copies the live subtree breadth-first into the other half.  Memory per
+//     game is 2 * arena_blocks * 160 B, with arena_blocks >= n_iterations + 2.
 //   * The network batch is dense and de-duplicated, like the reference's NN thread builds it
-//     (self_play.rs:203-220: HashSet<Pos> per model): every selected leaf is inserted into an
-//     epoch-tagged hash table (smallest slot wins a key), a scan numbers the winners, and only they
-//     write input planes, to rows 0..n_rows-1.  Every game remembers the row that holds its answer.
+//     (self_play.rs:203-220: HashSet<Pos> per model).  One cooperative kernel per tick (k_post)
+//     inserts every waiting leaf into an epoch-tagged hash table (smallest slot wins a key),
+//     numbers the winners in slot order with a decoupled look-back scan, and lets only them write
+//     input planes, to rows 0..n_rows-1.  Every game remembers the row that holds its answer.
 //
-// One tick = k_begin -> k_step -> k_move -> k_scan -> k_pack, then the network on rows [0, n_rows).
+// One tick = k_step -> k_move -> k_post, then the network on rows [0, n_rows).
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <string.h>
@@ -37,6 +43,8 @@
 #include "c4_rng.cuh"
 #include "c4_rules.cuh"
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -54,31 +62,56 @@ struct __align__(32) Block {
   float P[8];         // initial_policy_value of child c   (mcts.rs:338)
   uint32_t child[8];  // block index of child c's own block, 0 = child not expanded
 };
-static_assert(sizeof(Block) == 160, "block must be five 32-byte sectors");
+static_assert(sizeof(Block) == 160, "block must be ten 16-byte vectors");
+
+// Everything a game needs besides its tree, one 128-byte line per slot.
+struct __align__(128) Slot {
+  uint64_t root_mask, root_value;
+  uint64_t leaf_mask, leaf_value;  // the leaf waiting for the network (= its de-duplication key)
+  uint64_t leaf_model;             //   ... and the model that must evaluate it (mcts.rs:70-76)
+  uint32_t root_N;
+  float root_Qp, root_Qn;
+  uint32_t root_block;             // block of the root's children, 0 = root not expanded
+  uint32_t n_alloc;                // next free block index of the live arena half (index 0 unused)
+  uint32_t path_len;
+  uint32_t state;
+  uint32_t half;
+  uint32_t req;                    // request index of the game seated here
+  uint32_t n_moves;
+  uint32_t nn_row;                 // network row holding this game's answer
+  uint32_t urow;                   // row assigned to this slot when it leads its key
+  unsigned long long c_sims, c_exp, c_term, c_depth;
+};
+static_assert(sizeof(Slot) == 128, "slot state must be one cache line");
 
 constexpr int PATH_STRIDE = 44;  // <= 42 levels below a root
 constexpr int MAXS = C4A0_MAX_SAMPLES;
-constexpr int SCAN_THREADS = 1024;
+constexpr int STEP_THREADS = 128;
+constexpr int POST_THREADS = 256;
+constexpr int MOVE_THREADS = 128;
 enum : uint32_t { ST_IDLE = 0, ST_WAIT_NN = 1, ST_CONTINUE = 2, ST_NEED_MOVE = 3 };
 
 struct Globals {  // one instance in device memory
-  uint32_t tick;  // epoch of the hash table: leaves selected during tick t carry epoch t
+  uint32_t tick;  // epoch of the hash table / scan: advanced at the end of every k_post
   uint32_t n_req;
   uint32_t next_req;
   uint32_t n_finished;
   uint32_t n_running;
   uint32_t n_movers;
   uint32_t n_rows;
+  uint32_t n_waiting;
   int32_t error;
+  uint32_t pad;
   unsigned long long skipped_root_sims;
   unsigned long long moves;
   unsigned long long samples;
   unsigned long long compacted_blocks;
-  unsigned long long rows_total;   // sum over ticks of n_rows (positions actually evaluated)
-  unsigned long long leaves_total; // sum over ticks of games waiting for the network
+  unsigned long long compactions;
+  unsigned long long rows_total;    // sum over ticks of n_rows (positions actually evaluated)
+  unsigned long long leaves_total;  // sum over ticks of games waiting for the network
 };
 
-struct HostStatus {  // mapped pinned host memory, written by k_scan at the end of every tick
+struct HostStatus {  // mapped pinned host memory, written by k_post at the end of every tick
   volatile uint32_t tick;
   volatile uint32_t n_rows;
   volatile uint32_t n_finished;
@@ -90,14 +123,9 @@ struct HostStatus {  // mapped pinned host memory, written by k_scan at the end 
 struct Dev {  // passed to kernels by value
   uint32_t n_slots, n_iter, cap, max_inline, plane_bf16, plane_stride, dedup, table_mask;
   float c_expl, c_pen;
-  // per slot
-  uint64_t *root_mask, *root_value, *leaf_mask, *leaf_value, *leaf_model;
-  uint32_t *root_N, *root_block, *half, *n_alloc, *state, *req, *n_moves, *path_len, *path;
-  uint32_t *bucket, *urow, *nn_row;
-  float *root_Qp, *root_Qn;
-  unsigned long long *c_sims, *c_evals, *c_term, *c_depth;
-  Block* blocks;  // [n_slots][2][cap]
-  // per row
+  Slot* slots;
+  uint32_t* path;   // [n_slots][PATH_STRIDE]: (block << 3 | column) per level of the selected path
+  Block* blocks;    // [n_slots][2][cap]
   uint32_t* row_slot;
   // per request
   const uint64_t *game_id, *p0, *p1;
@@ -108,7 +136,8 @@ struct Dev {  // passed to kernels by value
   Globals* g;
   HostStatus* status;  // device address of the mapped host struct
   uint32_t* movers;
-  unsigned long long* table;  // [table_mask+1] entries: epoch << 32 | leader slot
+  unsigned long long* table;       // [table_mask+1]: epoch << 32 | leader slot
+  unsigned long long* cta_counts;  // [k_post grid]:   epoch << 32 | leaders in that CTA
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
@@ -125,216 +154,342 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-// ------------------------------------------------------------------------------------------------
-// 8-lane group helpers
-// ------------------------------------------------------------------------------------------------
-struct Group {
-  unsigned mask;  // the 8 lanes of this game within the warp
-  int l;          // 0..7 ; lanes 0..6 own children/columns 0..6
-};
-__device__ __forceinline__ Group make_group() {
-  Group g;
-  int lane = threadIdx.x & 31;
-  g.mask = 0xffu << (lane & 24);
-  g.l = lane & 7;
-  return g;
-}
-template <typename T>
-__device__ __forceinline__ T gshfl(const Group& g, T v, int src) {
-  return __shfl_sync(g.mask, v, src, 8);
-}
-template <typename T>
-__device__ __forceinline__ T gxor(const Group& g, T v, int m) {
-  return __shfl_xor_sync(g.mask, v, m, 8);
-}
-
-// NN input planes of `p` into row `row` (c4r.rs:378-392): 84 values, written by 8 lanes as
-// 16-byte (f32) or 8-byte (bf16) vectors.
-__device__ __forceinline__ void write_planes(const Dev& D, int l, uint32_t row, Pos p) {
-  uint64_t mine = p.mask & p.value, theirs = p.mask & ~p.value;
+// NN input planes of `p` into row `row` (c4r.rs:378-392): 84 values as 16-byte vectors.
+__device__ __forceinline__ void write_planes(const Dev& D, uint32_t row, Pos p) {
+  const uint64_t mine = p.mask & p.value, theirs = p.mask & ~p.value;
+  // bit i of `bits` (i < 84) is plane element i
+  const uint64_t lo = mine | (theirs << 42);  // elements 0..63
+  const uint64_t hi = theirs >> 22;           // elements 64..83
   if (D.plane_bf16) {
-    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(D.planes) + (size_t)row * D.plane_stride);
-    for (int v = l; v < 21; v += 8) {
-      uint32_t w[2];
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(D.planes) + (size_t)row * D.plane_stride;
+    if ((D.plane_stride & 7u) == 0u) {  // rows are 16-byte aligned: 8 bf16 per store
+      uint4* dst = reinterpret_cast<uint4*>(base);
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        int i0 = v * 4 + h * 2, i1 = i0 + 1;
-        uint32_t b0 = (uint32_t)(((i0 < 42 ? mine >> i0 : theirs >> (i0 - 42))) & 1ull);
-        uint32_t b1 = (uint32_t)(((i1 < 42 ? mine >> i1 : theirs >> (i1 - 42))) & 1ull);
-        w[h] = (b0 ? 0x3f80u : 0u) | (b1 ? 0x3f800000u : 0u);  // bf16(1.0) = 0x3f80
+      for (int v = 0; v < 11; v++) {  // elements 84..87 of the last vector are padding (zeros)
+        uint32_t b = (uint32_t)((v < 8 ? lo >> (8 * v) : hi >> (8 * (v - 8))) & 0xffull);
+        if (v == 10) b &= 0x0fu;
+        uint4 w;
+        w.x = ((b & 1u) ? 0x3f80u : 0u) | ((b & 2u) ? 0x3f800000u : 0u);  // bf16(1.0) = 0x3f80
+        w.y = ((b & 4u) ? 0x3f80u : 0u) | ((b & 8u) ? 0x3f800000u : 0u);
+        w.z = ((b & 16u) ? 0x3f80u : 0u) | ((b & 32u) ? 0x3f800000u : 0u);
+        w.w = ((b & 64u) ? 0x3f80u : 0u) | ((b & 128u) ? 0x3f800000u : 0u);
+        dst[v] = w;
       }
-      dst[v] = make_uint2(w[0], w[1]);
+    } else {  // e.g. the natural stride 84: rows are 8-byte aligned, 4 bf16 per store
+      uint2* dst = reinterpret_cast<uint2*>(base);
+#pragma unroll
+      for (int v = 0; v < 21; v++) {
+        uint32_t b = (uint32_t)((v < 16 ? lo >> (4 * v) : hi >> (4 * (v - 16))) & 0xfull);
+        dst[v] = make_uint2(((b & 1u) ? 0x3f80u : 0u) | ((b & 2u) ? 0x3f800000u : 0u),
+                            ((b & 4u) ? 0x3f80u : 0u) | ((b & 8u) ? 0x3f800000u : 0u));
+      }
     }
   } else {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(D.planes) + (size_t)row * D.plane_stride);
-    for (int v = l; v < 21; v += 8) {
-      float f[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        int i = v * 4 + k;
-        f[k] = (float)(((i < 42 ? mine >> i : theirs >> (i - 42))) & 1ull);
-      }
-      dst[v] = make_float4(f[0], f[1], f[2], f[3]);
+    for (int v = 0; v < 21; v++) {
+      uint32_t b = (uint32_t)((v < 16 ? lo >> (4 * v) : hi >> (4 * (v - 16))) & 0xfull);
+      dst[v] = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Leaf de-duplication (self_play.rs:203-208).  Called by ONE lane per game once its leaf is known.
-// Table entry = epoch << 32 | leader slot; an entry whose epoch is not the current tick is empty,
-// so the table never needs clearing.  Among games with equal (position, model) the smallest slot
-// becomes the leader (atomicMin) — deterministic whatever order the games arrive in.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, Pos leaf, uint32_t epoch) {
-  uint32_t r = D.req[slot];
-  uint64_t model = (c4::ply(leaf.mask) & 1) ? D.p1[r] : D.p0[r];  // mcts.rs:70-76
-  D.leaf_mask[slot] = leaf.mask;
-  D.leaf_value[slot] = leaf.value;
-  D.leaf_model[slot] = model;
-  if (!D.dedup) return;
-  __threadfence();  // the key must be visible before the slot can be found in the table
-  uint32_t h = (uint32_t)splitmix64(leaf.mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(leaf.value ^ model)) & D.table_mask;
-  const unsigned long long mine = ((unsigned long long)epoch << 32) | slot;
-  for (;;) {
-    unsigned long long* e = D.table + h;
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e);
-    if ((uint32_t)(cur >> 32) != epoch) {
-      unsigned long long prev = atomicCAS(e, cur, mine);
-      if (prev == cur) break;  // first game with this key in this tick
-      cur = prev;
-      if ((uint32_t)(cur >> 32) != epoch) continue;
-    }
-    uint32_t leader = (uint32_t)cur;
-    if (__ldcg(D.leaf_mask + leader) == leaf.mask && __ldcg(D.leaf_value + leader) == leaf.value &&
-        __ldcg(D.leaf_model + leader) == model) {
-      atomicMin(e, mine);
-      break;
-    }
-    h = (h + 1) & D.table_mask;  // another key lives here: linear probing
-  }
-  D.bucket[slot] = h;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Per-game working set held in registers by all 8 lanes (group-uniform values)
+// Per-game working set (registers of the owning thread)
 // ------------------------------------------------------------------------------------------------
 struct Game {
   uint32_t slot;
-  Pos root;
-  uint32_t rootN, root_block, n_alloc, len;
+  Pos root, leaf;
+  uint64_t leaf_model;
+  uint32_t rootN, root_block, n_alloc, len, half, req, n_moves;
   float rootQp, rootQn;
   Block* arena;
   uint32_t* path;
-  unsigned long long sims, evals, term, depth;
+  unsigned long long sims, exps, term, depth;
 };
 
 __device__ __forceinline__ void load_game(const Dev& D, uint32_t slot, Game& G) {
+  const Slot* S = D.slots + slot;
   G.slot = slot;
-  G.root.mask = D.root_mask[slot];
-  G.root.value = D.root_value[slot];
-  G.rootN = D.root_N[slot];
-  G.rootQp = D.root_Qp[slot];
-  G.rootQn = D.root_Qn[slot];
-  G.root_block = D.root_block[slot];
-  G.n_alloc = D.n_alloc[slot];
-  G.len = D.path_len[slot];
-  G.arena = arena_of(D, slot, D.half[slot]);
+  G.root.mask = S->root_mask;
+  G.root.value = S->root_value;
+  G.leaf.mask = S->leaf_mask;
+  G.leaf.value = S->leaf_value;
+  G.leaf_model = S->leaf_model;
+  G.rootN = S->root_N;
+  G.rootQp = S->root_Qp;
+  G.rootQn = S->root_Qn;
+  G.root_block = S->root_block;
+  G.n_alloc = S->n_alloc;
+  G.len = S->path_len;
+  G.half = S->half;
+  G.req = S->req;
+  G.n_moves = S->n_moves;
+  G.arena = arena_of(D, slot, G.half);
   G.path = D.path + (size_t)slot * PATH_STRIDE;
-  G.sims = G.evals = G.term = G.depth = 0;
+  G.sims = G.exps = G.term = G.depth = 0;
 }
-__device__ __forceinline__ void store_game(const Dev& D, const Group& g, const Game& G, uint32_t state) {
-  if (g.l == 0) {
-    uint32_t s = G.slot;
-    D.root_N[s] = G.rootN;
-    D.root_Qp[s] = G.rootQp;
-    D.root_Qn[s] = G.rootQn;
-    D.root_block[s] = G.root_block;
-    D.n_alloc[s] = G.n_alloc;
-    D.path_len[s] = G.len;
-    D.state[s] = state;
-    if (G.sims) D.c_sims[s] += G.sims;
-    if (G.evals) D.c_evals[s] += G.evals;
-    if (G.term) D.c_term[s] += G.term;
-    if (G.depth) D.c_depth[s] += G.depth;
-  }
+__device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t state) {
+  Slot* S = D.slots + G.slot;
+  S->root_mask = G.root.mask;
+  S->root_value = G.root.value;
+  S->leaf_mask = G.leaf.mask;
+  S->leaf_value = G.leaf.value;
+  S->leaf_model = G.leaf_model;
+  S->root_N = G.rootN;
+  S->root_Qp = G.rootQp;
+  S->root_Qn = G.rootQn;
+  S->root_block = G.root_block;
+  S->n_alloc = G.n_alloc;
+  S->path_len = G.len;
+  S->state = state;
+  S->half = G.half;
+  S->req = G.req;
+  S->n_moves = G.n_moves;
+  if (G.sims) S->c_sims += G.sims;
+  if (G.exps) S->c_exp += G.exps;
+  if (G.term) S->c_term += G.term;
+  if (G.depth) S->c_depth += G.depth;
 }
 
-// mcts.rs:137-155 — add (qp, qn) at the leaf, alternate the sign towards the root.
-__device__ __forceinline__ void backup(const Group& g, Game& G, float qp, float qn) {
-  __syncwarp(g.mask);  // path[] written by lane 0 of this group
-  for (uint32_t j = g.l; j < G.len; j += 8) {
-    uint32_t e = G.path[j];
-    Block* B = G.arena + (e >> 3);
-    uint32_t c = e & 7u;
-    bool neg = ((G.len - 1 - j) & 1u) != 0;
-    B->N[c] += 1u;
-    B->Qp[c] += neg ? -qp : qp;
-    B->Qn[c] += neg ? -qn : qn;
+// mcts.rs:137-155 — add (qp, qn) at the leaf, alternate the sign towards the root.  The path
+// nodes are distinct, so their read-modify-writes are independent: issue them four at a time.
+__device__ __forceinline__ void backup(Game& G, float qp, float qn) {
+  const uint32_t len = G.len;
+  for (uint32_t j0 = 0; j0 < len; j0 += 4) {
+    uint32_t e[4], n[4];
+    float a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) e[k] = (j0 + k < len) ? G.path[j0 + k] : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (j0 + k < len) {
+        const Block* B = G.arena + (e[k] >> 3);
+        uint32_t c = e[k] & 7u;
+        n[k] = B->N[c];
+        a[k] = B->Qp[c];
+        b[k] = B->Qn[c];
+      }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (j0 + k < len) {
+        Block* B = G.arena + (e[k] >> 3);
+        uint32_t c = e[k] & 7u;
+        bool neg = ((len - 1 - (j0 + k)) & 1u) != 0;
+        B->N[c] = n[k] + 1u;
+        B->Qp[c] = a[k] + (neg ? -qp : qp);
+        B->Qn[c] = b[k] + (neg ? -qn : qn);
+      }
   }
-  bool neg = (G.len & 1u) != 0;
+  bool neg = (len & 1u) != 0;
   G.rootN += 1u;
   G.rootQp += neg ? -qp : qp;
   G.rootQn += neg ? -qn : qn;
-  __syncwarp(g.mask);  // statistics visible to the selection that follows
 }
 
-// mcts.rs:160-183 + 359-388 — walk from the root to a node without children.
-__device__ __forceinline__ Pos select_leaf(const Dev& D, const Group& g, Game& G) {
+// mcts.rs:359-388: -(Qp/(N+1)) + c * (sqrt(ln(N_parent)/(N+1)) * (P + 1e-8)), f32, no contraction
+__device__ __forceinline__ float uct(uint32_t n, float qs, float pr, float lnp, float c_expl) {
+  float nf = (float)n + 1.0f;
+  float q = qs / nf;
+  float ex = sqrtf(lnp / nf);
+  ex = ex * (pr + 1e-8f);
+  return (-q) + (c_expl * ex);
+}
+
+// mcts.rs:160-183 — walk from the root to a node without children; records the path.
+__device__ __forceinline__ Pos select_leaf(const Dev& D, Game& G) {
   Pos pos = G.root;
   uint32_t np = G.rootN, b = G.root_block, len = 0;
-  const float ninf = -c4::f32_inf();
   while (b != 0u && len < 43u) {  // a tree is at most 42 plies deep
-    const Block* B = G.arena + b;
-    uint32_t n = B->N[g.l];
-    float qs = B->Qp[g.l];
-    float pr = B->P[g.l];
-    uint32_t ch = B->child[g.l];
-    unsigned legal = c4::legal_mask(pos.mask);
-    float lnp = c4::c4_logf((float)np);             // ln(parent visits), mcts.rs:378-379
-    float nf = (float)n + 1.0f;
-    float q = qs / nf;                              // mcts.rs:359-361
-    float ex = sqrtf(lnp / nf);
-    ex = ex * (pr + 1e-8f);                         // mcts.rs:380
-    float u = (-q) + (D.c_expl * ex);               // mcts.rs:386-388
-    bool ok = (g.l < 7) && ((legal >> g.l) & 1u);
-    float bu = ok ? u : ninf;
-    int bl = ok ? g.l : -1;
+    const uint4* V = reinterpret_cast<const uint4*>(G.arena + b);
+    const uint4 n0 = V[0], n1 = V[1], q0 = V[2], q1 = V[3], p0 = V[6], p1 = V[7], c0 = V[8], c1 = V[9];
+    const unsigned legal = c4::legal_mask(pos.mask);
+    const float lnp = c4::c4_logf((float)np);  // ln(parent visits), mcts.rs:378-379
+    const uint32_t nn[7] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z};
+    const uint32_t qq[7] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};
+    const uint32_t pp[7] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z};
+    const uint32_t cc[7] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
+    int best = -1;
+    float bu = 0.0f;
+    uint32_t bn = 0u, bc = 0u;
 #pragma unroll
-    for (int m = 1; m < 8; m <<= 1) {               // max_by_key: the LAST maximum wins
-      float ou = gxor(g, bu, m);
-      int ol = gxor(g, bl, m);
-      bool take = (ol >= 0) && (bl < 0 || ou > bu || (ou == bu && ol > bl));
-      bu = take ? ou : bu;
-      bl = take ? ol : bl;
+    for (int c = 0; c < 7; c++) {
+      float u = uct(nn[c], __uint_as_float(qq[c]), __uint_as_float(pp[c]), lnp, D.c_expl);
+      bool take = ((legal >> c) & 1u) && (best < 0 || u >= bu);  // max_by_key: the LAST maximum wins
+      best = take ? c : best;
+      bu = take ? u : bu;
+      bn = take ? nn[c] : bn;
+      bc = take ? cc[c] : bc;
     }
-    if (g.l == 0) G.path[len] = (b << 3) | (uint32_t)bl;
+    if (best < 0) break;  // cannot happen: an expanded node has a legal move
+    G.path[len] = (b << 3) | (uint32_t)best;
     len++;
-    pos = c4::make_move(pos, bl);
-    np = gshfl(g, n, bl);
-    b = gshfl(g, ch, bl);
+    pos = c4::make_move(pos, best);
+    np = bn;
+    b = bc;
   }
   G.len = len;
   return pos;
 }
 
-// Run simulations from "leaf unknown" until a leaf needs the network, the root needs to move, or
-// the per-step budget of in-kernel (terminal-leaf) simulations is spent.
-__device__ __forceinline__ uint32_t advance(const Dev& D, const Group& g, Game& G, uint32_t epoch) {
-  for (uint32_t it = 0;; it++) {
-    Pos leaf = select_leaf(D, g, G);
+// mask_policy + softmax + expand_leaf + backup for the leaf the network just evaluated
+// (c4r.rs:272-286, mcts.rs:416-434, 114-132, 137-155).  false = arena overflow (engine bug).
+__device__ __forceinline__ bool apply_network(const Dev& D, Game& G, uint32_t row) {
+  const unsigned legal = c4::legal_mask(G.leaf.mask);
+  float x[7], p[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) x[i] = ((legal >> i) & 1u) ? D.logits[(size_t)row * 7 + i] : -c4::f32_inf();
+  const float vq = D.qp[row], vn = D.qn[row];
+  if (!c4::softmax7(x, p)) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) p[i] = 0.0f;
+  }
+  const uint32_t nb = G.n_alloc;
+  if (nb >= D.cap) return false;
+  G.n_alloc = nb + 1u;
+  uint4* V = reinterpret_cast<uint4*>(G.arena + nb);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  V[0] = z; V[1] = z; V[2] = z; V[3] = z; V[4] = z; V[5] = z;
+  V[6] = make_uint4(__float_as_uint(p[0]), __float_as_uint(p[1]), __float_as_uint(p[2]), __float_as_uint(p[3]));
+  V[7] = make_uint4(__float_as_uint(p[4]), __float_as_uint(p[5]), __float_as_uint(p[6]), 0u);
+  V[8] = z; V[9] = z;
+  if (G.len == 0) {
+    G.root_block = nb;
+  } else {
+    uint32_t e = G.path[G.len - 1];
+    G.arena[e >> 3].child[e & 7u] = nb;
+  }
+  G.depth += G.len;
+  backup(G, vq, vn);
+  G.sims++;
+  G.exps++;
+  return true;
+}
+
+__device__ __forceinline__ void seat_game(Game& G, uint32_t r) {
+  G.root = Pos{0ull, 0ull};
+  G.rootN = 0u;
+  G.rootQp = 0.0f;
+  G.rootQn = 0.0f;
+  G.root_block = 0u;
+  G.n_alloc = 1u;
+  G.req = r;
+  G.n_moves = 0u;
+  G.len = 0u;
+}
+
+enum MoveResult { MV_CONTINUE, MV_IDLE, MV_COMPACT };
+
+// The root reached n_iterations (self_play.rs:283-313): sample and play a move (mcts.rs:187-222) or,
+// when that ends the game, emit its samples (mcts.rs:271-313) and seat the next request.
+__device__ __noinline__ MoveResult play_move(const Dev& D, Game& G) {
+  Globals* g = D.g;
+  const uint32_t rb = G.root_block;
+  float pol[7], tempered[7];
+  const float uniform = 1.0f / 7.0f;
+  uint32_t cn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rb) {  // root_policy (mcts.rs:396-412): visit counts of the children, normalised
+    const uint4* V = reinterpret_cast<const uint4*>(G.arena + rb);
+    uint4 a = V[0], b = V[1];
+    cn[0] = a.x; cn[1] = a.y; cn[2] = a.z; cn[3] = a.w; cn[4] = b.x; cn[5] = b.y; cn[6] = b.z;
+    float cnt[7], sum = 0.0f;
+    for (int i = 0; i < 7; i++) cnt[i] = (float)cn[i];
+    for (int i = 0; i < 7; i++) sum = sum + cnt[i];
+    for (int i = 0; i < 7; i++) pol[i] = (sum == 0.0f) ? uniform : cnt[i] / sum;
+  } else {
+    for (int i = 0; i < 7; i++) pol[i] = uniform;
+  }
+  const float T = c4::temperature_for_ply(c4::ply(G.root.mask));  // self_play.rs:294-299
+  c4::apply_temperature7(pol, T, tempered);
+  const int col = c4::weighted_sample7(tempered, c4::move_seed(D.game_id[G.req], (int)G.n_moves));
+  const unsigned legal = c4::legal_mask(G.root.mask);
+  if (col < 0 || !((legal >> col) & 1u) || rb == 0u || G.n_moves >= 42u) {
+    g->error = C4A0_E_ENGINE;  // the reference panics here (mcts.rs:190-197): park the game, report
+    atomicSub(&g->n_running, 1u);
+    return MV_IDLE;
+  }
+  // RecordedMove (mcts.rs:198-203) goes straight into the sample store
+  const size_t s0 = (size_t)G.req * MAXS;
+  size_t si = s0 + G.n_moves;
+  D.s_mask[si] = G.root.mask;
+  D.s_value[si] = G.root.value;
+  for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = pol[i];
+  G.n_moves += 1u;
+  const Block* RB = G.arena + rb;
+  const Pos np = c4::make_move(G.root, col);
+  const uint32_t newN = cn[col];
+  const float newQp = RB->Qp[col], newQn = RB->Qn[col];
+  const uint32_t child = RB->child[col];
+  atomicAdd(&g->moves, 1ull);
+  float tqp, tqn;
+  const int t = c4::terminal_value(np, D.c_pen, &tqp, &tqn);
+  if (t != c4::NONE) {
+    // to_result (mcts.rs:271-313): alternate the terminal value back through the moves
+    const uint32_t L = G.n_moves;
+    for (uint32_t k = 0; k < L; k++) {
+      bool neg = ((L - k) & 1u) != 0;
+      D.s_qp[s0 + k] = neg ? -tqp : tqp;
+      D.s_qn[s0 + k] = neg ? -tqn : tqn;
+    }
+    si = s0 + L;
+    D.s_mask[si] = np.mask;
+    D.s_value[si] = np.value;
+    for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = uniform;
+    D.s_qp[si] = tqp;
+    D.s_qn[si] = tqn;
+    D.n_samples[G.req] = L + 1u;
+    atomicAdd(&g->samples, (unsigned long long)(L + 1u));
+    atomicAdd(&g->n_finished, 1u);
+    // the reference keeps simulating the terminal root until N >= n
+    if (newN < D.n_iter) atomicAdd(&g->skipped_root_sims, (unsigned long long)(D.n_iter - newN));
+    // seat the next waiting request in this slot (self_play.rs:55-58 queues them all up front)
+    const uint32_t r = atomicAdd(&g->next_req, 1u);
+    if (r < g->n_req) {
+      seat_game(G, r);
+      return MV_CONTINUE;
+    }
+    atomicSub(&g->n_running, 1u);
+    return MV_IDLE;
+  }
+  // re-root (mcts.rs:200-205): the child's subtree and statistics are kept
+  G.root = np;
+  G.rootN = newN;
+  G.rootQp = newQp;
+  G.rootQn = newQn;
+  G.root_block = child;
+  G.len = 0u;
+  // until the next move at most n_iter - N expansions happen: do they still fit in this half?
+  const uint32_t need = (D.n_iter > newN ? D.n_iter - newN : 0u) + 1u;
+  if (G.n_alloc + need > D.cap) return MV_COMPACT;
+  return MV_CONTINUE;
+}
+
+// Advance a game until it needs the network (WAIT_NN), has used its in-kernel budget of
+// terminal-leaf simulations (CONTINUE), needs its tree compacted (NEED_MOVE) or has no game (IDLE).
+__device__ __forceinline__ uint32_t run_game(const Dev& D, Game& G) {
+  uint32_t inl = 0;
+  for (;;) {
+    if (G.rootN >= D.n_iter) {  // self_play.rs:283: checked after every simulation
+      MoveResult r = play_move(D, G);
+      if (r == MV_IDLE) return ST_IDLE;
+      if (r == MV_COMPACT) return ST_NEED_MOVE;
+      continue;
+    }
+    if (inl >= D.max_inline) return ST_CONTINUE;
+    Pos leaf = select_leaf(D, G);
     float tqp, tqn;
     int t = c4::terminal_value(leaf, D.c_pen, &tqp, &tqn);
     if (t == c4::NONE) {
-      if (g.l == 0) publish_leaf(D, G.slot, leaf, epoch);
+      G.leaf = leaf;
+      G.leaf_model = (c4::ply(leaf.mask) & 1) ? D.p1[G.req] : D.p0[G.req];  // mcts.rs:70-76
       return ST_WAIT_NN;
     }
     // terminal leaf: mcts.rs:92-98 — no expansion, back up the objective value
     G.depth += G.len;
-    backup(g, G, tqp, tqn);
+    backup(G, tqp, tqn);
     G.sims++;
     G.term++;
-    if (G.rootN >= D.n_iter) return ST_NEED_MOVE;   // self_play.rs:283
-    if (it + 1 >= D.max_inline) return ST_CONTINUE;
+    inl++;
   }
 }
 
@@ -344,199 +499,50 @@ __device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_step: apply network outputs (expand + backup), then select the next leaf.  8 lanes per game.
+// K_step: one thread per game.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_step(Dev D) {
-  uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+__global__ void __launch_bounds__(STEP_THREADS) k_step(Dev D) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= D.n_slots) return;
-  Group g = make_group();
-  uint32_t st = D.state[slot];
+  const uint32_t st = D.slots[slot].state;
   if (st == ST_IDLE) return;
-  if (st == ST_NEED_MOVE) {  // reached n_iterations inside k_move's own advance()
-    if (g.l == 0) push_mover(D, slot);
+  if (st == ST_NEED_MOVE) {  // asked for compaction inside k_move's own run_game()
+    push_mover(D, slot);
     return;
   }
-  const uint32_t epoch = D.g->tick;
   Game G;
   load_game(D, slot, G);
   if (st == ST_WAIT_NN) {
-    // mask_policy + softmax (c4r.rs:272-286, mcts.rs:416-434) over the leaf's legal moves
-    const uint32_t row = D.nn_row[slot];
-    unsigned legal = c4::legal_mask(D.leaf_mask[slot]);
-    bool ok = (g.l < 7) && ((legal >> g.l) & 1u);
-    float x = ok ? D.logits[(size_t)row * 7 + g.l] : -c4::f32_inf();
-    float mx = x;
-#pragma unroll
-    for (int m = 1; m < 8; m <<= 1) mx = fmaxf(mx, gxor(g, mx, m));
-    float e = ok ? c4::c4_expf(x - mx) : 0.0f;
-    float s = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 7; i++) s = s + gshfl(g, e, i);  // left fold, as iter().sum()
-    float p = ok ? e / s : 0.0f;
-    // expand_leaf (mcts.rs:114-132): one new block holding the 7 children
-    uint32_t nb = G.n_alloc++;
-    if (nb >= D.cap) {
-      if (g.l == 0) D.g->error = C4A0_E_ENGINE;
-      return;
-    }
-    Block* B = G.arena + nb;
-    B->N[g.l] = 0u;
-    B->Qp[g.l] = 0.0f;
-    B->Qn[g.l] = 0.0f;
-    B->P[g.l] = p;
-    B->child[g.l] = 0u;
-    if (G.len == 0) {
-      G.root_block = nb;
-    } else if (g.l == 0) {
-      uint32_t e2 = G.path[G.len - 1];
-      G.arena[e2 >> 3].child[e2 & 7u] = nb;
-    }
-    G.depth += G.len;
-    backup(g, G, D.qp[row], D.qn[row]);
-    G.sims++;
-    G.evals++;
-    if (G.rootN >= D.n_iter) {  // self_play.rs:283-300: time to move (or finish)
-      store_game(D, g, G, ST_NEED_MOVE);
-      if (g.l == 0) push_mover(D, slot);
+    if (!apply_network(D, G, D.slots[slot].nn_row)) {
+      D.g->error = C4A0_E_ENGINE;
       return;
     }
   }
-  uint32_t ns = advance(D, g, G, epoch);
-  store_game(D, g, G, ns);
-  if (ns == ST_NEED_MOVE && g.l == 0) push_mover(D, slot);
+  const uint32_t ns = run_game(D, G);
+  store_game(D, G, ns);
+  if (ns == ST_NEED_MOVE) push_mover(D, slot);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_move: one CTA per game that has to move.
+// K_move: one CTA per game whose arena half is full — copy the live subtree breadth-first into the
+// other half, then let the game carry on.
 // ------------------------------------------------------------------------------------------------
-constexpr int MOVE_THREADS = 128;
-
-__device__ void seat_game(const Dev& D, uint32_t slot, uint32_t r) {
-  D.root_mask[slot] = 0ull;
-  D.root_value[slot] = 0ull;
-  D.root_N[slot] = 0u;
-  D.root_Qp[slot] = 0.0f;
-  D.root_Qn[slot] = 0.0f;
-  D.root_block[slot] = 0u;
-  D.half[slot] = 0u;
-  D.n_alloc[slot] = 1u;
-  D.req[slot] = r;
-  D.n_moves[slot] = 0u;
-  D.path_len[slot] = 0u;
-  D.state[slot] = ST_WAIT_NN;
-}
-
 __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
-  __shared__ uint32_t sh_src, sh_next, sh_head, sh_mode;  // mode: 0 re-root, 1 game over, 2 error
-  __shared__ Pos sh_newpos;
-  __shared__ uint32_t sh_newN;
-  __shared__ float sh_newQp, sh_newQn, sh_tqp, sh_tqn;
+  __shared__ uint32_t sh_next, sh_head;
   const uint32_t n_movers = D.g->n_movers;
-  const uint32_t epoch = D.g->tick;
-  const uint32_t n_req = D.g->n_req;
   for (uint32_t m = blockIdx.x; m < n_movers; m += gridDim.x) {
     const uint32_t slot = D.movers[m];
-    const uint32_t req = D.req[slot];
-    const uint32_t half = D.half[slot];
+    Slot* S = D.slots + slot;
+    const uint32_t half = S->half;
+    const uint32_t src_root = S->root_block;
     Block* src = arena_of(D, slot, half);
     Block* dst = arena_of(D, slot, half ^ 1u);
     if (threadIdx.x == 0) {
-      Pos root{D.root_mask[slot], D.root_value[slot]};
-      uint32_t rb = D.root_block[slot];
-      uint32_t nm = D.n_moves[slot];
-      // root_policy (mcts.rs:396-412): visit counts of the children, normalised
-      float pol[7], tempered[7];
-      const float uniform = 1.0f / 7.0f;
-      if (rb) {
-        float cnt[7], sum = 0.0f;
-        for (int i = 0; i < 7; i++) cnt[i] = (float)src[rb].N[i];
-        for (int i = 0; i < 7; i++) sum = sum + cnt[i];
-        for (int i = 0; i < 7; i++) pol[i] = (sum == 0.0f) ? uniform : cnt[i] / sum;
-      } else {
-        for (int i = 0; i < 7; i++) pol[i] = uniform;
-      }
-      // self_play.rs:294-299 + mcts.rs:214-222
-      float T = c4::temperature_for_ply(c4::ply(root.mask));
-      c4::apply_temperature7(pol, T, tempered);
-      int col = c4::weighted_sample7(tempered, c4::move_seed(D.game_id[req], (int)nm));
-      unsigned legal = c4::legal_mask(root.mask);
-      if (col < 0 || !((legal >> col) & 1u) || rb == 0u || nm >= 42u) {
-        // the reference panics here (mcts.rs:190-197); park the game and report
-        D.g->error = C4A0_E_ENGINE;
-        D.state[slot] = ST_IDLE;
-        atomicSub(&D.g->n_running, 1u);
-        sh_mode = 2u;
-      } else {
-        // RecordedMove (mcts.rs:198-203) goes straight into the sample store
-        size_t si = (size_t)req * MAXS + nm;
-        D.s_mask[si] = root.mask;
-        D.s_value[si] = root.value;
-        for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = pol[i];
-        D.n_moves[slot] = nm + 1u;
-        Pos np = c4::make_move(root, col);
-        sh_newpos = np;
-        sh_newN = src[rb].N[col];
-        sh_newQp = src[rb].Qp[col];
-        sh_newQn = src[rb].Qn[col];
-        sh_src = src[rb].child[col];
-        float tqp, tqn;
-        int t = c4::terminal_value(np, D.c_pen, &tqp, &tqn);
-        sh_tqp = tqp;
-        sh_tqn = tqn;
-        sh_mode = (t != c4::NONE) ? 1u : 0u;
-        atomicAdd(&D.g->moves, 1ull);
-      }
-    }
-    __syncthreads();
-    const uint32_t mode = sh_mode;
-    if (mode == 1u) {
-      // to_result (mcts.rs:271-313): alternate the terminal value back through the moves
-      const uint32_t L = D.n_moves[slot];
-      const float tqp = sh_tqp, tqn = sh_tqn;
-      for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) {
-        bool neg = ((L - k) & 1u) != 0;
-        size_t si = (size_t)req * MAXS + k;
-        D.s_qp[si] = neg ? -tqp : tqp;
-        D.s_qn[si] = neg ? -tqn : tqn;
-      }
-      if (threadIdx.x == 0) {
-        size_t si = (size_t)req * MAXS + L;
-        D.s_mask[si] = sh_newpos.mask;
-        D.s_value[si] = sh_newpos.value;
-        for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = 1.0f / 7.0f;
-        D.s_qp[si] = tqp;
-        D.s_qn[si] = tqn;
-        D.n_samples[req] = L + 1u;
-        atomicAdd(&D.g->samples, (unsigned long long)(L + 1u));
-        atomicAdd(&D.g->n_finished, 1u);
-        // the reference keeps simulating the terminal root until N >= n
-        uint32_t nN = sh_newN;
-        if (nN < D.n_iter) atomicAdd(&D.g->skipped_root_sims, (unsigned long long)(D.n_iter - nN));
-        // seat the next waiting request in this slot (self_play.rs:55-58 queues them all up front)
-        uint32_t r = atomicAdd(&D.g->next_req, 1u);
-        if (r < n_req) {
-          seat_game(D, slot, r);
-          publish_leaf(D, slot, Pos{0ull, 0ull}, epoch);
-        } else {
-          D.state[slot] = ST_IDLE;
-          atomicSub(&D.g->n_running, 1u);
-        }
-      }
-      __syncthreads();
-      continue;
-    }
-    if (mode == 2u) {
-      __syncthreads();
-      continue;
-    }
-    // ---- re-root: copy the kept subtree breadth-first into the other arena half -------------
-    if (threadIdx.x == 0) {
       sh_head = 1u;
-      sh_next = sh_src ? 2u : 1u;
+      sh_next = src_root ? 2u : 1u;
     }
-    if (sh_src && threadIdx.x < 10) {
-      reinterpret_cast<uint4*>(dst + 1)[threadIdx.x] = reinterpret_cast<const uint4*>(src + sh_src)[threadIdx.x];
-    }
+    if (src_root && threadIdx.x < 10)
+      reinterpret_cast<uint4*>(dst + 1)[threadIdx.x] = reinterpret_cast<const uint4*>(src + src_root)[threadIdx.x];
     __syncthreads();
     for (;;) {
       const uint32_t head = sh_head, tail = sh_next;  // blocks [head, tail) form one tree level
@@ -565,34 +571,21 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
       __syncthreads();
     }
     if (threadIdx.x == 0) {
-      D.root_mask[slot] = sh_newpos.mask;
-      D.root_value[slot] = sh_newpos.value;
-      D.root_N[slot] = sh_newN;
-      D.root_Qp[slot] = sh_newQp;
-      D.root_Qn[slot] = sh_newQn;
-      D.root_block[slot] = sh_src ? 1u : 0u;
-      D.half[slot] = half ^ 1u;
-      D.n_alloc[slot] = sh_next;
-      D.path_len[slot] = 0u;
+      S->root_block = src_root ? 1u : 0u;
+      S->half = half ^ 1u;
+      S->n_alloc = sh_next;
+      S->path_len = 0u;
       atomicAdd(&D.g->compacted_blocks, (unsigned long long)(sh_next - 1u));
-    }
-    __syncthreads();
-    // mcts.rs:205: select the new leaf under the new root
-    if (threadIdx.x < 8) {
-      Group g = make_group();
+      atomicAdd(&D.g->compactions, 1ull);
+      __threadfence_block();
       Game G;
       load_game(D, slot, G);
-      uint32_t ns = advance(D, g, G, epoch);
-      store_game(D, g, G, ns);
+      // the live subtree holds at most N_root blocks, so the fresh half always has room again
+      uint32_t ns = run_game(D, G);
+      store_game(D, G, ns);
     }
     __syncthreads();
   }
-}
-
-// First kernel of a tick: new epoch, empty mover list.
-__global__ void k_begin_step(Dev D) {
-  D.g->tick += 1u;
-  D.g->n_movers = 0u;
 }
 
 // Seat the first min(n_slots, n_req) games (self_play.rs:55-58).
@@ -608,96 +601,135 @@ __global__ void k_init(Dev D, uint32_t n_req) {
     *D.g = z;
   }
   if (slot >= D.n_slots) return;
-  D.c_sims[slot] = D.c_evals[slot] = D.c_term[slot] = D.c_depth[slot] = 0ull;
+  Slot S;
+  memset(&S, 0, sizeof(S));
+  S.n_alloc = 1u;
   if (slot < n_req) {
-    seat_game(D, slot, slot);
-    publish_leaf(D, slot, Pos{0ull, 0ull}, 1u);
-  } else {
-    D.state[slot] = ST_IDLE;
+    S.req = slot;
+    S.state = ST_WAIT_NN;
+    S.leaf_model = D.p0[slot];  // ply 0: player 0 moves (mcts.rs:70-76)
   }
+  D.slots[slot] = S;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_scan (one CTA): number the leaders in slot order -> urow[], n_rows; publish the tick's status
-// to the host.  K_pack: leaders write their planes to their row, every waiting game records the row
-// that will hold its answer.
+// K_post (cooperative): de-duplicate the waiting leaves, number the leaders in slot order, pack
+// their planes densely, publish the tick's status to the host, open the next tick.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool is_leader(const Dev& D, uint32_t slot) {
-  if (D.state[slot] != ST_WAIT_NN) return false;
-  if (!D.dedup) return true;
-  return (uint32_t)D.table[D.bucket[slot]] == slot;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(Dev D) {
-  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
-  __shared__ uint32_t warp_wait[SCAN_THREADS / 32];
-  const uint32_t per = (D.n_slots + SCAN_THREADS - 1) / SCAN_THREADS;
-  const uint32_t lo = threadIdx.x * per;
-  const uint32_t hi = min(lo + per, D.n_slots);
-  uint32_t cnt = 0, waiting = 0;
-  for (uint32_t s = lo; s < hi; s++) {
-    cnt += is_leader(D, s) ? 1u : 0u;
-    waiting += (D.state[s] == ST_WAIT_NN) ? 1u : 0u;
-  }
-  // block-wide exclusive scan of cnt
+__global__ void __launch_bounds__(POST_THREADS) k_post(Dev D) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t warp_cnt[POST_THREADS / 32];
+  __shared__ uint32_t warp_wait[POST_THREADS / 32];
+  __shared__ uint32_t sh_base;
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t epoch = D.g->tick;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t incl = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
+  Slot* S = D.slots + slot;
+  bool waiting = false;
+  uint64_t km = 0, kv = 0, kmod = 0;
+  if (slot < D.n_slots && S->state == ST_WAIT_NN) {
+    waiting = true;
+    km = S->leaf_mask;
+    kv = S->leaf_value;
+    kmod = S->leaf_model;
   }
-  uint32_t wsum = waiting;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
-  if (lane == 31) warp_sums[warp] = incl;
-  if (lane == 0) warp_wait[warp] = wsum;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t v = warp_sums[lane];
-    uint32_t iv = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, iv, d);
-      if (lane >= d) iv += t;
+  uint32_t bucket = 0;
+  if (D.dedup) {
+    // Table entry = epoch << 32 | leader slot; an entry of another epoch is empty, so the table is
+    // never cleared.  Among games with equal (position, model) the smallest slot becomes the
+    // leader (atomicMin) — deterministic whatever order the games arrive in.
+    if (waiting) {
+      uint32_t h = (uint32_t)splitmix64(km * 0x9E3779B97F4A7C15ULL ^ splitmix64(kv ^ kmod)) & D.table_mask;
+      const unsigned long long mine = ((unsigned long long)epoch << 32) | slot;
+      for (;;) {
+        unsigned long long* e = D.table + h;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e);
+        if ((uint32_t)(cur >> 32) != epoch) {
+          unsigned long long prev = atomicCAS(e, cur, mine);
+          if (prev == cur) break;  // first game with this key in this tick
+          cur = prev;
+          if ((uint32_t)(cur >> 32) != epoch) continue;
+        }
+        const Slot* Ld = D.slots + (uint32_t)cur;  // keys were written by an earlier kernel
+        if (Ld->leaf_mask == km && Ld->leaf_value == kv && Ld->leaf_model == kmod) {
+          atomicMin(e, mine);
+          break;
+        }
+        h = (h + 1) & D.table_mask;  // another key lives here: linear probing
+      }
+      bucket = h;
     }
-    warp_sums[lane] = iv - v;  // exclusive prefix of the warp totals
-    uint32_t ww = warp_wait[lane];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) ww += __shfl_xor_sync(0xffffffffu, ww, d);
-    if (lane == 31) {
-      uint32_t total = iv;
-      Globals* G = D.g;
-      G->n_rows = total;
-      G->rows_total += total;
-      G->leaves_total += ww;
-      HostStatus* hs = D.status;
-      hs->n_rows = total;
-      hs->n_finished = G->n_finished;
-      hs->n_running = G->n_running;
-      hs->n_movers = G->n_movers;
-      hs->error = G->error;
-      __threadfence_system();
-      hs->tick = G->tick;  // written last: the host spins on it
-    }
+    grid.sync();
+  }
+  uint32_t leader = slot;
+  if (waiting && D.dedup) leader = (uint32_t)D.table[bucket];
+  const bool lead = waiting && leader == slot;
+  // CTA-level exclusive scan of `lead`
+  const unsigned bal = __ballot_sync(0xffffffffu, lead);
+  const unsigned balw = __ballot_sync(0xffffffffu, waiting);
+  if (lane == 0) {
+    warp_cnt[warp] = __popc(bal);
+    warp_wait[warp] = __popc(balw);
   }
   __syncthreads();
-  uint32_t base = warp_sums[warp] + (incl - cnt);
-  for (uint32_t s = lo; s < hi; s++)
-    if (is_leader(D, s)) D.urow[s] = base++;
-}
-
-__global__ void __launch_bounds__(256) k_pack(Dev D) {
-  uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  if (slot >= D.n_slots) return;
-  if (D.state[slot] != ST_WAIT_NN) return;
-  const int l = threadIdx.x & 7;
-  uint32_t leader = D.dedup ? (uint32_t)D.table[D.bucket[slot]] : slot;
-  uint32_t row = D.urow[leader];
-  if (l == 0) D.nn_row[slot] = row;
-  if (leader == slot) {
-    if (l == 0) D.row_slot[row] = slot;
-    write_planes(D, l, row, Pos{D.leaf_mask[slot], D.leaf_value[slot]});
+  uint32_t before = 0, total = 0, wtotal = 0;
+#pragma unroll
+  for (int w = 0; w < POST_THREADS / 32; w++) {
+    before += (w < warp) ? warp_cnt[w] : 0u;
+    total += warp_cnt[w];
+    wtotal += warp_wait[w];
+  }
+  const uint32_t local = before + __popc(bal & ((1u << lane) - 1u));
+  // decoupled look-back over the CTAs before this one
+  if (threadIdx.x == 0) {
+    sh_base = 0u;
+    volatile unsigned long long* mine = D.cta_counts + blockIdx.x;
+    __threadfence();
+    *mine = ((unsigned long long)epoch << 32) | total;
+    if (wtotal) atomicAdd(&D.g->n_waiting, wtotal);
+  }
+  __syncthreads();
+  uint32_t part = 0;
+  for (uint32_t j = threadIdx.x; j < blockIdx.x; j += blockDim.x) {
+    volatile unsigned long long* p = D.cta_counts + j;
+    unsigned long long v;
+    do {
+      v = *p;
+    } while ((uint32_t)(v >> 32) != epoch);
+    part += (uint32_t)v;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  if (lane == 0 && part) atomicAdd(&sh_base, part);
+  __syncthreads();
+  const uint32_t base = sh_base;
+  if (lead) S->urow = base + local;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) D.g->n_rows = base + total;
+  grid.sync();
+  if (waiting) {
+    const uint32_t row = (leader == slot) ? base + local : D.slots[leader].urow;
+    S->nn_row = row;
+    if (leader == slot) {
+      D.row_slot[row] = slot;
+      write_planes(D, row, Pos{km, kv});
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    Globals* G = D.g;
+    const uint32_t rows = G->n_rows;
+    G->rows_total += rows;
+    G->leaves_total += G->n_waiting;
+    G->n_waiting = 0u;
+    HostStatus* hs = D.status;
+    hs->n_rows = rows;
+    hs->n_finished = G->n_finished;
+    hs->n_running = G->n_running;
+    hs->n_movers = G->n_movers;
+    hs->error = G->error;
+    __threadfence_system();
+    hs->tick = epoch;  // written last: the host spins on it
+    G->tick = epoch + 1u;  // open the next tick
+    G->n_movers = 0u;
   }
 }
 
@@ -713,8 +745,8 @@ __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float*
     qn[row] = 0.0f;
     return;
   }
-  uint32_t slot = D.row_slot[row];
-  uint64_t mask = D.leaf_mask[slot], value = D.leaf_value[slot], model = D.leaf_model[slot];
+  const Slot* S = D.slots + D.row_slot[row];
+  uint64_t mask = S->leaf_mask, value = S->leaf_value, model = S->leaf_model;
   uint64_t h = splitmix64(mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(value ^ model));
   for (int k = 0; k < 7; k++) {
     uint64_t hk = splitmix64(h + (uint64_t)k);
@@ -728,19 +760,20 @@ __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float*
 __global__ void k_gather_rows(Dev D, uint64_t* mask, uint64_t* value, uint64_t* model) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= D.g->n_rows) return;
-  uint32_t slot = D.row_slot[row];
-  mask[row] = D.leaf_mask[slot];
-  value[row] = D.leaf_value[slot];
-  model[row] = D.leaf_model[slot];
+  const Slot* S = D.slots + D.row_slot[row];
+  mask[row] = S->leaf_mask;
+  value[row] = S->leaf_value;
+  model[row] = S->leaf_model;
 }
 
 __global__ void k_sum_counters(Dev D, unsigned long long* out4) {
   unsigned long long a = 0, b = 0, c = 0, d = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.n_slots; i += gridDim.x * blockDim.x) {
-    a += D.c_sims[i];
-    b += D.c_evals[i];
-    c += D.c_term[i];
-    d += D.c_depth[i];
+    const Slot* S = D.slots + i;
+    a += S->c_sims;
+    b += S->c_exp;
+    c += S->c_term;
+    d += S->c_depth;
   }
   atomicAdd(out4 + 0, a);
   atomicAdd(out4 + 1, b);
@@ -760,6 +793,7 @@ struct c4a0_engine {
   size_t bytes = 0;
   bool io_bound = false, have_requests = false;
   uint32_t n_req = 0;
+  uint32_t post_grid = 0;
   uint64_t steps = 0;
   unsigned long long* scratch4 = nullptr;
   uint64_t *row_mask = nullptr, *row_value = nullptr, *row_model = nullptr;
@@ -792,18 +826,24 @@ int dalloc(c4a0_engine* e, T** p, size_t n) {
     }                                      \
   } while (0)
 
+int launch_post(c4a0_engine* e, cudaStream_t s) {
+  Dev d = e->D;
+  void* args[] = {&d};
+  CK(cudaLaunchCooperativeKernel((void*)k_post, dim3(e->post_grid), dim3(POST_THREADS), args, 0, s));
+  return 0;
+}
+
 // Enqueue one tick.  `ev` (3 events) brackets k_step and k_move when given.
 int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
   const Dev& D = e->D;
-  k_begin_step<<<1, 1, 0, s>>>(D);
   if (ev) CK(cudaEventRecord(ev[0], s));
-  k_step<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  k_step<<<blocks_for(D.n_slots, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
   if (ev) CK(cudaEventRecord(ev[1], s));
-  unsigned grid = D.n_slots < 148u * 8u ? D.n_slots : 148u * 8u;
+  unsigned grid = D.n_slots < 296u ? D.n_slots : 296u;
   k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
   if (ev) CK(cudaEventRecord(ev[2], s));
-  k_scan<<<1, SCAN_THREADS, 0, s>>>(D);
-  k_pack<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
+  int r = launch_post(e, s);
+  if (r) return r;
   CK(cudaGetLastError());
   e->steps++;
   return 0;
@@ -821,22 +861,36 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   if (cfg->n_slots == 0 || cfg->n_mcts_iterations == 0 || cfg->max_requests == 0)
     return fail(C4A0_E_INVALID, "n_slots, max_requests and n_mcts_iterations must be >= 1");
   if (cfg->plane_dtype > C4A0_PLANES_BF16) return fail(C4A0_E_INVALID, "bad plane_dtype");
-  if (cfg->plane_stride && (cfg->plane_stride < 84 || cfg->plane_stride % 4))
-    return fail(C4A0_E_INVALID, "plane_stride must be 0 or a multiple of 4 that is >= 84");
+  if (cfg->plane_stride && (cfg->plane_stride < 84 || cfg->plane_stride % 4 ||
+                            (cfg->plane_stride > 84 && cfg->plane_stride < 88)))
+    return fail(C4A0_E_INVALID, "plane_stride must be 0, 84, or a multiple of 4 that is >= 88");
   if (cfg->n_mcts_iterations > (1u << 24))
     return fail(C4A0_E_INVALID, "n_mcts_iterations above 2^24 is not exactly representable in f32");
   if (cfg->n_slots > (1u << 24)) return fail(C4A0_E_INVALID, "n_slots above 2^24 is not supported");
+  if (cfg->arena_blocks && cfg->arena_blocks < cfg->n_mcts_iterations + 2)
+    return fail(C4A0_E_INVALID, "arena_blocks must be 0 or >= n_mcts_iterations + 2");
+  if (cfg->arena_blocks >= (1u << 29)) return fail(C4A0_E_INVALID, "arena_blocks too large");
   int r = c4host::no_gpu_error();
   if (r) return r;
   CK(cudaSetDevice(cfg->device));
+  // k_post is a cooperative kernel: its whole grid must be resident at once
+  int per_sm = 0, sms = 0, coop = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_post, POST_THREADS, 0));
+  uint32_t post_grid = blocks_for(cfg->n_slots, POST_THREADS);
+  if (!coop || (uint64_t)post_grid > (uint64_t)per_sm * sms)
+    return fail(C4A0_E_INVALID, "n_slots=%u needs %u co-resident CTAs, device allows %d", cfg->n_slots, post_grid, per_sm * sms);
   c4a0_engine* e = new c4a0_engine();
   e->cfg = *cfg;
+  e->post_grid = post_grid;
   Dev& D = e->D;
   memset(&D, 0, sizeof(D));
   D.n_slots = cfg->n_slots;
   D.n_iter = cfg->n_mcts_iterations;
-  D.cap = cfg->n_mcts_iterations + 2;  // index 0 unused; at most n_iter expanded nodes per tree
-  D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : 8;
+  // index 0 is unused; a tree holds at most n_iter expanded nodes, so n_iter + 2 always suffices
+  D.cap = cfg->arena_blocks ? cfg->arena_blocks : cfg->n_mcts_iterations + 2;
+  D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : 2;
   D.plane_bf16 = cfg->plane_dtype == C4A0_PLANES_BF16;
   D.plane_stride = cfg->plane_stride ? cfg->plane_stride : 84;
   D.dedup = (cfg->flags & C4A0_FLAG_NO_DEDUP) ? 0u : 1u;
@@ -846,14 +900,9 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   size_t T = 1;
   while (T < 2 * S) T <<= 1;
   D.table_mask = (uint32_t)(T - 1);
-  DA(D.root_mask, S); DA(D.root_value, S); DA(D.leaf_mask, S); DA(D.leaf_value, S); DA(D.leaf_model, S);
-  DA(D.root_N, S); DA(D.root_block, S); DA(D.half, S); DA(D.n_alloc, S); DA(D.state, S);
-  DA(D.req, S); DA(D.n_moves, S); DA(D.path_len, S); DA(D.path, S * PATH_STRIDE);
-  DA(D.bucket, S); DA(D.urow, S); DA(D.nn_row, S); DA(D.row_slot, S);
-  DA(D.root_Qp, S); DA(D.root_Qn, S);
-  DA(D.c_sims, S); DA(D.c_evals, S); DA(D.c_term, S); DA(D.c_depth, S);
+  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
-  DA(D.table, T);
+  DA(D.table, T); DA(D.cta_counts, post_grid);
   uint64_t *gid, *p0, *p1;
   DA(gid, R); DA(p0, R); DA(p1, R);
   D.game_id = gid; D.p0 = p0; D.p1 = p1;
@@ -861,9 +910,10 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   DA(D.s_policy, R * MAXS * 7); DA(D.s_qp, R * MAXS); DA(D.s_qn, R * MAXS);
   DA(D.g, 1); DA(D.movers, S);
   DA(e->scratch4, 4); DA(e->row_mask, S); DA(e->row_value, S); DA(e->row_model, S);
-  cudaError_t err = cudaMemset(D.state, 0, S * sizeof(uint32_t));
+  cudaError_t err = cudaMemset(D.slots, 0, S * sizeof(Slot));
   if (err == cudaSuccess) err = cudaMemset(D.g, 0, sizeof(Globals));
   if (err == cudaSuccess) err = cudaMemset(D.table, 0, T * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(D.cta_counts, 0, post_grid * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_globals, sizeof(Globals));
   if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_status, sizeof(HostStatus), cudaHostAllocMapped);
   if (err == cudaSuccess) {
@@ -929,10 +979,11 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
     CK(cudaMemsetAsync(D.s_qn, 0, (size_t)n * MAXS * 4, s));
   }
   CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
+  CK(cudaMemsetAsync(D.cta_counts, 0, e->post_grid * sizeof(unsigned long long), s));
   k_init<<<blocks_for(D.n_slots, 256), 256, 0, s>>>(D, n);
-  k_scan<<<1, SCAN_THREADS, 0, s>>>(D);
-  k_pack<<<blocks_for((size_t)D.n_slots * 8, 256), 256, 0, s>>>(D);
   CK(cudaGetLastError());
+  int r = launch_post(e, s);
+  if (r) return r;
   CK(cudaStreamSynchronize(s));  // the host arrays may be freed by the caller after return
   e->n_req = n;
   e->have_requests = true;
@@ -981,7 +1032,7 @@ int c4a0_engine_poll(c4a0_engine* e, c4a0_progress* out, void* stream) {
   out->n_started = g.next_req < g.n_req ? g.next_req : g.n_req;
   out->n_finished = g.n_finished;
   out->n_running = g.n_running;
-  out->n_movers = g.n_movers;
+  out->n_movers = e->h_status->n_movers;
   out->n_rows = g.n_rows;
   out->error = g.error;
   if (g.error) return fail(C4A0_E_ENGINE, "%s", kEngineErr);
@@ -1010,6 +1061,7 @@ int c4a0_engine_stats(c4a0_engine* e, c4a0_stats* out, void* stream) {
   out->samples = g.samples;
   out->steps = e->steps;
   out->compacted_blocks = g.compacted_blocks;
+  out->compactions = g.compactions;
   return 0;
 }
 
@@ -1065,20 +1117,19 @@ int c4a0_engine_slot_info(c4a0_engine* e, uint32_t slot, c4a0_slot_info* out, vo
   if (!e || !out) return fail(C4A0_E_INVALID, "null argument");
   if (slot >= e->D.n_slots) return fail(C4A0_E_INVALID, "slot out of range");
   cudaStream_t s = (cudaStream_t)stream;
-  const Dev& D = e->D;
-  uint32_t na;
-  CK(cudaMemcpyAsync(&out->state, D.state + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->request, D.req + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->n_moves, D.n_moves + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->root_visits, D.root_N + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->root_mask, D.root_mask + slot, 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->root_value, D.root_value + slot, 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->root_q_sum_penalty, D.root_Qp + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->root_q_sum_no_penalty, D.root_Qn + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&na, D.n_alloc + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&out->nn_row, D.nn_row + slot, 4, cudaMemcpyDeviceToHost, s));
+  Slot S;
+  CK(cudaMemcpyAsync(&S, e->D.slots + slot, sizeof(Slot), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  out->n_blocks = na ? na - 1 : 0;
+  out->state = S.state;
+  out->request = S.req;
+  out->n_moves = S.n_moves;
+  out->root_visits = S.root_N;
+  out->root_mask = S.root_mask;
+  out->root_value = S.root_value;
+  out->root_q_sum_penalty = S.root_Qp;
+  out->root_q_sum_no_penalty = S.root_Qn;
+  out->n_blocks = S.n_alloc ? S.n_alloc - 1 : 0;
+  out->nn_row = S.nn_row;
   return 0;
 }
 
@@ -1113,25 +1164,22 @@ struct Dumper {
 int c4a0_engine_dump_tree(c4a0_engine* e, uint32_t slot, uint32_t* buf, size_t cap, size_t* needed,
                           void* stream) {
   if (!e || !needed) return fail(C4A0_E_INVALID, "null argument");
-  c4a0_slot_info info;
-  int r = c4a0_engine_slot_info(e, slot, &info, stream);
-  if (r) return r;
+  if (slot >= e->D.n_slots) return fail(C4A0_E_INVALID, "slot out of range");
   cudaStream_t s = (cudaStream_t)stream;
   const Dev& D = e->D;
-  uint32_t half, rb;
-  CK(cudaMemcpyAsync(&half, D.half + slot, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&rb, D.root_block + slot, 4, cudaMemcpyDeviceToHost, s));
+  Slot S;
+  CK(cudaMemcpyAsync(&S, D.slots + slot, sizeof(Slot), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  std::vector<Block> host(info.n_blocks + 1);
-  const Block* src = D.blocks + ((size_t)slot * 2 + half) * D.cap;
+  std::vector<Block> host(S.n_alloc ? S.n_alloc : 1);
+  const Block* src = D.blocks + ((size_t)slot * 2 + S.half) * D.cap;
   CK(cudaMemcpyAsync(host.data(), src, host.size() * sizeof(Block), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   Dumper d{host.data(), buf, buf ? cap : 0, 0};
-  d.put(rb ? 2u : 1u);
-  d.put(info.root_visits);
-  d.put(c4::f32_bits(info.root_q_sum_penalty));
-  d.put(c4::f32_bits(info.root_q_sum_no_penalty));
-  if (rb) d.children(rb, Pos{info.root_mask, info.root_value});
+  d.put(S.root_block ? 2u : 1u);
+  d.put(S.root_N);
+  d.put(c4::f32_bits(S.root_Qp));
+  d.put(c4::f32_bits(S.root_Qn));
+  if (S.root_block) d.children(S.root_block, Pos{S.root_mask, S.root_value});
   *needed = d.w;
   return 0;
 }

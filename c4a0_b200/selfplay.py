@@ -35,7 +35,7 @@ from .engine import Engine, GameSamples, run_engines
 
 # process-wide defaults, overridable by tools (bench.py turns kernel sampling on)
 DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 2, "dedup": True,
-            "max_inline_sims": 0}
+            "max_inline_sims": 0, "arena_blocks": None}
 
 BUCKETS = (128, 256, 512, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072)
 
@@ -93,11 +93,13 @@ def _sum_stats(stats: List[dict]) -> dict:
 class _Lane:
     """One engine + its NN I/O tensors + its stream."""
 
-    def __init__(self, n_slots, max_requests, n_iter, c_expl, c_pen, plane_dtype, device, max_inline, stride, flags):
+    def __init__(self, n_slots, max_requests, n_iter, c_expl, c_pen, plane_dtype, device, max_inline, stride, flags,
+                 arena_blocks):
         self.n_slots = n_slots
         self.engine = Engine(
             n_slots, max(1, max_requests), n_iter, c_expl, c_pen,
             L.PLANES_BF16 if plane_dtype == torch.bfloat16 else L.PLANES_F32, max_inline, device.index, stride, flags,
+            arena_blocks,
         )
         self.planes = torch.zeros(n_slots, stride, dtype=plane_dtype, device=device)
         self.logits = torch.zeros(n_slots, 7, dtype=torch.float32, device=device)
@@ -153,6 +155,7 @@ class SelfPlaySession:
         plane_stride: int = 84,
         n_lanes: Optional[int] = None,
         dedup: Optional[bool] = None,
+        arena_blocks: Optional[int] = None,
     ):
         if not torch.cuda.is_available():
             raise RuntimeError("c4a0_b200 needs a CUDA device: there is no CPU fallback")
@@ -169,10 +172,18 @@ class SelfPlaySession:
         self.plane_dtype = plane_dtype
         self.plane_stride = plane_stride
         flags = 0 if dedup else L.FLAG_NO_DEDUP
+        if arena_blocks is None:
+            arena_blocks = DEFAULTS["arena_blocks"]
+        if arena_blocks is None:
+            # Roomy arena halves make re-rooting copy-free (see engine.cu): up to 8x the minimum,
+            # within a third of the free device memory.  2 halves x 160 B per block per game.
+            free_b, _ = torch.cuda.mem_get_info(self.device)
+            minimum = n_mcts_iterations + 2
+            arena_blocks = max(minimum, min(8 * minimum, int(free_b / 3) // (n_slots * 320)))
         per = [(n_slots + i) // n_lanes for i in range(n_lanes)][::-1]
         self.lanes = [
             _Lane(s, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, self.device,
-                  max_inline_sims, plane_stride, flags)
+                  max_inline_sims, plane_stride, flags, arena_blocks)
             for s in per if s > 0
         ]
 

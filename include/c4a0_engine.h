@@ -63,11 +63,13 @@ typedef struct {
   float c_exploration;
   float c_ply_penalty;
   uint32_t plane_dtype;        /* C4A0_PLANES_F32 | C4A0_PLANES_BF16 */
-  uint32_t max_inline_sims;    /* terminal-leaf simulations a game may run inside one step (0 = 8) */
+  uint32_t max_inline_sims;    /* terminal-leaf simulations a game may run inside one step (0 = 2) */
   int32_t device;              /* CUDA device ordinal */
   uint32_t plane_stride;       /* elements between consecutive rows of planes_dev (0 = 84; a multiple of
                                   4, >= 84; elements 84.. of a row are never written) */
   uint32_t flags;              /* C4A0_FLAG_* */
+  uint32_t arena_blocks;       /* tree blocks (160 B) per arena half per game; 0 = n_mcts_iterations + 2,
+                                  the minimum.  Larger halves make re-rooting copy-free until a half fills. */
 } c4a0_config;
 
 /* Evaluate every waiting leaf even when several games wait on the same (position, model); by default
@@ -96,7 +98,8 @@ typedef struct {
   uint64_t select_depth_sum;   /* sum over sims of the depth of the selected leaf */
   uint64_t expansions;         /* nodes expanded (== non-terminal leaves applied) */
   uint64_t steps;              /* c4a0_engine_step() calls since set_requests() */
-  uint64_t compacted_blocks;   /* tree blocks copied by re-rooting (mcts.rs:187-206 keeps the subtree) */
+  uint64_t compacted_blocks;   /* tree blocks copied when an arena half filled up */
+  uint64_t compactions;        /* number of such copies (re-roots that fit the arena copy nothing) */
 } c4a0_stats;
 
 const char *c4a0_last_error(void);
@@ -125,11 +128,11 @@ int c4a0_engine_bind_io(c4a0_engine *e, void *planes_dev, const float *logits_de
 int c4a0_engine_set_requests(c4a0_engine *e, const uint64_t *game_id, const uint64_t *player0_id,
                              const uint64_t *player1_id, uint32_t n, void *stream);
 
-/* One lockstep tick: consume the network outputs for every row in WAIT_NN (mask+softmax, expand,
- * negamax backup: mcts.rs:83-155), play the move of every game whose root reached
- * n_mcts_iterations (temperature + seeded sample + re-root: self_play.rs:283-300,
- * mcts.rs:187-222), emit finished games (mcts.rs:271-313) and seat waiting requests in their slots,
- * then select every game's next leaf (mcts.rs:160-183) and write its planes. */
+/* One lockstep tick: every game consumes its network answer (mask+softmax, expand, negamax
+ * backup: mcts.rs:83-155), plays its move if the root reached n_mcts_iterations (temperature +
+ * seeded sample + re-root: self_play.rs:283-300, mcts.rs:187-222), is emitted if that ended it
+ * (mcts.rs:271-313; the next waiting request takes its slot) and selects its next leaf
+ * (mcts.rs:160-183); the distinct waiting leaves are then packed as rows [0, n_rows) of planes_dev. */
 int c4a0_engine_step(c4a0_engine *e, void *stream);
 
 /* step() with CUDA events around its two kernels (synchronises): device milliseconds of the
