@@ -125,6 +125,7 @@ SIGNATURES = {
     "c4a0_engine_set_requests": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P]),
     "c4a0_engine_step": (C.c_int, [_P, _P]),
     "c4a0_engine_step_timed": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "c4a0_engine_debug_phases": (C.c_int, [_P, _P, _P]),
     "c4a0_engine_eval_builtin": (C.c_int, [_P, C.c_int, _P]),
     "c4a0_engine_poll": (C.c_int, [_P, C.POINTER(Progress), _P]),
     "c4a0_engine_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),

@@ -141,6 +141,8 @@ struct Dev {  // passed to kernels by value
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
+  // optional per-slot phase timing of k_step (8 x u32 cycles per slot), see c4a0_engine_debug_phases
+  uint32_t* dbg;
 };
 
 __device__ __forceinline__ Block* arena_of(const Dev& D, uint32_t slot, uint32_t half) {
@@ -466,17 +468,29 @@ __device__ __noinline__ MoveResult play_move(const Dev& D, Game& G) {
 
 // Advance a game until it needs the network (WAIT_NN), has used its in-kernel budget of
 // terminal-leaf simulations (CONTINUE), needs its tree compacted (NEED_MOVE) or has no game (IDLE).
-__device__ __forceinline__ uint32_t run_game(const Dev& D, Game& G) {
+struct PhaseClock {  // cycles spent per phase by one thread (debug only)
+  uint32_t move = 0, select = 0, term = 0, n_select = 0, max_len = 0;
+};
+
+__device__ __forceinline__ uint32_t run_game(const Dev& D, Game& G, PhaseClock* pc = nullptr) {
   uint32_t inl = 0;
   for (;;) {
     if (G.rootN >= D.n_iter) {  // self_play.rs:283: checked after every simulation
+      long long c0 = pc ? clock64() : 0;
       MoveResult r = play_move(D, G);
+      if (pc) pc->move += (uint32_t)(clock64() - c0);
       if (r == MV_IDLE) return ST_IDLE;
       if (r == MV_COMPACT) return ST_NEED_MOVE;
       continue;
     }
     if (inl >= D.max_inline) return ST_CONTINUE;
+    long long c1 = pc ? clock64() : 0;
     Pos leaf = select_leaf(D, G);
+    if (pc) {
+      pc->select += (uint32_t)(clock64() - c1);
+      pc->n_select++;
+      pc->max_len = G.len > pc->max_len ? G.len : pc->max_len;
+    }
     float tqp, tqn;
     int t = c4::terminal_value(leaf, D.c_pen, &tqp, &tqn);
     if (t == c4::NONE) {
@@ -485,11 +499,13 @@ __device__ __forceinline__ uint32_t run_game(const Dev& D, Game& G) {
       return ST_WAIT_NN;
     }
     // terminal leaf: mcts.rs:92-98 — no expansion, back up the objective value
+    long long c2 = pc ? clock64() : 0;
     G.depth += G.len;
     backup(G, tqp, tqn);
     G.sims++;
     G.term++;
     inl++;
+    if (pc) pc->term += (uint32_t)(clock64() - c2);
   }
 }
 
@@ -510,17 +526,34 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(Dev D) {
     push_mover(D, slot);
     return;
   }
+  const bool prof = D.dbg != nullptr;
+  const long long t0 = prof ? clock64() : 0;
   Game G;
   load_game(D, slot, G);
+  const long long t1 = prof ? clock64() : 0;
   if (st == ST_WAIT_NN) {
     if (!apply_network(D, G, D.slots[slot].nn_row)) {
       D.g->error = C4A0_E_ENGINE;
       return;
     }
   }
-  const uint32_t ns = run_game(D, G);
+  const long long t2 = prof ? clock64() : 0;
+  PhaseClock pc;
+  const uint32_t ns = run_game(D, G, prof ? &pc : nullptr);
+  const long long t3 = prof ? clock64() : 0;
   store_game(D, G, ns);
   if (ns == ST_NEED_MOVE) push_mover(D, slot);
+  if (prof) {
+    uint32_t* o = D.dbg + (size_t)slot * 8;
+    o[0] = (uint32_t)(t1 - t0);          // load slot state
+    o[1] = (uint32_t)(t2 - t1);          // softmax + expand + backup
+    o[2] = pc.move;                      // play_move
+    o[3] = pc.select;                    // select_leaf (all passes)
+    o[4] = pc.term;                      // terminal-leaf backups
+    o[5] = pc.n_select | (pc.max_len << 8);
+    o[6] = (uint32_t)(clock64() - t3);   // store
+    o[7] = (uint32_t)(clock64() - t0);   // whole thread
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1012,6 +1045,26 @@ int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* 
   if (ms_step) *ms_step = a;
   if (ms_move) *ms_move = b;
   return 0;
+}
+
+int c4a0_engine_debug_phases(c4a0_engine* e, void* stream, uint32_t* out8_per_slot) {
+  if (!e || !out8_per_slot) return fail(C4A0_E_INVALID, "null argument");
+  if (!e->have_requests) return fail(C4A0_E_INVALID, "set_requests() must precede step()");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t n = (size_t)e->D.n_slots * 8;
+  uint32_t* d = nullptr;
+  CK(cudaMalloc((void**)&d, n * 4));
+  CK(cudaMemsetAsync(d, 0, n * 4, s));
+  e->D.dbg = d;
+  int r = launch_tick(e, s, nullptr);
+  e->D.dbg = nullptr;
+  if (!r) {
+    cudaError_t err = cudaMemcpyAsync(out8_per_slot, d, n * 4, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) r = fail(C4A0_E_CUDA, "debug copy failed: %s", cudaGetErrorString(err));
+  }
+  cudaFree(d);
+  return r;
 }
 
 int c4a0_engine_eval_builtin(c4a0_engine* e, int kind, void* stream) {

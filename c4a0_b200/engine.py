@@ -96,6 +96,12 @@ class Engine:
         L.check(self._lib.c4a0_engine_step_timed(self._h, stream, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def debug_phases(self, stream: int = 0) -> np.ndarray:
+        """One step() with per-game cycle counters: [n_slots, 8] uint32 (see the header)."""
+        out = np.zeros((self.n_slots, 8), np.uint32)
+        L.check(self._lib.c4a0_engine_debug_phases(self._h, stream, L.ptr(out)))
+        return out
+
     def eval_builtin(self, kind: int, stream: int = 0) -> None:
         L.check(self._lib.c4a0_engine_eval_builtin(self._h, kind, stream))
 
