@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sample-kernels-every", type=int, default=53)
-    ap.add_argument("--lanes", type=int, default=2, help="engines per GPU (2 = tree ticks overlap the other half's network)")
+    ap.add_argument("--lanes", type=int, default=1, help="engines per GPU (2 = tree ticks overlap the other half's network)")
     ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
     ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
     ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")

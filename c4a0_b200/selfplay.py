@@ -34,7 +34,7 @@ from . import _lib as L
 from .engine import Engine, GameSamples, run_engines
 
 # process-wide defaults, overridable by tools (bench.py turns kernel sampling on)
-DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 2, "dedup": True,
+DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 1, "dedup": True,
             "max_inline_sims": 0, "arena_blocks": None}
 
 BUCKETS = (128, 256, 512, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072)
