@@ -1,0 +1,71 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/c4a0_engine.h declares;
+compute entry points fail loudly without a GPU (no CPU fallback)."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "c4a0_engine.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(c4a0_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from c4a0_b200 import _lib as L
+
+    lib = L.lib()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in L.SIGNATURES, f"{n} has no ctypes signature"
+    assert lib.c4a0_abi_version() == 1
+
+
+def test_struct_sizes_match_the_header():
+    from c4a0_b200 import _lib as L
+
+    assert C.sizeof(L.Config) == 11 * 4
+    assert C.sizeof(L.Progress) == 7 * 4
+    assert C.sizeof(L.Stats) == 12 * 8
+    assert C.sizeof(L.RunReport) == 3 * 8 + 2 * 8 + 8 + 2 * 8 + 32 * 8
+    assert C.sizeof(L.NNGraph) == 16
+
+
+def test_no_cpu_fallback():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from c4a0_b200 import _lib as L
+    from c4a0_b200 import engine as E
+
+    with pytest.raises(L.EngineError) as ei:
+        E.Engine(4, 4, 10, 1.0, 0.01)
+    assert ei.value.code == L.E_CUDA and "no CPU fallback" in str(ei.value)
+    with pytest.raises(L.EngineError):
+        E.rules_batch([0], [0])
+    with pytest.raises(L.EngineError):
+        E.math_batch(L.MATH_LOGF, np.ones(4, np.float32))
+    import c4a0_rust as R
+
+    with pytest.raises(RuntimeError):
+        R.play_games([R.GameMetadata(0, 0, 0)], 4, 2, 1.0, 0.01, lambda m, p: None)
+
+
+def test_product_does_not_import_the_oracle():
+    bad = []
+    for pkg in ("c4a0_b200", "c4a0_rust"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dirpath, f), errors="replace").read()
+                    if re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M) or "c4a0_oracle" in txt or "c4o_" in txt:
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
