@@ -131,8 +131,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm: oracle/selfplay_threads.cpp (the reference's thread/channel architecture)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(n_games: int, n_iter: int, width: int, nn_device: str):
-    """Returns dict(positions, sims, seconds, threads, nn_batches)."""
+def cpu_reference_run(n_games: int, n_iter: int, width: int, nn_device: str, max_sims: int = 0):
+    """The oracle's threaded port of rust/src/self_play.rs on the host cores.  max_sims > 0 stops
+    the run after that many simulations (time-boxed sample at full concurrency).
+    Returns dict(positions, moves, sims, seconds, threads, nn_batches)."""
     import oracle
 
     model = make_model(width, torch.float32, nn_device)
@@ -158,31 +160,40 @@ def cpu_reference_run(n_games: int, n_iter: int, width: int, nn_device: str):
     nb = C.c_uint64(0)
     threads = max(1, (os.cpu_count() or 2) - 1)  # self_play.rs:78
     t0 = time.perf_counter()
-    rc = L.c4o_self_play_threaded(
-        md, n_games, 2000, n_iter, C_EXPLORATION, C_PLY_PENALTY, C.cast(fn, C.c_void_p), None, threads, out, out_n,
-        C.byref(st), C.byref(nb),
+    rc = L.c4o_self_play_threaded_budget(
+        md, n_games, 2000, n_iter, C_EXPLORATION, C_PLY_PENALTY, C.cast(fn, C.c_void_p), None, threads, max_sims,
+        out, out_n, C.byref(st), C.byref(nb),
     )
     dt = time.perf_counter() - t0
     if rc != 0:
         raise RuntimeError(f"CPU reference self-play failed rc={rc}")
-    return dict(positions=int(st.samples), sims=int(st.sims), seconds=dt, threads=threads + 1, nn_batches=int(nb.value))
+    finished = sum(1 for i in range(n_games) if out_n[i] > 0)
+    return dict(positions=int(st.samples), moves=int(st.moves), finished=finished, sims=int(st.sims), seconds=dt,
+                threads=threads + 1, nn_batches=int(nb.value))
+
+
+CPU_GAMES = 1000  # BASELINE.json configs[0]: the reference's own CPU-runnable case (1,000 games x 600 sims)
 
 
 def cpu_baseline(args, budget_s: float) -> dict:
+    """Time-boxed sample of configs[0] at its full concurrency (1,000 games in flight, which sets the
+    reference's NN batch size).  Every move yields exactly one training position at game end
+    (mcts.rs:198-203, 271-313) and every finished game one more, so positions/s of the sample =
+    (moves + finished games) / seconds."""
     nn_device = "cuda:0" if torch.cuda.is_available() else "cpu"
-    probe_games = 16
-    probe = cpu_reference_run(probe_games, args.sims, args.width, nn_device)
+    probe = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=150_000)
     rate = probe["sims"] / probe["seconds"]
-    sims_per_game = probe["sims"] / probe_games
-    n = int(max(32, min(1000, rate * budget_s / sims_per_game)))
-    run = cpu_reference_run(n, args.sims, args.width, nn_device)
+    budget = int(max(300_000, rate * budget_s))
+    run = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=budget)
+    positions = run["moves"] + run["finished"]
     return {
-        "value": run["positions"] / run["seconds"],
+        "value": positions / run["seconds"],
         "unit": UNIT,
         "cores": run["threads"],
         "kind": "port",
-        "sample": f"{n} concurrent games x {args.sims} sims/move (game_id 0..{n - 1}) of the same workload, "
-                  f"threaded port of rust/src/self_play.rs, fp32 network via numpy callback on {nn_device}",
+        "sample": f"first {run['sims']} simulations ({run['seconds']:.1f} s) of {CPU_GAMES} concurrent games x {args.sims} "
+                  f"sims/move (BASELINE configs[0]); threaded port of rust/src/self_play.rs on the host cores, fp32 "
+                  f"network via the numpy callback on {nn_device}; positions = moves made + games finished",
         "sims_per_s": run["sims"] / run["seconds"],
         "seconds": run["seconds"],
         "host_cpus": os.cpu_count(),

@@ -9,12 +9,13 @@
 //     and holds the statistics of its 7 children column-wise (N[8], Qp[8], Qn[8], P[8], child[8]),
 //     i.e. exactly the fields UCT selection reads for one level (mcts.rs:359-388), fetched as
 //     16-byte vectors.  Node positions are never stored: selection replays the moves on bitboards.
-//   * One THREAD owns one game for a whole tick (k_step): it consumes the network's answer
-//     (mask + softmax + expand + backup, mcts.rs:83-155), plays the move when the root reached
-//     n_iterations (temperature + seeded sample + re-root, self_play.rs:283-300, mcts.rs:187-222),
-//     finishes / re-seats the game, and selects the next leaf (mcts.rs:160-183).  The work of one
-//     tick is a short dependent chain per game, so what matters is the length of that chain, not
-//     lanes per game; 32 independent games per warp give the memory system 32x the requests.
+//   * Eight lanes own one game for a whole tick (k_step; four games per warp, warp-uniform control
+//     flow): they consume the network's answer (mask + softmax + expand + backup, mcts.rs:83-155),
+//     play the move when the root reached n_iterations (temperature + seeded sample + re-root,
+//     self_play.rs:283-300, mcts.rs:187-222), finish / re-seat the game, and select the next leaf
+//     (mcts.rs:160-183; lane c evaluates child c, argmax = 3 shuffle steps + a ballot with the
+//     reference's last-maximum tie-break).  A tick is a dependent chain per game; the 7-way UCT
+//     math, the softmax and the move sampling are the parts that shorten when spread over lanes.
 //   * Backup walks the path recorded by selection: one f32 add per node per simulation in
 //     simulation order — the reference's accumulation order.
 //   * Re-rooting keeps the chosen child's subtree and drops the siblings.  Nothing is copied while
@@ -86,7 +87,7 @@ static_assert(sizeof(Slot) == 128, "slot state must be one cache line");
 
 constexpr int PATH_STRIDE = 44;  // <= 42 levels below a root
 constexpr int MAXS = C4A0_MAX_SAMPLES;
-constexpr int STEP_THREADS = 128;
+constexpr int STEP_THREADS = 256;
 constexpr int POST_THREADS = 256;
 constexpr int MOVE_THREADS = 128;
 enum : uint32_t { ST_IDLE = 0, ST_WAIT_NN = 1, ST_CONTINUE = 2, ST_NEED_MOVE = 3 };
@@ -197,8 +198,47 @@ __device__ __forceinline__ void write_planes(const Dev& D, uint32_t row, Pos p) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-game working set (registers of the owning thread)
+// Eight lanes per game, four games per warp.  Lane c (< 7) owns child / column c of whatever node
+// the game is looking at; lane 7 rides along.  ALL control flow is warp-uniform: every lane of the
+// warp executes every shuffle (constant full mask, width 8), and per-game decisions are predicates.
+// What matters for a tick is the length of the dependent chain per game, and the 7-way UCT math,
+// the softmax and the move sampling are exactly the parts that parallelise across the lanes.
 // ------------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Lanes {
+  int l;           // 0..7 within the game
+  unsigned gbase;  // first lane of the game within the warp (0, 8, 16, 24)
+};
+__device__ __forceinline__ Lanes make_lanes() {
+  int lane = threadIdx.x & 31;
+  return Lanes{lane & 7, (unsigned)(lane & 24)};
+}
+template <typename T>
+__device__ __forceinline__ T gshfl(T v, int src) {
+  return __shfl_sync(FULL, v, src, 8);
+}
+template <typename T>
+__device__ __forceinline__ T gxor(T v, int m) {
+  return __shfl_xor_sync(FULL, v, m, 8);
+}
+__device__ __forceinline__ unsigned gballot(const Lanes& L, bool p) {
+  return (__ballot_sync(FULL, p) >> L.gbase) & 0xffu;
+}
+// ((((((v0+v1)+v2)+v3)+v4)+v5)+v6): the reference's iter().sum() over the seven columns
+__device__ __forceinline__ float fold7(float v) {
+  float s = gshfl(v, 0);
+#pragma unroll
+  for (int i = 1; i < 7; i++) s = s + gshfl(v, i);
+  return s;
+}
+__device__ __forceinline__ float gmax8(float v) {
+#pragma unroll
+  for (int m = 1; m < 8; m <<= 1) v = fmaxf(v, gxor(v, m));
+  return v;
+}
+
+// Per-game working set: group-uniform values, held redundantly by the 8 lanes.
 struct Game {
   uint32_t slot;
   Pos root, leaf;
@@ -207,11 +247,11 @@ struct Game {
   float rootQp, rootQn;
   Block* arena;
   uint32_t* path;
-  unsigned long long sims, exps, term, depth;
+  uint32_t sims, exps, term, depth;
 };
 
 __device__ __forceinline__ void load_game(const Dev& D, uint32_t slot, Game& G) {
-  const Slot* S = D.slots + slot;
+  const Slot* S = D.slots + slot;  // all 8 lanes read the same line: one broadcast transaction
   G.slot = slot;
   G.root.mask = S->root_mask;
   G.root.value = S->root_value;
@@ -231,7 +271,7 @@ __device__ __forceinline__ void load_game(const Dev& D, uint32_t slot, Game& G) 
   G.path = D.path + (size_t)slot * PATH_STRIDE;
   G.sims = G.exps = G.term = G.depth = 0;
 }
-__device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t state) {
+__device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t state) {  // one lane
   Slot* S = D.slots + G.slot;
   S->root_mask = G.root.mask;
   S->root_value = G.root.value;
@@ -254,39 +294,26 @@ __device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t
   if (G.depth) S->c_depth += G.depth;
 }
 
-// mcts.rs:137-155 — add (qp, qn) at the leaf, alternate the sign towards the root.  The path
-// nodes are distinct, so their read-modify-writes are independent: issue them four at a time.
-__device__ __forceinline__ void backup(Game& G, float qp, float qn) {
-  const uint32_t len = G.len;
-  for (uint32_t j0 = 0; j0 < len; j0 += 4) {
-    uint32_t e[4], n[4];
-    float a[4], b[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) e[k] = (j0 + k < len) ? G.path[j0 + k] : 0u;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (j0 + k < len) {
-        const Block* B = G.arena + (e[k] >> 3);
-        uint32_t c = e[k] & 7u;
-        n[k] = B->N[c];
-        a[k] = B->Qp[c];
-        b[k] = B->Qn[c];
-      }
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (j0 + k < len) {
-        Block* B = G.arena + (e[k] >> 3);
-        uint32_t c = e[k] & 7u;
-        bool neg = ((len - 1 - (j0 + k)) & 1u) != 0;
-        B->N[c] = n[k] + 1u;
-        B->Qp[c] = a[k] + (neg ? -qp : qp);
-        B->Qn[c] = b[k] + (neg ? -qn : qn);
-      }
+// mcts.rs:137-155 — add (qp, qn) at the leaf, alternate the sign towards the root.  The path nodes
+// are distinct, so lanes update them in parallel: one f32 add per node per simulation.
+__device__ __forceinline__ void backup(const Lanes& L, Game& G, bool pred, float qp, float qn) {
+  __syncwarp();  // path[] (written by lane 0) and earlier block writes are visible
+  if (pred) {
+    for (uint32_t j = L.l; j < G.len; j += 8) {
+      uint32_t e = G.path[j];
+      Block* B = G.arena + (e >> 3);
+      uint32_t c = e & 7u;
+      bool neg = ((G.len - 1 - j) & 1u) != 0;
+      B->N[c] += 1u;
+      B->Qp[c] += neg ? -qp : qp;
+      B->Qn[c] += neg ? -qn : qn;
+    }
+    bool neg = (G.len & 1u) != 0;
+    G.rootN += 1u;
+    G.rootQp += neg ? -qp : qp;
+    G.rootQn += neg ? -qn : qn;
   }
-  bool neg = (len & 1u) != 0;
-  G.rootN += 1u;
-  G.rootQp += neg ? -qp : qp;
-  G.rootQn += neg ? -qn : qn;
+  __syncwarp();  // statistics visible to the selection that follows
 }
 
 // mcts.rs:359-388: -(Qp/(N+1)) + c * (sqrt(ln(N_parent)/(N+1)) * (P + 1e-8)), f32, no contraction
@@ -298,74 +325,90 @@ __device__ __forceinline__ float uct(uint32_t n, float qs, float pr, float lnp, 
   return (-q) + (c_expl * ex);
 }
 
-// mcts.rs:160-183 — walk from the root to a node without children; records the path.
-__device__ __forceinline__ Pos select_leaf(const Dev& D, Game& G) {
+// order-preserving map f32 -> u32 (never 0), with -0.0 folded onto +0.0 like a float comparison
+__device__ __forceinline__ uint32_t ordkey(float u) {
+  uint32_t b = __float_as_uint(u + 0.0f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// mcts.rs:160-183 — walk from the root to a node without children; records the path.  One tree
+// level per iteration for every game of the warp that is still descending.
+__device__ __forceinline__ Pos select_leaf(const Dev& D, const Lanes& L, Game& G, bool pred) {
   Pos pos = G.root;
-  uint32_t np = G.rootN, b = G.root_block, len = 0;
-  while (b != 0u && len < 43u) {  // a tree is at most 42 plies deep
-    const uint4* V = reinterpret_cast<const uint4*>(G.arena + b);
-    const uint4 n0 = V[0], n1 = V[1], q0 = V[2], q1 = V[3], p0 = V[6], p1 = V[7], c0 = V[8], c1 = V[9];
+  uint32_t np = G.rootN, b = pred ? G.root_block : 0u, len = 0;
+  while (__any_sync(FULL, b != 0u)) {
+    const bool act = b != 0u;
+    uint32_t n = 0u, ch = 0u;
+    float qs = 0.0f, pr = 0.0f;
+    if (act) {
+      const Block* B = G.arena + b;
+      n = B->N[L.l];
+      qs = B->Qp[L.l];
+      pr = B->P[L.l];
+      ch = B->child[L.l];
+    }
     const unsigned legal = c4::legal_mask(pos.mask);
     const float lnp = c4::c4_logf((float)np);  // ln(parent visits), mcts.rs:378-379
-    const uint32_t nn[7] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z};
-    const uint32_t qq[7] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};
-    const uint32_t pp[7] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z};
-    const uint32_t cc[7] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
-    int best = -1;
-    float bu = 0.0f;
-    uint32_t bn = 0u, bc = 0u;
+    const float u = uct(n, qs, pr, lnp, D.c_expl);
+    const bool ok = act && L.l < 7 && ((legal >> L.l) & 1u);
+    const uint32_t key = ok ? ordkey(u) : 0u;
+    uint32_t m = key;
 #pragma unroll
-    for (int c = 0; c < 7; c++) {
-      float u = uct(nn[c], __uint_as_float(qq[c]), __uint_as_float(pp[c]), lnp, D.c_expl);
-      bool take = ((legal >> c) & 1u) && (best < 0 || u >= bu);  // max_by_key: the LAST maximum wins
-      best = take ? c : best;
-      bu = take ? u : bu;
-      bn = take ? nn[c] : bn;
-      bc = take ? cc[c] : bc;
+    for (int k = 1; k < 8; k <<= 1) m = max(m, gxor(m, k));
+    const unsigned winners = gballot(L, ok && key == m);
+    const int best = 31 - __clz(winners);  // max_by_key: the LAST maximum wins; -1 if none
+    const int src = best & 7;
+    const uint32_t bn = gshfl(n, src), bc = gshfl(ch, src);
+    if (act) {
+      if (best >= 0 && len < 42u) {
+        if (L.l == 0) G.path[len] = (b << 3) | (uint32_t)best;
+        len++;
+        pos = c4::make_move(pos, best);
+        np = bn;
+        b = bc;
+      } else {
+        b = 0u;  // cannot happen: an expanded node has a legal move and a tree is <= 42 plies deep
+      }
     }
-    if (best < 0) break;  // cannot happen: an expanded node has a legal move
-    G.path[len] = (b << 3) | (uint32_t)best;
-    len++;
-    pos = c4::make_move(pos, best);
-    np = bn;
-    b = bc;
   }
-  G.len = len;
+  if (pred) G.len = len;
   return pos;
 }
 
 // mask_policy + softmax + expand_leaf + backup for the leaf the network just evaluated
-// (c4r.rs:272-286, mcts.rs:416-434, 114-132, 137-155).  false = arena overflow (engine bug).
-__device__ __forceinline__ bool apply_network(const Dev& D, Game& G, uint32_t row) {
+// (c4r.rs:272-286, mcts.rs:416-434, 114-132, 137-155).  Returns false for a game whose arena
+// overflowed (engine bug; reported).
+__device__ __forceinline__ bool apply_network(const Dev& D, const Lanes& L, Game& G, bool pred, uint32_t row) {
   const unsigned legal = c4::legal_mask(G.leaf.mask);
-  float x[7], p[7];
-#pragma unroll
-  for (int i = 0; i < 7; i++) x[i] = ((legal >> i) & 1u) ? D.logits[(size_t)row * 7 + i] : -c4::f32_inf();
-  const float vq = D.qp[row], vn = D.qn[row];
-  if (!c4::softmax7(x, p)) {
-#pragma unroll
-    for (int i = 0; i < 7; i++) p[i] = 0.0f;
-  }
+  const bool ok = pred && L.l < 7 && ((legal >> L.l) & 1u);
+  const float x = ok ? D.logits[(size_t)row * 7 + L.l] : -c4::f32_inf();
+  const float vq = pred ? D.qp[row] : 0.0f, vn = pred ? D.qn[row] : 0.0f;
+  const float mx = gmax8(x);
+  const float e = ok ? c4::c4_expf(x - mx) : 0.0f;
+  const float s = fold7(e);
+  const float p = ok ? e / s : 0.0f;
   const uint32_t nb = G.n_alloc;
-  if (nb >= D.cap) return false;
-  G.n_alloc = nb + 1u;
-  uint4* V = reinterpret_cast<uint4*>(G.arena + nb);
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  V[0] = z; V[1] = z; V[2] = z; V[3] = z; V[4] = z; V[5] = z;
-  V[6] = make_uint4(__float_as_uint(p[0]), __float_as_uint(p[1]), __float_as_uint(p[2]), __float_as_uint(p[3]));
-  V[7] = make_uint4(__float_as_uint(p[4]), __float_as_uint(p[5]), __float_as_uint(p[6]), 0u);
-  V[8] = z; V[9] = z;
-  if (G.len == 0) {
-    G.root_block = nb;
-  } else {
-    uint32_t e = G.path[G.len - 1];
-    G.arena[e >> 3].child[e & 7u] = nb;
+  const bool fits = nb < D.cap;
+  if (pred && fits) {
+    G.n_alloc = nb + 1u;
+    Block* B = G.arena + nb;  // expand_leaf: one new block holding the 7 children
+    B->N[L.l] = 0u;
+    B->Qp[L.l] = 0.0f;
+    B->Qn[L.l] = 0.0f;
+    B->P[L.l] = p;
+    B->child[L.l] = 0u;
+    if (G.len == 0) {
+      G.root_block = nb;
+    } else if (L.l == 0) {
+      uint32_t e2 = G.path[G.len - 1];
+      G.arena[e2 >> 3].child[e2 & 7u] = nb;
+    }
+    G.depth += G.len;
+    G.sims++;
+    G.exps++;
   }
-  G.depth += G.len;
-  backup(G, vq, vn);
-  G.sims++;
-  G.exps++;
-  return true;
+  backup(L, G, pred && fits, vq, vn);
+  return !pred || fits;
 }
 
 __device__ __forceinline__ void seat_game(Game& G, uint32_t r) {
@@ -380,133 +423,187 @@ __device__ __forceinline__ void seat_game(Game& G, uint32_t r) {
   G.len = 0u;
 }
 
-enum MoveResult { MV_CONTINUE, MV_IDLE, MV_COMPACT };
+enum MoveResult : int { MV_CONTINUE = 0, MV_IDLE = 1, MV_COMPACT = 2 };
 
 // The root reached n_iterations (self_play.rs:283-313): sample and play a move (mcts.rs:187-222) or,
-// when that ends the game, emit its samples (mcts.rs:271-313) and seat the next request.
-__device__ __noinline__ MoveResult play_move(const Dev& D, Game& G) {
+// when that ends the game, emit its samples (mcts.rs:271-313) and seat the next request.  Executed
+// by the whole warp; `pred` marks the games that actually move.
+__device__ __noinline__ int play_move(const Dev& D, const Lanes& L, Game& G, bool pred) {
   Globals* g = D.g;
-  const uint32_t rb = G.root_block;
-  float pol[7], tempered[7];
+  const int l = L.l;
   const float uniform = 1.0f / 7.0f;
-  uint32_t cn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (rb) {  // root_policy (mcts.rs:396-412): visit counts of the children, normalised
-    const uint4* V = reinterpret_cast<const uint4*>(G.arena + rb);
-    uint4 a = V[0], b = V[1];
-    cn[0] = a.x; cn[1] = a.y; cn[2] = a.z; cn[3] = a.w; cn[4] = b.x; cn[5] = b.y; cn[6] = b.z;
-    float cnt[7], sum = 0.0f;
-    for (int i = 0; i < 7; i++) cnt[i] = (float)cn[i];
-    for (int i = 0; i < 7; i++) sum = sum + cnt[i];
-    for (int i = 0; i < 7; i++) pol[i] = (sum == 0.0f) ? uniform : cnt[i] / sum;
-  } else {
-    for (int i = 0; i < 7; i++) pol[i] = uniform;
+  const float ninf = -c4::f32_inf();
+  const uint32_t rb = pred ? G.root_block : 0u;
+  uint32_t n_c = 0u, ch = 0u;
+  float q_p = 0.0f, q_n = 0.0f;
+  if (rb) {
+    const Block* RB = G.arena + rb;
+    n_c = RB->N[l];
+    q_p = RB->Qp[l];
+    q_n = RB->Qn[l];
+    ch = RB->child[l];
   }
-  const float T = c4::temperature_for_ply(c4::ply(G.root.mask));  // self_play.rs:294-299
-  c4::apply_temperature7(pol, T, tempered);
-  const int col = c4::weighted_sample7(tempered, c4::move_seed(D.game_id[G.req], (int)G.n_moves));
+  // root_policy (mcts.rs:396-412): visit counts of the children, normalised
+  const float cnt = (float)n_c;
+  const float sum = fold7(cnt);
+  const float pol = (rb == 0u || sum == 0.0f) ? uniform : cnt / sum;
+  // apply_temperature (mcts.rs:439-454); T from self_play.rs:294-299
+  const float T = c4::temperature_for_ply(c4::ply(G.root.mask));
+  const float p0 = gshfl(pol, 0);
+  const bool alleq = gballot(L, l == 7 || pol == p0) == 0xffu;
+  const float lg = c4::c4_logf(pol) / T;
+  const float ex = (l < 7) ? c4::c4_expf(lg) : 0.0f;
+  const float lse = c4::c4_logf(fold7(ex));
+  float v = c4::c4_expf(lg - lse);
+  v = v < 0.0f ? 0.0f : v;
+  v = v > 1.0f ? 1.0f : v;
+  const float pmx = gmax8(l < 7 ? pol : ninf);
+  const float one = (l < 7 && pol == pmx) ? 1.0f : 0.0f;
+  const float v0 = one / fold7(one);
+  float w = (T == 1.0f || alleq) ? pol : (T == 0.0f ? v0 : v);
+  if (l == 7) w = 0.0f;
+  // WeightedIndex::new(w) (cumulative left fold) and Uniform<f32>[0, total)
+  float run = 0.0f, cum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    float wi = gshfl(w, i);
+    run = (i == 0) ? wi : run + wi;
+    if (i == l) cum = run;
+  }
+  const float total = run;
+  const bool bad = gballot(L, l < 7 && !(w >= 0.0f)) != 0u || !(total > 0.0f) || total == c4::f32_inf();
+  float scale = total;
+  const float max_rand = c4::bits_f32(0x3f7ffffeu);
+  if (!bad)
+    while (scale * max_rand + 0.0f >= total) scale = c4::bits_f32(c4::f32_bits(scale) - 1u);
+  uint32_t key[8];
+  c4::seed_to_key(c4::move_seed(pred ? D.game_id[G.req] : 0ull, (int)G.n_moves), key);
+  const uint32_t u32 = c4::chacha12_first_word(key);
+  const float x = (c4::bits_f32((u32 >> 9) | 0x3f800000u) - 1.0f) * scale + 0.0f;
+  const int col = __popc(gballot(L, l < 6 && cum <= x));  // partition_point(|c| c <= x) over 6 entries
   const unsigned legal = c4::legal_mask(G.root.mask);
-  if (col < 0 || !((legal >> col) & 1u) || rb == 0u || G.n_moves >= 42u) {
-    g->error = C4A0_E_ENGINE;  // the reference panics here (mcts.rs:190-197): park the game, report
-    atomicSub(&g->n_running, 1u);
-    return MV_IDLE;
-  }
-  // RecordedMove (mcts.rs:198-203) goes straight into the sample store
-  const size_t s0 = (size_t)G.req * MAXS;
-  size_t si = s0 + G.n_moves;
-  D.s_mask[si] = G.root.mask;
-  D.s_value[si] = G.root.value;
-  for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = pol[i];
-  G.n_moves += 1u;
-  const Block* RB = G.arena + rb;
-  const Pos np = c4::make_move(G.root, col);
-  const uint32_t newN = cn[col];
-  const float newQp = RB->Qp[col], newQn = RB->Qn[col];
-  const uint32_t child = RB->child[col];
-  atomicAdd(&g->moves, 1ull);
+  const bool err = pred && (bad || col > 6 || !((legal >> col) & 1u) || rb == 0u || G.n_moves >= 42u);
+  const bool go = pred && !err;
+  // the chosen child: position, statistics, subtree
+  const int src = col & 7;
+  const uint32_t newN = gshfl(n_c, src), child = gshfl(ch, src);
+  const float newQp = gshfl(q_p, src), newQn = gshfl(q_n, src);
+  const Pos np = c4::make_move(G.root, col > 6 ? 0 : col);
   float tqp, tqn;
   const int t = c4::terminal_value(np, D.c_pen, &tqp, &tqn);
-  if (t != c4::NONE) {
-    // to_result (mcts.rs:271-313): alternate the terminal value back through the moves
-    const uint32_t L = G.n_moves;
-    for (uint32_t k = 0; k < L; k++) {
-      bool neg = ((L - k) & 1u) != 0;
-      D.s_qp[s0 + k] = neg ? -tqp : tqp;
-      D.s_qn[s0 + k] = neg ? -tqn : tqn;
+  const bool fin = go && t != c4::NONE;
+  // the next request, should the game end here (self_play.rs:55-58 queues them all up front)
+  uint32_t r = 0u;
+  if (fin && l == 0) r = atomicAdd(&g->next_req, 1u);
+  r = gshfl(r, 0);
+  int result = MV_CONTINUE;
+  if (err) {
+    if (l == 0) {
+      g->error = C4A0_E_ENGINE;  // the reference panics here (mcts.rs:190-197): park the game, report
+      atomicSub(&g->n_running, 1u);
     }
-    si = s0 + L;
-    D.s_mask[si] = np.mask;
-    D.s_value[si] = np.value;
-    for (int i = 0; i < 7; i++) D.s_policy[si * 7 + i] = uniform;
-    D.s_qp[si] = tqp;
-    D.s_qn[si] = tqn;
-    D.n_samples[G.req] = L + 1u;
-    atomicAdd(&g->samples, (unsigned long long)(L + 1u));
-    atomicAdd(&g->n_finished, 1u);
-    // the reference keeps simulating the terminal root until N >= n
-    if (newN < D.n_iter) atomicAdd(&g->skipped_root_sims, (unsigned long long)(D.n_iter - newN));
-    // seat the next waiting request in this slot (self_play.rs:55-58 queues them all up front)
-    const uint32_t r = atomicAdd(&g->next_req, 1u);
-    if (r < g->n_req) {
-      seat_game(G, r);
-      return MV_CONTINUE;
-    }
-    atomicSub(&g->n_running, 1u);
-    return MV_IDLE;
+    result = MV_IDLE;
   }
-  // re-root (mcts.rs:200-205): the child's subtree and statistics are kept
-  G.root = np;
-  G.rootN = newN;
-  G.rootQp = newQp;
-  G.rootQn = newQn;
-  G.root_block = child;
-  G.len = 0u;
-  // until the next move at most n_iter - N expansions happen: do they still fit in this half?
-  const uint32_t need = (D.n_iter > newN ? D.n_iter - newN : 0u) + 1u;
-  if (G.n_alloc + need > D.cap) return MV_COMPACT;
-  return MV_CONTINUE;
+  if (go) {
+    // RecordedMove (mcts.rs:198-203) goes straight into the sample store
+    const size_t s0 = (size_t)G.req * MAXS;
+    size_t si = s0 + G.n_moves;
+    if (l < 7) D.s_policy[si * 7 + l] = pol;
+    if (l == 0) {
+      D.s_mask[si] = G.root.mask;
+      D.s_value[si] = G.root.value;
+      atomicAdd(&g->moves, 1ull);
+    }
+    G.n_moves += 1u;
+    if (fin) {
+      // to_result (mcts.rs:271-313): alternate the terminal value back through the moves
+      const uint32_t Lm = G.n_moves;
+      for (uint32_t k = l; k < Lm; k += 8) {
+        bool neg = ((Lm - k) & 1u) != 0;
+        D.s_qp[s0 + k] = neg ? -tqp : tqp;
+        D.s_qn[s0 + k] = neg ? -tqn : tqn;
+      }
+      si = s0 + Lm;
+      if (l < 7) D.s_policy[si * 7 + l] = uniform;
+      if (l == 0) {
+        D.s_mask[si] = np.mask;
+        D.s_value[si] = np.value;
+        D.s_qp[si] = tqp;
+        D.s_qn[si] = tqn;
+        D.n_samples[G.req] = Lm + 1u;
+        atomicAdd(&g->samples, (unsigned long long)(Lm + 1u));
+        atomicAdd(&g->n_finished, 1u);
+        // the reference keeps simulating the terminal root until N >= n
+        if (newN < D.n_iter) atomicAdd(&g->skipped_root_sims, (unsigned long long)(D.n_iter - newN));
+      }
+      if (r < g->n_req) {
+        seat_game(G, r);
+      } else {
+        if (l == 0) atomicSub(&g->n_running, 1u);
+        result = MV_IDLE;
+      }
+    } else {
+      // re-root (mcts.rs:200-205): the child's subtree and statistics are kept
+      G.root = np;
+      G.rootN = newN;
+      G.rootQp = newQp;
+      G.rootQn = newQn;
+      G.root_block = child;
+      G.len = 0u;
+      // until the next move at most n_iter - N expansions happen: do they still fit in this half?
+      const uint32_t need = (D.n_iter > newN ? D.n_iter - newN : 0u) + 1u;
+      if (G.n_alloc + need > D.cap) result = MV_COMPACT;
+    }
+  }
+  return result;
 }
 
-// Advance a game until it needs the network (WAIT_NN), has used its in-kernel budget of
-// terminal-leaf simulations (CONTINUE), needs its tree compacted (NEED_MOVE) or has no game (IDLE).
-struct PhaseClock {  // cycles spent per phase by one thread (debug only)
-  uint32_t move = 0, select = 0, term = 0, n_select = 0, max_len = 0;
-};
-
-__device__ __forceinline__ uint32_t run_game(const Dev& D, Game& G, PhaseClock* pc = nullptr) {
+// Advance the (up to four) games of this warp until each needs the network (WAIT_NN), has used its
+// in-kernel budget of terminal-leaf simulations (CONTINUE), needs its tree compacted (NEED_MOVE) or
+// holds no game (IDLE).  `running` marks the lanes of live games; returns the new state.
+__device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game& G, bool running, uint32_t state) {
   uint32_t inl = 0;
   for (;;) {
-    if (G.rootN >= D.n_iter) {  // self_play.rs:283: checked after every simulation
-      long long c0 = pc ? clock64() : 0;
-      MoveResult r = play_move(D, G);
-      if (pc) pc->move += (uint32_t)(clock64() - c0);
-      if (r == MV_IDLE) return ST_IDLE;
-      if (r == MV_COMPACT) return ST_NEED_MOVE;
+    const bool need_move = running && G.rootN >= D.n_iter;  // self_play.rs:283: after every simulation
+    if (__any_sync(FULL, need_move)) {
+      const int r = play_move(D, L, G, need_move);
+      if (need_move && r == MV_IDLE) {
+        running = false;
+        state = ST_IDLE;
+      }
+      if (need_move && r == MV_COMPACT) {
+        running = false;
+        state = ST_NEED_MOVE;
+      }
       continue;
     }
-    if (inl >= D.max_inline) return ST_CONTINUE;
-    long long c1 = pc ? clock64() : 0;
-    Pos leaf = select_leaf(D, G);
-    if (pc) {
-      pc->select += (uint32_t)(clock64() - c1);
-      pc->n_select++;
-      pc->max_len = G.len > pc->max_len ? G.len : pc->max_len;
+    if (running && inl >= D.max_inline) {
+      running = false;
+      state = ST_CONTINUE;
     }
+    if (!__any_sync(FULL, running)) break;
+    const Pos leaf = select_leaf(D, L, G, running);
     float tqp, tqn;
-    int t = c4::terminal_value(leaf, D.c_pen, &tqp, &tqn);
-    if (t == c4::NONE) {
+    const int t = c4::terminal_value(leaf, D.c_pen, &tqp, &tqn);
+    const bool term = running && t != c4::NONE;
+    if (running && t == c4::NONE) {
       G.leaf = leaf;
       G.leaf_model = (c4::ply(leaf.mask) & 1) ? D.p1[G.req] : D.p0[G.req];  // mcts.rs:70-76
-      return ST_WAIT_NN;
+      running = false;
+      state = ST_WAIT_NN;
     }
-    // terminal leaf: mcts.rs:92-98 — no expansion, back up the objective value
-    long long c2 = pc ? clock64() : 0;
-    G.depth += G.len;
-    backup(G, tqp, tqn);
-    G.sims++;
-    G.term++;
-    inl++;
-    if (pc) pc->term += (uint32_t)(clock64() - c2);
+    if (__any_sync(FULL, term)) {
+      // terminal leaf: mcts.rs:92-98 — no expansion, back up the objective value
+      if (term) {
+        G.depth += G.len;
+        G.sims++;
+        G.term++;
+        inl++;
+      }
+      backup(L, G, term, tqp, tqn);
+    }
   }
+  return state;
 }
 
 __device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
@@ -515,44 +612,51 @@ __device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_step: one thread per game.
+// K_step: the tick of every game.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STEP_THREADS) k_step(Dev D) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= D.n_slots) return;
-  const uint32_t st = D.slots[slot].state;
-  if (st == ST_IDLE) return;
-  if (st == ST_NEED_MOVE) {  // asked for compaction inside k_move's own run_game()
-    push_mover(D, slot);
-    return;
-  }
+  const Lanes L = make_lanes();
+  const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool valid = slot < D.n_slots;
+  const uint32_t st = valid ? D.slots[slot].state : (uint32_t)ST_IDLE;
+  if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction in k_move's own run
+  const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
+  if (!__any_sync(FULL, live)) return;
   const bool prof = D.dbg != nullptr;
   const long long t0 = prof ? clock64() : 0;
   Game G;
-  load_game(D, slot, G);
+  if (live) {
+    load_game(D, slot, G);
+  } else {
+    memset(&G, 0, sizeof(G));
+  }
   const long long t1 = prof ? clock64() : 0;
-  if (st == ST_WAIT_NN) {
-    if (!apply_network(D, G, D.slots[slot].nn_row)) {
-      D.g->error = C4A0_E_ENGINE;
-      return;
+  const bool waiting = live && st == ST_WAIT_NN;
+  bool running = live;
+  if (__any_sync(FULL, waiting)) {
+    const uint32_t row = waiting ? D.slots[slot].nn_row : 0u;
+    if (!apply_network(D, L, G, waiting, row)) {
+      if (L.l == 0) D.g->error = C4A0_E_ENGINE;
+      running = false;
     }
   }
   const long long t2 = prof ? clock64() : 0;
-  PhaseClock pc;
-  const uint32_t ns = run_game(D, G, prof ? &pc : nullptr);
+  const uint32_t ns = run_games(D, L, G, running, st);
   const long long t3 = prof ? clock64() : 0;
-  store_game(D, G, ns);
-  if (ns == ST_NEED_MOVE) push_mover(D, slot);
-  if (prof) {
-    uint32_t* o = D.dbg + (size_t)slot * 8;
-    o[0] = (uint32_t)(t1 - t0);          // load slot state
-    o[1] = (uint32_t)(t2 - t1);          // softmax + expand + backup
-    o[2] = pc.move;                      // play_move
-    o[3] = pc.select;                    // select_leaf (all passes)
-    o[4] = pc.term;                      // terminal-leaf backups
-    o[5] = pc.n_select | (pc.max_len << 8);
-    o[6] = (uint32_t)(clock64() - t3);   // store
-    o[7] = (uint32_t)(clock64() - t0);   // whole thread
+  if (live && L.l == 0) {
+    store_game(D, G, ns);
+    if (ns == ST_NEED_MOVE) push_mover(D, slot);
+    if (prof) {  // cycles of this game's warp per phase (c4a0_engine_debug_phases)
+      uint32_t* o = D.dbg + (size_t)slot * 8;
+      o[0] = (uint32_t)(t1 - t0);         // load slot state
+      o[1] = (uint32_t)(t2 - t1);         // softmax + expand + backup
+      o[2] = G.sims;                      // simulations this tick
+      o[3] = (uint32_t)(t3 - t2);         // moves + selection passes + terminal backups
+      o[4] = G.term;                      // ... of which terminal-leaf simulations
+      o[5] = G.len;                       // depth of the selected leaf
+      o[6] = (uint32_t)(clock64() - t3);  // store
+      o[7] = (uint32_t)(clock64() - t0);  // whole tick
+    }
   }
 }
 
@@ -610,12 +714,20 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
       S->path_len = 0u;
       atomicAdd(&D.g->compacted_blocks, (unsigned long long)(sh_next - 1u));
       atomicAdd(&D.g->compactions, 1ull);
-      __threadfence_block();
-      Game G;
-      load_game(D, slot, G);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // warp 0; its first 8 lanes carry the game on
       // the live subtree holds at most N_root blocks, so the fresh half always has room again
-      uint32_t ns = run_game(D, G);
-      store_game(D, G, ns);
+      const Lanes L = make_lanes();
+      const bool live = threadIdx.x < 8;
+      Game G;
+      if (live) {
+        load_game(D, slot, G);
+      } else {
+        memset(&G, 0, sizeof(G));
+      }
+      const uint32_t ns = run_games(D, L, G, live, ST_CONTINUE);
+      if (threadIdx.x == 0) store_game(D, G, ns);
     }
     __syncthreads();
   }
@@ -870,7 +982,7 @@ int launch_post(c4a0_engine* e, cudaStream_t s) {
 int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
   const Dev& D = e->D;
   if (ev) CK(cudaEventRecord(ev[0], s));
-  k_step<<<blocks_for(D.n_slots, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
+  k_step<<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
   if (ev) CK(cudaEventRecord(ev[1], s));
   unsigned grid = D.n_slots < 296u ? D.n_slots : 296u;
   k_move<<<grid, MOVE_THREADS, 0, s>>>(D);

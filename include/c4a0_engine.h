@@ -140,9 +140,10 @@ int c4a0_engine_step(c4a0_engine *e, void *stream);
  * the timed region; not capturable. */
 int c4a0_engine_step_timed(c4a0_engine *e, void *stream, float *ms_step_kernel, float *ms_move_kernel);
 
-/* Developer aid: runs one step() with per-game cycle counters inside the tick kernel and returns 8
- * words per slot {load, apply, move, select, terminal backups, n_select | max_depth << 8, store,
- * total} in SM cycles (zeros for idle slots).  Synchronises. */
+/* Developer aid: runs one step() with cycle counters inside the tick kernel and returns 8 words per
+ * slot {load cycles, apply cycles, simulations, run cycles (moves + selection + terminal backups),
+ * terminal simulations, leaf depth, store cycles, total cycles} (zeros for idle slots).  The cycle
+ * figures are those of the game's warp.  Synchronises. */
 int c4a0_engine_debug_phases(c4a0_engine *e, void *stream, uint32_t *out8_per_slot);
 
 /* Fill logits/q buffers for the current leaves with a synthetic evaluator (parity tiers E0/E1). */

@@ -150,6 +150,10 @@ def lib() -> C.CDLL:
         C.c_int, C.POINTER(Sample), C.POINTER(C.c_int), C.POINTER(Stats), C.POINTER(C.c_uint64),
     ]
     L.c4o_self_play_threaded.restype = C.c_int
+    L.c4o_self_play_threaded_budget.argtypes = sp_args + [
+        C.c_int, C.c_uint64, C.POINTER(Sample), C.POINTER(C.c_int), C.POINTER(Stats), C.POINTER(C.c_uint64),
+    ]
+    L.c4o_self_play_threaded_budget.restype = C.c_int
     L.c4o_player0_score.argtypes = [C.POINTER(Sample), C.c_int]
     L.c4o_player0_score.restype = C.c_float
     for ev in (L.c4o_eval_uniform, L.c4o_eval_hash):

@@ -129,6 +129,17 @@ int c4o_self_play(const c4o_metadata *reqs, size_t n_games, int max_nn_batch_siz
                   c4o_eval_fn eval, void *user, c4o_sample *out_samples, int *out_n,
                   c4o_stats *stats);
 
+/* selfplay_threads.cpp: the reference's thread/channel architecture (timed CPU baseline) */
+int c4o_self_play_threaded(const c4o_metadata *reqs, size_t n_games, int max_nn_batch_size,
+                           uint64_t n_mcts_iterations, float c_exploration, float c_ply_penalty,
+                           c4o_eval_fn eval, void *user, int n_mcts_threads, c4o_sample *out_samples,
+                           int *out_n, c4o_stats *stats, uint64_t *nn_batches);
+int c4o_self_play_threaded_budget(const c4o_metadata *reqs, size_t n_games, int max_nn_batch_size,
+                                  uint64_t n_mcts_iterations, float c_exploration,
+                                  float c_ply_penalty, c4o_eval_fn eval, void *user,
+                                  int n_mcts_threads, uint64_t max_sims, c4o_sample *out_samples,
+                                  int *out_n, c4o_stats *stats, uint64_t *nn_batches);
+
 float c4o_player0_score(const c4o_sample *samples, int n);
 
 /* libm pass-throughs used by tests that pin the product's restated logf/expf */

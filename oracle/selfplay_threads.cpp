@@ -107,6 +107,7 @@ struct Shared {
   std::atomic<int> error{0};
   std::atomic<uint64_t> sims{0}, nn_evals{0}, nn_batches{0}, moves{0}, samples{0};
   int max_nn_batch_size;
+  uint64_t max_sims = 0; /* bench only: abandon the games once this many simulations ran (0 = play out) */
   uint64_t n_mcts_iterations;
   float c_exploration, c_ply_penalty;
   int n_mcts_threads;
@@ -193,6 +194,20 @@ void mcts_thread(Shared *sh) {
     if (!sh->mcts_queue.recv(job)) break;
     if (job.poison) break;
     c4o_game *g = job.game.g;
+    if (sh->max_sims && sh->sims.load() >= sh->max_sims) {
+      /* time-boxed baseline run: the budget is spent, retire the game unfinished */
+      c4o_game_free(g);
+      if (sh->n_games_remaining.fetch_sub(1) == 1) {
+        for (int i = 0; i < sh->n_mcts_threads - 1; i++) {
+          Job pill;
+          pill.poison = true;
+          pill.game = Game{nullptr, 0};
+          sh->mcts_queue.send(pill);
+        }
+        break;
+      }
+      continue;
+    }
     sh->sims += 1;
     c4o_game_on_received_policy(g, job.res.policy, job.res.qp, job.res.qn, sh->c_exploration,
                                 sh->c_ply_penalty);
@@ -233,17 +248,39 @@ void mcts_thread(Shared *sh) {
 
 }  // namespace
 
+extern "C" int c4o_self_play_threaded_budget(const c4o_metadata *reqs, size_t n_games,
+                                             int max_nn_batch_size, uint64_t n_mcts_iterations,
+                                             float c_exploration, float c_ply_penalty,
+                                             c4o_eval_fn eval, void *user, int n_mcts_threads,
+                                             uint64_t max_sims, c4o_sample *out_samples, int *out_n,
+                                             c4o_stats *stats, uint64_t *nn_batches);
+
 extern "C" int c4o_self_play_threaded(const c4o_metadata *reqs, size_t n_games,
                                       int max_nn_batch_size, uint64_t n_mcts_iterations,
                                       float c_exploration, float c_ply_penalty, c4o_eval_fn eval,
                                       void *user, int n_mcts_threads, c4o_sample *out_samples,
                                       int *out_n, c4o_stats *stats, uint64_t *nn_batches) {
+  return c4o_self_play_threaded_budget(reqs, n_games, max_nn_batch_size, n_mcts_iterations,
+                                       c_exploration, c_ply_penalty, eval, user, n_mcts_threads, 0,
+                                       out_samples, out_n, stats, nn_batches);
+}
+
+/* Same, but stops after `max_sims` simulations (0 = never): a time-boxed sample of a workload whose
+ * concurrency (n_games) matters for the NN batch size.  Unfinished games report out_n = 0; stats
+ * count the moves made, each of which yields one training position at game end. */
+extern "C" int c4o_self_play_threaded_budget(const c4o_metadata *reqs, size_t n_games,
+                                             int max_nn_batch_size, uint64_t n_mcts_iterations,
+                                             float c_exploration, float c_ply_penalty,
+                                             c4o_eval_fn eval, void *user, int n_mcts_threads,
+                                             uint64_t max_sims, c4o_sample *out_samples, int *out_n,
+                                             c4o_stats *stats, uint64_t *nn_batches) {
   if (n_games == 0) {
     if (stats) std::memset(stats, 0, sizeof(*stats));
     return 0;
   }
   Shared sh;
   sh.max_nn_batch_size = max_nn_batch_size;
+  sh.max_sims = max_sims;
   sh.n_mcts_iterations = n_mcts_iterations;
   sh.c_exploration = c_exploration;
   sh.c_ply_penalty = c_ply_penalty;

@@ -18,7 +18,7 @@ sess = SelfPlaySession(n, n, sims, 6.6, 0.01, plane_dtype=torch.bfloat16, plane_
 ln = sess.lanes[0]
 ids = np.arange(n)
 z = np.zeros(n, np.uint64)
-names = ["load", "apply", "move", "select", "term", "nsel|depth", "store", "total"]
+names = ["load", "apply", "sims", "run", "term_sims", "depth", "store", "total"]
 with torch.cuda.stream(ln.stream):
     s = ln.stream.cuda_stream
     ln.engine.set_requests(ids, z, z, s)
@@ -28,16 +28,11 @@ with torch.cuda.stream(ln.stream):
             d = ln.engine.debug_phases(s).astype(np.int64)
             act = d[:, 7] > 0
             a = d[act]
-            w = d.reshape(-1, 32, 8)  # warps of 32 consecutive slots
-            wtot = w[:, :, 7].max(axis=1)
-            crit = int(wtot.argmax())
             p = ln.engine.poll(s)
             print(f"tick {tick}: active {act.sum()} rows {p.n_rows} finished {p.n_finished}")
-            print("   mean cycles/thread:", {k: int(a[:, i].mean()) for i, k in enumerate(names) if i != 5})
-            print("   max  cycles/thread:", {k: int(a[:, i].max()) for i, k in enumerate(names) if i != 5})
-            print("   n_select mean %.2f max %d ; depth max %d" % ((a[:, 5] & 255).mean(), (a[:, 5] & 255).max(), (a[:, 5] >> 8).max()))
-            print("   warp max-total: mean %d p90 %d max %d cycles  (%.1f us at 1.9 GHz)" % (wtot[wtot > 0].mean(), np.percentile(wtot[wtot > 0], 90), wtot.max(), wtot.max() / 1900))
-            print("   critical warp lanes:", w[crit][:, [1, 2, 3, 4, 7]].max(axis=0).tolist(), "(max apply, move, select, term, total)")
+            print("   mean:", {k: round(float(a[:, i].mean()), 1) for i, k in enumerate(names)})
+            print("   max :", {k: int(a[:, i].max()) for i, k in enumerate(names)})
+            print("   slowest game: %.1f us at 1.9 GHz" % (a[:, 7].max() / 1900))
             x, y = ln.engine.step_timed(s)
             ln.evaluate(ev, n)
             print("   step_timed: k_step %.1f us k_move %.1f us" % (x * 1e3, y * 1e3))
