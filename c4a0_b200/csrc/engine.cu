@@ -68,8 +68,8 @@ static_assert(sizeof(Block) == 160, "block must be ten 16-byte vectors");
 // Everything a game needs besides its tree, one 128-byte line per slot.
 struct __align__(128) Slot {
   uint64_t root_mask, root_value;
-  uint64_t leaf_mask, leaf_value;  // the leaf waiting for the network (= its de-duplication key)
-  uint64_t leaf_model;             //   ... and the model that must evaluate it (mcts.rs:70-76)
+  uint64_t leaf_mask, leaf_value;  // the leaf waiting for the network (= its de-duplication key ...
+  uint64_t model0, model1;         //   ... with the model to move: player0_id at even ply, mcts.rs:70-76)
   uint32_t root_N;
   float root_Qp, root_Qn;
   uint32_t root_block;             // block of the root's children, 0 = root not expanded
@@ -83,9 +83,12 @@ struct __align__(128) Slot {
   uint32_t urow;                   // row assigned to this slot when it leads its key
   unsigned long long c_sims, c_exp, c_term, c_depth;
 };
+__host__ __device__ inline uint64_t leaf_model_of(const Slot& S) {
+  return (c4::popc64(S.leaf_mask) & 1) ? S.model1 : S.model0;
+}
 static_assert(sizeof(Slot) == 128, "slot state must be one cache line");
 
-constexpr int PATH_STRIDE = 44;  // <= 42 levels below a root
+constexpr int PATH_STRIDE = 48;  // <= 42 levels below a root; six entries per lane
 constexpr int MAXS = C4A0_MAX_SAMPLES;
 constexpr int STEP_THREADS = 256;
 constexpr int POST_THREADS = 256;
@@ -240,24 +243,44 @@ __device__ __forceinline__ float gmax8(float v) {
 
 // Per-game working set: group-uniform values, held redundantly by the 8 lanes.
 struct Game {
-  uint32_t slot;
+  uint32_t slot, state;
   Pos root, leaf;
-  uint64_t leaf_model;
-  uint32_t rootN, root_block, n_alloc, len, half, req, n_moves;
+  uint64_t model0, model1;
+  uint32_t rootN, root_block, n_alloc, len, half, req, n_moves, nn_row;
   float rootQp, rootQn;
   Block* arena;
   uint32_t* path;
+  uint32_t pr[6];  // this lane's share of the selected path: entries l, l+8, ..., l+40
   uint32_t sims, exps, term, depth;
+  unsigned long long c_sims, c_exp, c_term, c_depth;  // the slot's running totals
 };
 
-__device__ __forceinline__ void load_game(const Dev& D, uint32_t slot, Game& G) {
-  const Slot* S = D.slots + slot;  // all 8 lanes read the same line: one broadcast transaction
+__device__ __forceinline__ uint32_t pr_get(const uint32_t (&pr)[6], uint32_t k) {
+  uint32_t v = pr[0];
+#pragma unroll
+  for (int i = 1; i < 6; i++) v = (k == (uint32_t)i) ? pr[i] : v;
+  return v;
+}
+__device__ __forceinline__ void pr_set(uint32_t (&pr)[6], uint32_t k, uint32_t v) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) pr[i] = (k == (uint32_t)i) ? v : pr[i];
+}
+
+// One dependent memory round trip: the slot line (same address for the 8 lanes = one broadcast
+// transaction) and this lane's path entries are fetched together.
+__device__ __forceinline__ void load_game(const Dev& D, const Lanes& L, uint32_t slot, Game& G) {
+  const Slot* S = D.slots + slot;
   G.slot = slot;
+  G.path = D.path + (size_t)slot * PATH_STRIDE;
+#pragma unroll
+  for (int k = 0; k < 6; k++) G.pr[k] = G.path[L.l + 8 * k];
+  G.state = S->state;
   G.root.mask = S->root_mask;
   G.root.value = S->root_value;
   G.leaf.mask = S->leaf_mask;
   G.leaf.value = S->leaf_value;
-  G.leaf_model = S->leaf_model;
+  G.model0 = S->model0;
+  G.model1 = S->model1;
   G.rootN = S->root_N;
   G.rootQp = S->root_Qp;
   G.rootQn = S->root_Qn;
@@ -267,8 +290,12 @@ __device__ __forceinline__ void load_game(const Dev& D, uint32_t slot, Game& G) 
   G.half = S->half;
   G.req = S->req;
   G.n_moves = S->n_moves;
+  G.nn_row = S->nn_row;
+  G.c_sims = S->c_sims;
+  G.c_exp = S->c_exp;
+  G.c_term = S->c_term;
+  G.c_depth = S->c_depth;
   G.arena = arena_of(D, slot, G.half);
-  G.path = D.path + (size_t)slot * PATH_STRIDE;
   G.sims = G.exps = G.term = G.depth = 0;
 }
 __device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t state) {  // one lane
@@ -277,7 +304,8 @@ __device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t
   S->root_value = G.root.value;
   S->leaf_mask = G.leaf.mask;
   S->leaf_value = G.leaf.value;
-  S->leaf_model = G.leaf_model;
+  S->model0 = G.model0;
+  S->model1 = G.model1;
   S->root_N = G.rootN;
   S->root_Qp = G.rootQp;
   S->root_Qn = G.rootQn;
@@ -288,27 +316,31 @@ __device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t
   S->half = G.half;
   S->req = G.req;
   S->n_moves = G.n_moves;
-  if (G.sims) S->c_sims += G.sims;
-  if (G.exps) S->c_exp += G.exps;
-  if (G.term) S->c_term += G.term;
-  if (G.depth) S->c_depth += G.depth;
+  S->c_sims = G.c_sims + G.sims;
+  S->c_exp = G.c_exp + G.exps;
+  S->c_term = G.c_term + G.term;
+  S->c_depth = G.c_depth + G.depth;
 }
 
 // mcts.rs:137-155 — add (qp, qn) at the leaf, alternate the sign towards the root.  The path nodes
 // are distinct, so lanes update them in parallel: one f32 add per node per simulation.
 __device__ __forceinline__ void backup(const Lanes& L, Game& G, bool pred, float qp, float qn) {
-  __syncwarp();  // path[] (written by lane 0) and earlier block writes are visible
+  __syncwarp();  // earlier block writes of the other lanes are visible
   if (pred) {
-    for (uint32_t j = L.l; j < G.len; j += 8) {
-      uint32_t e = G.path[j];
-      Block* B = G.arena + (e >> 3);
-      uint32_t c = e & 7u;
-      bool neg = ((G.len - 1 - j) & 1u) != 0;
-      B->N[c] += 1u;
-      B->Qp[c] += neg ? -qp : qp;
-      B->Qn[c] += neg ? -qn : qn;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const uint32_t j = L.l + 8 * k;
+      if (j < G.len) {
+        const uint32_t e = G.pr[k];
+        Block* B = G.arena + (e >> 3);
+        const uint32_t c = e & 7u;
+        const bool neg = ((G.len - 1 - j) & 1u) != 0;
+        B->N[c] += 1u;
+        B->Qp[c] += neg ? -qp : qp;
+        B->Qn[c] += neg ? -qn : qn;
+      }
     }
-    bool neg = (G.len & 1u) != 0;
+    const bool neg = (G.len & 1u) != 0;
     G.rootN += 1u;
     G.rootQp += neg ? -qp : qp;
     G.rootQn += neg ? -qn : qn;
@@ -361,7 +393,11 @@ __device__ __forceinline__ Pos select_leaf(const Dev& D, const Lanes& L, Game& G
     const uint32_t bn = gshfl(n, src), bc = gshfl(ch, src);
     if (act) {
       if (best >= 0 && len < 42u) {
-        if (L.l == 0) G.path[len] = (b << 3) | (uint32_t)best;
+        if ((len & 7u) == (uint32_t)L.l) {  // the lane that owns this level keeps and persists it
+          const uint32_t e = (b << 3) | (uint32_t)best;
+          pr_set(G.pr, len >> 3, e);
+          G.path[len] = e;
+        }
         len++;
         pos = c4::make_move(pos, best);
         np = bn;
@@ -397,21 +433,22 @@ __device__ __forceinline__ bool apply_network(const Dev& D, const Lanes& L, Game
     B->Qn[L.l] = 0.0f;
     B->P[L.l] = p;
     B->child[L.l] = 0u;
-    if (G.len == 0) {
-      G.root_block = nb;
-    } else if (L.l == 0) {
-      uint32_t e2 = G.path[G.len - 1];
-      G.arena[e2 >> 3].child[e2 & 7u] = nb;
-    }
+    if (G.len == 0) G.root_block = nb;
     G.depth += G.len;
     G.sims++;
     G.exps++;
   }
+  // the new block hangs under the last node of the path, which lane (len-1)&7 remembers
+  const uint32_t last = G.len ? G.len - 1u : 0u;
+  const uint32_t e2 = gshfl(pr_get(G.pr, last >> 3), (int)(last & 7u));
+  if (pred && fits && G.len != 0u && L.l == 0) G.arena[e2 >> 3].child[e2 & 7u] = nb;
   backup(L, G, pred && fits, vq, vn);
   return !pred || fits;
 }
 
-__device__ __forceinline__ void seat_game(Game& G, uint32_t r) {
+__device__ __forceinline__ void seat_game(const Dev& D, Game& G, uint32_t r) {
+  G.model0 = D.p0[r];
+  G.model1 = D.p1[r];
   G.root = Pos{0ull, 0ull};
   G.rootN = 0u;
   G.rootQp = 0.0f;
@@ -537,7 +574,7 @@ __device__ __noinline__ int play_move(const Dev& D, const Lanes& L, Game& G, boo
         if (newN < D.n_iter) atomicAdd(&g->skipped_root_sims, (unsigned long long)(D.n_iter - newN));
       }
       if (r < g->n_req) {
-        seat_game(G, r);
+        seat_game(D, G, r);
       } else {
         if (l == 0) atomicSub(&g->n_running, 1u);
         result = MV_IDLE;
@@ -588,7 +625,6 @@ __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game
     const bool term = running && t != c4::NONE;
     if (running && t == c4::NONE) {
       G.leaf = leaf;
-      G.leaf_model = (c4::ply(leaf.mask) & 1) ? D.p1[G.req] : D.p0[G.req];  // mcts.rs:70-76
       running = false;
       state = ST_WAIT_NN;
     }
@@ -618,24 +654,23 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(Dev D) {
   const Lanes L = make_lanes();
   const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const bool valid = slot < D.n_slots;
-  const uint32_t st = valid ? D.slots[slot].state : (uint32_t)ST_IDLE;
-  if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction in k_move's own run
-  const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
-  if (!__any_sync(FULL, live)) return;
   const bool prof = D.dbg != nullptr;
   const long long t0 = prof ? clock64() : 0;
   Game G;
-  if (live) {
-    load_game(D, slot, G);
+  if (valid) {
+    load_game(D, L, slot, G);
   } else {
     memset(&G, 0, sizeof(G));
   }
+  const uint32_t st = G.state;
+  if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction in k_move's own run
+  const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
+  if (!__any_sync(FULL, live)) return;
   const long long t1 = prof ? clock64() : 0;
   const bool waiting = live && st == ST_WAIT_NN;
   bool running = live;
   if (__any_sync(FULL, waiting)) {
-    const uint32_t row = waiting ? D.slots[slot].nn_row : 0u;
-    if (!apply_network(D, L, G, waiting, row)) {
+    if (!apply_network(D, L, G, waiting, G.nn_row)) {
       if (L.l == 0) D.g->error = C4A0_E_ENGINE;
       running = false;
     }
@@ -722,7 +757,7 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
       const bool live = threadIdx.x < 8;
       Game G;
       if (live) {
-        load_game(D, slot, G);
+        load_game(D, L, slot, G);
       } else {
         memset(&G, 0, sizeof(G));
       }
@@ -752,7 +787,8 @@ __global__ void k_init(Dev D, uint32_t n_req) {
   if (slot < n_req) {
     S.req = slot;
     S.state = ST_WAIT_NN;
-    S.leaf_model = D.p0[slot];  // ply 0: player 0 moves (mcts.rs:70-76)
+    S.model0 = D.p0[slot];
+    S.model1 = D.p1[slot];
   }
   D.slots[slot] = S;
 }
@@ -776,7 +812,7 @@ __global__ void __launch_bounds__(POST_THREADS) k_post(Dev D) {
     waiting = true;
     km = S->leaf_mask;
     kv = S->leaf_value;
-    kmod = S->leaf_model;
+    kmod = leaf_model_of(*S);
   }
   uint32_t bucket = 0;
   if (D.dedup) {
@@ -796,7 +832,7 @@ __global__ void __launch_bounds__(POST_THREADS) k_post(Dev D) {
           if ((uint32_t)(cur >> 32) != epoch) continue;
         }
         const Slot* Ld = D.slots + (uint32_t)cur;  // keys were written by an earlier kernel
-        if (Ld->leaf_mask == km && Ld->leaf_value == kv && Ld->leaf_model == kmod) {
+        if (Ld->leaf_mask == km && Ld->leaf_value == kv && leaf_model_of(*Ld) == kmod) {
           atomicMin(e, mine);
           break;
         }
@@ -891,7 +927,7 @@ __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float*
     return;
   }
   const Slot* S = D.slots + D.row_slot[row];
-  uint64_t mask = S->leaf_mask, value = S->leaf_value, model = S->leaf_model;
+  uint64_t mask = S->leaf_mask, value = S->leaf_value, model = leaf_model_of(*S);
   uint64_t h = splitmix64(mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(value ^ model));
   for (int k = 0; k < 7; k++) {
     uint64_t hk = splitmix64(h + (uint64_t)k);
@@ -908,7 +944,7 @@ __global__ void k_gather_rows(Dev D, uint64_t* mask, uint64_t* value, uint64_t* 
   const Slot* S = D.slots + D.row_slot[row];
   mask[row] = S->leaf_mask;
   value[row] = S->leaf_value;
-  model[row] = S->leaf_model;
+  model[row] = leaf_model_of(*S);
 }
 
 __global__ void k_sum_counters(Dev D, unsigned long long* out4) {
