@@ -90,7 +90,7 @@ static_assert(sizeof(Slot) == 128, "slot state must be one cache line");
 
 constexpr int PATH_STRIDE = 48;  // <= 42 levels below a root; six entries per lane
 constexpr int MAXS = C4A0_MAX_SAMPLES;
-constexpr int STEP_THREADS = 256;
+constexpr int STEP_THREADS = 128;
 constexpr int POST_THREADS = 256;
 constexpr int MOVE_THREADS = 128;
 enum : uint32_t { ST_IDLE = 0, ST_WAIT_NN = 1, ST_CONTINUE = 2, ST_NEED_MOVE = 3 };
@@ -465,7 +465,7 @@ enum MoveResult : int { MV_CONTINUE = 0, MV_IDLE = 1, MV_COMPACT = 2 };
 // The root reached n_iterations (self_play.rs:283-313): sample and play a move (mcts.rs:187-222) or,
 // when that ends the game, emit its samples (mcts.rs:271-313) and seat the next request.  Executed
 // by the whole warp; `pred` marks the games that actually move.
-__device__ __noinline__ int play_move(const Dev& D, const Lanes& L, Game& G, bool pred) {
+__device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, bool pred) {
   Globals* g = D.g;
   const int l = L.l;
   const float uniform = 1.0f / 7.0f;
@@ -650,7 +650,7 @@ __device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
 // ------------------------------------------------------------------------------------------------
 // K_step: the tick of every game.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(STEP_THREADS) k_step(Dev D) {
+__global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 registers: 16,384 games in one wave
   const Lanes L = make_lanes();
   const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const bool valid = slot < D.n_slots;
