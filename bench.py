@@ -264,10 +264,15 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    state = {"ev": None}
+
     def one_step():
         t0 = time.perf_counter()
         D.broadcast_model(model)  # a generation's weights: rank 0 -> all (NCCL); no-op at N=1
-        evaluator = DeviceEvaluator.from_model(model, dtype, fold=not args.no_fold)  # weights -> inference form
+        # weights -> inference form, loaded in place into the previous generation's evaluator so the
+        # captured CUDA graphs and the engine of the previous call are reused
+        evaluator = DeviceEvaluator.from_model(model, dtype, fold=not args.no_fold, reuse=state["ev"])
+        state["ev"] = evaluator
         reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
         res = c4a0_rust.play_games(reqs, G, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
         n_pos = int(res._soa.n_samples.sum())

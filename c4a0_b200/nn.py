@@ -153,10 +153,31 @@ class FoldedNet(nn.Module):
 
     def __init__(self, model: ConnectFourNet, dtype: torch.dtype = torch.bfloat16, device=None):
         super().__init__()
-        model = model.eval()
         device = device if device is not None else next(model.parameters()).device
+        self.F, self.dtype = model.fc_size, dtype
+        tensors, meta = self._fold(model)
+        self.n_blocks, self.joint_first, self.n_p, self.n_v = meta
+        for name, t in tensors.items():
+            self.register_buffer(name, t.to(device=device, dtype=dtype).contiguous(), persistent=False)
+
+    @torch.no_grad()
+    def refresh(self, model: ConnectFourNet) -> "FoldedNet":
+        """Load a new generation's weights IN PLACE (same architecture): CUDA graphs captured over
+        this module stay valid, so nothing is re-captured between generations."""
+        tensors, meta = self._fold(model)
+        if meta != (self.n_blocks, self.joint_first, self.n_p, self.n_v) or model.fc_size != self.F:
+            raise ValueError("refresh() needs a model of the same architecture")
+        for name, t in tensors.items():
+            getattr(self, name).copy_(t)
+        return self
+
+    @classmethod
+    @torch.no_grad()
+    def _fold(cls, model: ConnectFourNet):
+        """float64 folded weights {buffer name: tensor} + structure (n_blocks, joint_first, n_p, n_v)."""
+        model = model.eval()
         F = model.fc_size
-        self.F, self.dtype = F, dtype
+        out = {}
         layers = list(model.conv.children())
         stem, blocks = layers[0], layers[1:]
         w_in, b_in = _conv_as_matrix(stem)  # x = planes @ w_in + b_in   [84 -> F]
@@ -170,24 +191,18 @@ class FoldedNet(nn.Module):
             s, t = _bn_scale_shift(bn, 42)
             return (ma @ mb) * s[None, :], (ba @ mb + bb) * s + t
 
-        def reg(name, t):
-            self.register_buffer(name, t.to(device=device, dtype=dtype).contiguous(), persistent=False)
-
-        self.n_blocks = len(blocks)
+        n_blocks = len(blocks)
         if blocks:
             wb, bb_ = block_affine(blocks[0])
             w0 = torch.cat([w_in @ wb, w_in], dim=1)  # [84, 2F]: block pre-activation | block input
             b0 = torch.cat([b_in @ wb + bb_, b_in])
         else:
             w0, b0 = w_in, b_in
-        w0p = torch.zeros(self.IN_PAD, w0.shape[1], dtype=torch.float64, device=w0.device)
+        w0p = torch.zeros(cls.IN_PAD, w0.shape[1], dtype=torch.float64, device=w0.device)
         w0p[:84] = w0
-        reg("w0", w0p)
-        reg("b0", b0)
+        out["w0"], out["b0"] = w0p, b0
         for j, blk in enumerate(blocks[1:], start=1):
-            wj, bj = block_affine(blk)
-            reg(f"wblk{j}", wj)
-            reg(f"bblk{j}", bj)
+            out[f"wblk{j}"], out[f"bblk{j}"] = block_affine(blk)
 
         def head_layers(seq):
             hidden, final = [], None
@@ -204,18 +219,15 @@ class FoldedNet(nn.Module):
 
         ph, pf = head_layers(model.fc_policy)
         vh, vf = head_layers(model.fc_value)
-        self.joint_first = bool(ph) and bool(vh)
-        if self.joint_first:
-            reg("wh0", torch.cat([ph[0][0], vh[0][0]], dim=1))
-            reg("bh0", torch.cat([ph[0][1], vh[0][1]]))
+        joint_first = bool(ph) and bool(vh)
+        if joint_first:
+            out["wh0"] = torch.cat([ph[0][0], vh[0][0]], dim=1)
+            out["bh0"] = torch.cat([ph[0][1], vh[0][1]])
             ph, vh = ph[1:], vh[1:]
-        self.n_p, self.n_v = len(ph), len(vh)
         for i, (w, b) in enumerate(ph):
-            reg(f"wp{i}", w)
-            reg(f"bp{i}", b)
+            out[f"wp{i}"], out[f"bp{i}"] = w, b
         for i, (w, b) in enumerate(vh):
-            reg(f"wv{i}", w)
-            reg(f"bv{i}", b)
+            out[f"wv{i}"], out[f"bv{i}"] = w, b
         # final layers, output width padded to 8 columns
         dev0 = pf[0].device
         wpf = torch.zeros(F, 8, dtype=torch.float64, device=dev0)
@@ -226,11 +238,8 @@ class FoldedNet(nn.Module):
         wvf[:, :2] = vf[0]
         bvf = torch.zeros(8, dtype=torch.float64, device=dev0)
         bvf[:2] = vf[1]
-        reg("wpf", wpf)
-        reg("bpf", bpf)
-        reg("wvf", wvf)
-        reg("bvf", bvf)
-        self._flops = None
+        out.update(wpf=wpf, bpf=bpf, wvf=wvf, bvf=bvf)
+        return out, (n_blocks, joint_first, len(ph), len(vh))
 
     @staticmethod
     def _lin_relu(x, w, b):

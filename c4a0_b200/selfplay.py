@@ -37,7 +37,17 @@ from .engine import Engine, GameSamples, run_engines
 DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 1, "dedup": True,
             "max_inline_sims": 0, "arena_blocks": None}
 
-BUCKETS = (128, 256, 512, 1024, 1536, 2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 49152, 65536, 98304, 131072)
+def _buckets():
+    """Network batch sizes that get their own CUDA graph: fine steps (a tick launches the smallest
+    graph covering its live rows, so coarse steps waste GEMM rows), multiples of 256 above 1024."""
+    b = [128, 256, 384, 512, 768, 1024]
+    b += list(range(1536, 4096 + 1, 512))
+    b += list(range(5120, 32768 + 1, 1024))
+    b += list(range(36864, 131072 + 1, 4096))
+    return tuple(b)
+
+
+BUCKETS = _buckets()
 
 
 class DeviceEvaluator:
@@ -55,11 +65,20 @@ class DeviceEvaluator:
             module_or_fn.eval()
 
     @classmethod
-    def from_model(cls, model, dtype: torch.dtype = torch.bfloat16, fold: bool = True) -> "DeviceEvaluator":
-        """ConnectFourNet -> evaluator.  fold=True uses the GEMM-folded inference form (nn.FoldedNet)."""
+    def from_model(cls, model, dtype: torch.dtype = torch.bfloat16, fold: bool = True,
+                   reuse: Optional["DeviceEvaluator"] = None) -> "DeviceEvaluator":
+        """ConnectFourNet -> evaluator.  fold=True uses the GEMM-folded inference form (nn.FoldedNet).
+        Pass the previous generation's evaluator as `reuse` to load the new weights into it in place:
+        the CUDA graphs captured over it (and the cached session) stay valid."""
         from .nn import ConnectFourNet, FoldedNet
 
         if fold and isinstance(model, ConnectFourNet):
+            if reuse is not None and isinstance(reuse.fn, FoldedNet) and reuse.dtype == dtype:
+                try:
+                    reuse.fn.refresh(model)
+                    return reuse
+                except ValueError:
+                    pass
             return cls(FoldedNet(model, dtype=dtype), dtype, FoldedNet.IN_PAD)
         p = next(model.parameters(), None)
         return cls(model, p.dtype if p is not None else dtype, 84)
@@ -119,9 +138,8 @@ class _Lane:
             self.qn[:rows].copy_(b.reshape(rows))
 
     def capture(self, evaluator) -> List[Tuple[int, int]]:
-        key = id(evaluator)
-        if self.graph_key != key:
-            self.graphs, self.graph_key = {}, key
+        if self.graph_key is not evaluator:  # identity, and a strong reference: ids can be recycled
+            self.graphs, self.graph_key = {}, evaluator
             self.pool = torch.cuda.graph_pool_handle()
             sizes = [b for b in BUCKETS if b < self.n_slots] + [self.n_slots]
             with torch.cuda.stream(self.stream):

@@ -303,6 +303,33 @@ for _cls in (GameMetadata, Sample, GameResult, PlayGamesResult):
     _cls.__module__ = "c4a0_rust"  # pybridge.rs:57-59: pickles name the class as c4a0_rust.<Class>
 
 
+_SESSION = {"key": None, "sess": None}
+
+
+def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes):
+    """One engine (tree arenas, NN I/O tensors, captured graphs) is kept between calls with the same
+    configuration — a training loop calls play_games once per generation with identical settings."""
+    from c4a0_b200 import selfplay
+    from c4a0_b200.selfplay import SelfPlaySession
+
+    knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks")))
+    key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes, knobs)
+    if _SESSION["key"] == key and _SESSION["sess"] is not None and _SESSION["cap"] >= n_req:
+        return _SESSION["sess"]
+    close_cached_session()
+    sess = SelfPlaySession(n_slots, n_req, n_iter, c_expl, c_pen, plane_dtype=dtype, device=device,
+                           plane_stride=stride, n_lanes=n_lanes)
+    _SESSION.update(key=key, sess=sess, cap=n_req)
+    return sess
+
+
+def close_cached_session() -> None:
+    """Free the engine kept by the last play_games call (device memory is released)."""
+    if _SESSION["sess"] is not None:
+        _SESSION["sess"].close()
+    _SESSION.update(key=None, sess=None, cap=0)
+
+
 def play_games(
     reqs: Sequence[GameMetadata],
     max_nn_batch_size: int,
@@ -342,22 +369,25 @@ def play_games(
             py_eval_pos_cb = DeviceEvaluator.from_model(py_eval_pos_cb, p.dtype if p is not None else torch.float32)
         if len(np.unique(meta[:, 1:])) != 1:
             raise ValueError("the device fast path plays one model against itself; use the numpy callback for tournaments")
-        sess = SelfPlaySession(
+        sess = _session(
             n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
-            plane_dtype=py_eval_pos_cb.dtype, device=torch.cuda.current_device(), plane_stride=py_eval_pos_cb.plane_stride,
+            py_eval_pos_cb.dtype, torch.cuda.current_device(), py_eval_pos_cb.plane_stride, None,
         )
-    else:
-        sess = SelfPlaySession(
-            n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
-            plane_dtype=torch.float32, device=torch.cuda.current_device(), n_lanes=1,
-        )
-    try:
-        if fast:
+        try:
             soa, info = sess.play(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb)
-        else:
+        except Exception:
+            close_cached_session()  # never keep an engine in an unknown state
+            raise
+    else:
+        sess = _session(
+            n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
+            torch.float32, torch.cuda.current_device(), 84, 1,
+        )
+        try:
             soa, info = sess.play_callback(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb, int(max_nn_batch_size))
-    finally:
-        sess.close()
+        except Exception:
+            close_cached_session()
+            raise
     out = PlayGamesResult._from_soa(meta, soa)
     out._run_info = info  # additive: counters and timings of this call (c4a0_b200.selfplay.RunInfo)
     return out
