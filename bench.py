@@ -277,6 +277,10 @@ def run_ours(args):
         res = c4a0_rust.play_games(reqs, G, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
         n_pos = int(res._soa.n_samples.sum())
         checksum = float(res._soa.q_no_penalty.sum())  # touch the host result
+        if world > 1:  # the trainer lives on rank 0: gather every rank's samples there (NCCL)
+            gm, gs = D.gather_samples(res._meta, res._soa, device=device)
+            if rank == 0:
+                assert int(gs.n_samples.sum()) >= n_pos
         return time.perf_counter() - t0, res._run_info, n_pos, checksum
 
     for _ in range(args.warmup):
