@@ -98,6 +98,8 @@ class RunReport(C.Structure):
         ("kernel_samples", C.c_uint32),
         ("k_step_ms_sum", C.c_double),
         ("k_move_ms_sum", C.c_double),
+        ("k_post_ms_sum", C.c_double),
+        ("nn_ms_sum", C.c_double),
         ("bucket_launches", C.c_uint64 * 32),
     ]
 

@@ -981,7 +981,7 @@ struct c4a0_engine {
   Globals* h_globals = nullptr;   // pinned
   HostStatus* h_status = nullptr; // pinned + mapped
   float *b_logits = nullptr, *b_qp = nullptr, *b_qn = nullptr;  // writable aliases for eval_builtin
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -1014,7 +1014,7 @@ int launch_post(c4a0_engine* e, cudaStream_t s) {
   return 0;
 }
 
-// Enqueue one tick.  `ev` (3 events) brackets k_step and k_move when given.
+// Enqueue one tick.  `ev` (4 events) brackets k_step, k_move and k_post when given.
 int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
   const Dev& D = e->D;
   if (ev) CK(cudaEventRecord(ev[0], s));
@@ -1025,6 +1025,7 @@ int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
   if (ev) CK(cudaEventRecord(ev[2], s));
   int r = launch_post(e, s);
   if (r) return r;
+  if (ev) CK(cudaEventRecord(ev[3], s));
   CK(cudaGetLastError());
   e->steps++;
   return 0;
@@ -1183,7 +1184,7 @@ int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* 
   if (!e->have_requests) return fail(C4A0_E_INVALID, "set_requests() must precede step()");
   cudaStream_t s = (cudaStream_t)stream;
   if (!e->ev[0])
-    for (int i = 0; i < 3; i++) CK(cudaEventCreate(&e->ev[i]));
+    for (int i = 0; i < 4; i++) CK(cudaEventCreate(&e->ev[i]));
   int r = launch_tick(e, s, e->ev);
   if (r) return r;
   CK(cudaStreamSynchronize(s));
@@ -1407,7 +1408,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     cudaEvent_t t0, t1;
   };
   std::vector<Lane> lanes(n_engines);
-  std::vector<cudaEvent_t> kev;  // triples
+  std::vector<cudaEvent_t> kev;  // five per sampled tick: before NN, before k_step, after k_step, k_move, k_post
   for (uint32_t i = 0; i < n_engines; i++) {
     c4a0_engine* e = engines[i];
     if (!e || !e->have_requests) return fail(C4A0_E_INVALID, "engine %u has no requests", i);
@@ -1432,8 +1433,20 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   auto wall0 = std::chrono::steady_clock::now();
   int rc = 0;
   // prime: the planes of the initial roots are already packed (set_requests) -> first network call
-  auto launch_nn = [&](uint32_t i) -> int {
+  // one tick of engine i: the network on the rows packed by the previous tick, then the tree kernels
+  auto launch_round = [&](uint32_t i) -> int {
     Lane& L = lanes[i];
+    cudaEvent_t* ev = nullptr;
+    if (time_kernels_every && (L.e->steps % time_kernels_every) == 0 && kev.size() < 5 * 4096) {
+      size_t b = kev.size();
+      for (int q = 0; q < 5; q++) {
+        cudaEvent_t x;
+        CK(cudaEventCreate(&x));
+        kev.push_back(x);
+      }
+      ev = &kev[b];
+      CK(cudaEventRecord(ev[0], L.s));
+    }
     uint32_t rows = L.e->h_status->n_rows;
     const c4a0_nn_graph* g = graphs[i];
     uint32_t k = 0;
@@ -1442,21 +1455,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     out->nn_launches++;
     out->bucket_launches[k < 31 ? k : 31]++;
     out->nn_rows_launched += g[k].rows;
-    return 0;
-  };
-  auto launch_tree = [&](uint32_t i) -> int {
-    Lane& L = lanes[i];
-    cudaEvent_t* ev = nullptr;
-    if (time_kernels_every && (L.e->steps % time_kernels_every) == 0 && kev.size() < 3 * 4096) {
-      size_t b = kev.size();
-      for (int q = 0; q < 3; q++) {
-        cudaEvent_t x;
-        CK(cudaEventCreate(&x));
-        kev.push_back(x);
-      }
-      ev = &kev[b];
-    }
-    int r = launch_tick(L.e, L.s, ev);
+    int r = launch_tick(L.e, L.s, ev ? ev + 1 : nullptr);
     if (r) return r;
     L.expect++;
     out->ticks++;
@@ -1466,8 +1465,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     Lane& L = lanes[i];
     CK(cudaEventRecord(L.t0, L.s));
     if (L.done) continue;
-    rc = launch_nn(i);
-    if (!rc) rc = launch_tree(i);
+    rc = launch_round(i);
   }
   uint32_t remaining = 0;
   for (auto& L : lanes) remaining += L.done ? 0 : 1;
@@ -1500,8 +1498,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
         rc = fail(C4A0_E_INVALID, "max_ticks reached before all games finished");
         break;
       } else {
-        rc = launch_nn(cur);
-        if (!rc) rc = launch_tree(cur);
+        rc = launch_round(cur);
       }
     }
     cur = (cur + 1) % n_engines;
@@ -1518,20 +1515,22 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
       if (cudaEventElapsedTime(&ms, L.t0, L.t1) == cudaSuccess && ms > mx) mx = ms;
     }
     out->device_ms = mx;
-    double a = 0, b = 0;
+    double sum[4] = {0, 0, 0, 0};
     uint32_t n = 0;
-    for (size_t q = 0; q + 2 < kev.size(); q += 3) {
-      float x = 0, y = 0;
-      if (cudaEventElapsedTime(&x, kev[q], kev[q + 1]) == cudaSuccess &&
-          cudaEventElapsedTime(&y, kev[q + 1], kev[q + 2]) == cudaSuccess) {
-        a += x;
-        b += y;
+    for (size_t q = 0; q + 4 < kev.size(); q += 5) {
+      float d[4];
+      bool ok = true;
+      for (int k = 0; k < 4; k++) ok = ok && cudaEventElapsedTime(&d[k], kev[q + k], kev[q + k + 1]) == cudaSuccess;
+      if (ok) {
+        for (int k = 0; k < 4; k++) sum[k] += d[k];
         n++;
       }
     }
     out->kernel_samples = n;
-    out->k_step_ms_sum = a;
-    out->k_move_ms_sum = b;
+    out->nn_ms_sum = sum[0];
+    out->k_step_ms_sum = sum[1];
+    out->k_move_ms_sum = sum[2];
+    out->k_post_ms_sum = sum[3];
   }
   out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   cleanup();

@@ -283,7 +283,8 @@ class SelfPlaySession:
             info.device_s = rep["device_ms"] / 1e3
             if rep["kernel_samples"]:
                 n = rep["kernel_samples"]
-                info.kernel_ms = {"k_step": rep["k_step_ms_sum"] / n, "k_move": rep["k_move_ms_sum"] / n, "samples": n}
+                info.kernel_ms = {"k_step": rep["k_step_ms_sum"] / n, "k_move": rep["k_move_ms_sum"] / n,
+                                  "k_post": rep["k_post_ms_sum"] / n, "nn": rep["nn_ms_sum"] / n, "samples": n}
         elif host_loop == "python":
             ev0 = torch.cuda.Event(enable_timing=True)
             ev1 = torch.cuda.Event(enable_timing=True)

@@ -177,7 +177,9 @@ typedef struct {
   double wall_ms;
   uint32_t kernel_samples;   /* ticks whose kernels were bracketed by events */
   double k_step_ms_sum;      /* summed device time of the apply+select kernel over those ticks */
-  double k_move_ms_sum;      /* ... of the move / re-root kernel */
+  double k_move_ms_sum;      /* ... of the compaction kernel */
+  double k_post_ms_sum;      /* ... of the dedup / scan / pack kernel */
+  double nn_ms_sum;          /* ... of the network graph that preceded them */
   uint64_t bucket_launches[32]; /* network launches per graph index (all engines) */
 } c4a0_run_report;
 
