@@ -20,15 +20,16 @@
 //     simulation order — the reference's accumulation order.
 //   * Re-rooting keeps the chosen child's subtree and drops the siblings.  Nothing is copied while
 //     the arena has room (root_block simply becomes the child's block); when a half fills up, one
-//     CTA per game (k_move) copies the live subtree breadth-first into the other half.  Memory per
-//     game is 2 * arena_blocks * 160 B, with arena_blocks >= n_iterations + 2.
+//     CTA per game copies the live subtree breadth-first into the other half.  Memory per
+//     game is 2 * arena_blocks * 160 B, with arena_blocks >= n_iterations + 2.  (The copy runs as
+//     phase 0 of k_post.)
 //   * The network batch is dense and de-duplicated, like the reference's NN thread builds it
 //     (self_play.rs:203-220: HashSet<Pos> per model).  One cooperative kernel per tick (k_post)
 //     inserts every waiting leaf into an epoch-tagged hash table (smallest slot wins a key),
 //     numbers the winners in slot order with a decoupled look-back scan, and lets only them write
 //     input planes, to rows 0..n_rows-1.  Every game remembers the row that holds its answer.
 //
-// One tick = k_step -> k_move -> k_post, then the network on rows [0, n_rows).
+// One tick = k_step -> k_post, then the network on rows [0, n_rows).
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
@@ -80,7 +81,7 @@ struct __align__(128) Slot {
   uint32_t req;                    // request index of the game seated here
   uint32_t n_moves;
   uint32_t nn_row;                 // network row holding this game's answer
-  uint32_t urow;                   // row assigned to this slot when it leads its key
+  uint32_t spare;
   unsigned long long c_sims, c_exp, c_term, c_depth;
 };
 __host__ __device__ inline uint64_t leaf_model_of(const Slot& S) {
@@ -92,7 +93,6 @@ constexpr int PATH_STRIDE = 48;  // <= 42 levels below a root; six entries per l
 constexpr int MAXS = C4A0_MAX_SAMPLES;
 constexpr int STEP_THREADS = 128;
 constexpr int POST_THREADS = 256;
-constexpr int MOVE_THREADS = 128;
 enum : uint32_t { ST_IDLE = 0, ST_WAIT_NN = 1, ST_CONTINUE = 2, ST_NEED_MOVE = 3 };
 
 struct Globals {  // one instance in device memory
@@ -131,6 +131,8 @@ struct Dev {  // passed to kernels by value
   uint32_t* path;   // [n_slots][PATH_STRIDE]: (block << 3 | column) per level of the selected path
   Block* blocks;    // [n_slots][2][cap]
   uint32_t* row_slot;
+  uint32_t* bucket;  // [n_slots] hash-table entry of the slot's waiting leaf
+  unsigned long long* rowtag;  // [n_slots] epoch << 32 | row, written by a slot that leads its key
   // per request
   const uint64_t *game_id, *p0, *p1;
   uint32_t* n_samples;
@@ -158,6 +160,37 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
   return x ^ (x >> 31);
+}
+
+// Leaf de-duplication (self_play.rs:203-208).  Called by ONE lane per game once its slot line
+// (leaf position + model ids) has been stored.  Table entry = epoch << 32 | leader slot; an entry of
+// another epoch is empty, so the table is never cleared.  Among games with equal (position, model)
+// the smallest slot becomes the leader (atomicMin) — deterministic whatever order games arrive in.
+__device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64_t km, uint64_t kv, uint64_t kmod,
+                                             uint32_t epoch) {
+  if (!D.dedup) return;
+  __threadfence();  // the slot line must be visible before the slot can be found in the table
+  uint32_t h = (uint32_t)splitmix64(km * 0x9E3779B97F4A7C15ULL ^ splitmix64(kv ^ kmod)) & D.table_mask;
+  const unsigned long long mine = ((unsigned long long)epoch << 32) | slot;
+  for (;;) {
+    unsigned long long* e = D.table + h;
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e);
+    if ((uint32_t)(cur >> 32) != epoch) {
+      unsigned long long prev = atomicCAS(e, cur, mine);
+      if (prev == cur) break;  // first game with this key in this tick
+      cur = prev;
+      if ((uint32_t)(cur >> 32) != epoch) continue;
+    }
+    const Slot* Ld = D.slots + (uint32_t)cur;
+    const uint64_t lm = __ldcg(&Ld->leaf_mask), lv = __ldcg(&Ld->leaf_value);
+    const uint64_t lmod = (c4::popc64(lm) & 1) ? __ldcg(&Ld->model1) : __ldcg(&Ld->model0);
+    if (lm == km && lv == kv && lmod == kmod) {
+      atomicMin(e, mine);
+      break;
+    }
+    h = (h + 1) & D.table_mask;  // another key lives here: linear probing
+  }
+  D.bucket[slot] = h;
 }
 
 // NN input planes of `p` into row `row` (c4r.rs:378-392): 84 values as 16-byte vectors.
@@ -663,7 +696,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     memset(&G, 0, sizeof(G));
   }
   const uint32_t st = G.state;
-  if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction in k_move's own run
+  if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction after a compaction (cannot happen, kept for safety)
   const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
   if (!__any_sync(FULL, live)) return;
   const long long t1 = prof ? clock64() : 0;
@@ -681,6 +714,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   if (live && L.l == 0) {
     store_game(D, G, ns);
     if (ns == ST_NEED_MOVE) push_mover(D, slot);
+    if (ns == ST_WAIT_NN)
+      publish_leaf(D, slot, G.leaf.mask, G.leaf.value, (c4::popc64(G.leaf.mask) & 1) ? G.model1 : G.model0, D.g->tick);
     if (prof) {  // cycles of this game's warp per phase (c4a0_engine_debug_phases)
       uint32_t* o = D.dbg + (size_t)slot * 8;
       o[0] = (uint32_t)(t1 - t0);         // load slot state
@@ -696,12 +731,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_move: one CTA per game whose arena half is full — copy the live subtree breadth-first into the
-// other half, then let the game carry on.
+// Compaction: one CTA per game whose arena half is full — copy the live subtree breadth-first into
+// the other half, then let the game carry on (phase 0 of k_post).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
+__device__ __forceinline__ void compact_movers(const Dev& D, uint32_t n_movers, uint32_t epoch) {
   __shared__ uint32_t sh_next, sh_head;
-  const uint32_t n_movers = D.g->n_movers;
   for (uint32_t m = blockIdx.x; m < n_movers; m += gridDim.x) {
     const uint32_t slot = D.movers[m];
     Slot* S = D.slots + slot;
@@ -762,7 +796,12 @@ __global__ void __launch_bounds__(MOVE_THREADS) k_move(Dev D) {
         memset(&G, 0, sizeof(G));
       }
       const uint32_t ns = run_games(D, L, G, live, ST_CONTINUE);
-      if (threadIdx.x == 0) store_game(D, G, ns);
+      if (threadIdx.x == 0) {
+        store_game(D, G, ns);
+        // a second overflow is impossible right after a compaction, so ns != NEED_MOVE here
+        if (ns == ST_WAIT_NN)
+          publish_leaf(D, slot, G.leaf.mask, G.leaf.value, (c4::popc64(G.leaf.mask) & 1) ? G.model1 : G.model0, epoch);
+      }
     }
     __syncthreads();
   }
@@ -791,59 +830,36 @@ __global__ void k_init(Dev D, uint32_t n_req) {
     S.model1 = D.p1[slot];
   }
   D.slots[slot] = S;
+  if (slot < n_req) publish_leaf(D, slot, 0ull, 0ull, S.model0, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_post (cooperative): de-duplicate the waiting leaves, number the leaders in slot order, pack
-// their planes densely, publish the tick's status to the host, open the next tick.
+// K_post (cooperative): compact the arenas that filled up, then number the leaders of the waiting
+// leaves in slot order (decoupled look-back over CTAs), pack their planes densely, publish the
+// tick's status to the host, open the next tick.  One grid-wide barrier: every leaf of this tick
+// (inserted by k_step, k_init or the compaction phase) must be in the table before leaders are read.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(POST_THREADS) k_post(Dev D) {
+__global__ void __launch_bounds__(POST_THREADS, 4) k_post(Dev D) {  // <= 64 registers: 592 co-resident CTAs
   cg::grid_group grid = cg::this_grid();
   __shared__ uint32_t warp_cnt[POST_THREADS / 32];
   __shared__ uint32_t warp_wait[POST_THREADS / 32];
   __shared__ uint32_t sh_base;
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t epoch = D.g->tick;
+  const uint32_t n_movers = D.g->n_movers;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (n_movers) compact_movers(D, n_movers, epoch);
+  grid.sync();
   Slot* S = D.slots + slot;
   bool waiting = false;
-  uint64_t km = 0, kv = 0, kmod = 0;
+  uint64_t km = 0, kv = 0;
   if (slot < D.n_slots && S->state == ST_WAIT_NN) {
     waiting = true;
     km = S->leaf_mask;
     kv = S->leaf_value;
-    kmod = leaf_model_of(*S);
-  }
-  uint32_t bucket = 0;
-  if (D.dedup) {
-    // Table entry = epoch << 32 | leader slot; an entry of another epoch is empty, so the table is
-    // never cleared.  Among games with equal (position, model) the smallest slot becomes the
-    // leader (atomicMin) — deterministic whatever order the games arrive in.
-    if (waiting) {
-      uint32_t h = (uint32_t)splitmix64(km * 0x9E3779B97F4A7C15ULL ^ splitmix64(kv ^ kmod)) & D.table_mask;
-      const unsigned long long mine = ((unsigned long long)epoch << 32) | slot;
-      for (;;) {
-        unsigned long long* e = D.table + h;
-        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e);
-        if ((uint32_t)(cur >> 32) != epoch) {
-          unsigned long long prev = atomicCAS(e, cur, mine);
-          if (prev == cur) break;  // first game with this key in this tick
-          cur = prev;
-          if ((uint32_t)(cur >> 32) != epoch) continue;
-        }
-        const Slot* Ld = D.slots + (uint32_t)cur;  // keys were written by an earlier kernel
-        if (Ld->leaf_mask == km && Ld->leaf_value == kv && leaf_model_of(*Ld) == kmod) {
-          atomicMin(e, mine);
-          break;
-        }
-        h = (h + 1) & D.table_mask;  // another key lives here: linear probing
-      }
-      bucket = h;
-    }
-    grid.sync();
   }
   uint32_t leader = slot;
-  if (waiting && D.dedup) leader = (uint32_t)D.table[bucket];
+  if (waiting && D.dedup) leader = (uint32_t)D.table[D.bucket[slot]];
   const bool lead = waiting && leader == slot;
   // CTA-level exclusive scan of `lead`
   const unsigned bal = __ballot_sync(0xffffffffu, lead);
@@ -861,13 +877,11 @@ __global__ void __launch_bounds__(POST_THREADS) k_post(Dev D) {
     wtotal += warp_wait[w];
   }
   const uint32_t local = before + __popc(bal & ((1u << lane) - 1u));
-  // decoupled look-back over the CTAs before this one
+  // decoupled look-back over the CTAs before this one (all CTAs are co-resident)
   if (threadIdx.x == 0) {
     sh_base = 0u;
-    volatile unsigned long long* mine = D.cta_counts + blockIdx.x;
-    __threadfence();
-    *mine = ((unsigned long long)epoch << 32) | total;
-    if (wtotal) atomicAdd(&D.g->n_waiting, wtotal);
+    *reinterpret_cast<volatile unsigned long long*>(D.cta_counts + blockIdx.x) = ((unsigned long long)epoch << 32) | total;
+    if (wtotal) atomicAdd(&D.g->leaves_total, (unsigned long long)wtotal);
   }
   __syncthreads();
   uint32_t part = 0;
@@ -884,28 +898,33 @@ __global__ void __launch_bounds__(POST_THREADS) k_post(Dev D) {
   if (lane == 0 && part) atomicAdd(&sh_base, part);
   __syncthreads();
   const uint32_t base = sh_base;
-  if (lead) S->urow = base + local;
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) D.g->n_rows = base + total;
-  grid.sync();
-  if (waiting) {
-    const uint32_t row = (leader == slot) ? base + local : D.slots[leader].urow;
-    S->nn_row = row;
-    if (leader == slot) {
-      D.row_slot[row] = slot;
-      write_planes(D, row, Pos{km, kv});
-    }
+  uint32_t row = base + local;
+  if (lead) {
+    // followers (possibly in other CTAs) wait for this word: it carries the epoch
+    *reinterpret_cast<volatile unsigned long long*>(D.rowtag + slot) = ((unsigned long long)epoch << 32) | row;
+    D.row_slot[row] = slot;
+    write_planes(D, row, Pos{km, kv});
+  } else if (waiting) {
+    volatile unsigned long long* p = D.rowtag + leader;
+    unsigned long long v;
+    do {
+      v = *p;
+    } while ((uint32_t)(v >> 32) != epoch);
+    row = (uint32_t)v;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (waiting) S->nn_row = row;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    // the last CTA knows the total; everybody has read `tick` and `n_movers` (before grid.sync)
     Globals* G = D.g;
-    const uint32_t rows = G->n_rows;
+    const uint32_t rows = base + total;
+    __threadfence();
+    G->n_rows = rows;
     G->rows_total += rows;
-    G->leaves_total += G->n_waiting;
-    G->n_waiting = 0u;
     HostStatus* hs = D.status;
     hs->n_rows = rows;
     hs->n_finished = G->n_finished;
     hs->n_running = G->n_running;
-    hs->n_movers = G->n_movers;
+    hs->n_movers = n_movers;
     hs->error = G->error;
     __threadfence_system();
     hs->tick = epoch;  // written last: the host spins on it
@@ -1014,15 +1033,13 @@ int launch_post(c4a0_engine* e, cudaStream_t s) {
   return 0;
 }
 
-// Enqueue one tick.  `ev` (4 events) brackets k_step, k_move and k_post when given.
+// Enqueue one tick.  `ev` (4 events) brackets k_step and k_post when given (ev[1] == ev[2]).
 int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
   const Dev& D = e->D;
   if (ev) CK(cudaEventRecord(ev[0], s));
   k_step<<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
   if (ev) CK(cudaEventRecord(ev[1], s));
-  unsigned grid = D.n_slots < 296u ? D.n_slots : 296u;
-  k_move<<<grid, MOVE_THREADS, 0, s>>>(D);
-  if (ev) CK(cudaEventRecord(ev[2], s));
+  if (ev) CK(cudaEventRecord(ev[2], s));  // (compaction is phase 0 of k_post)
   int r = launch_post(e, s);
   if (r) return r;
   if (ev) CK(cudaEventRecord(ev[3], s));
@@ -1082,7 +1099,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   size_t T = 1;
   while (T < 2 * S) T <<= 1;
   D.table_mask = (uint32_t)(T - 1);
-  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S);
+  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S); DA(D.bucket, S); DA(D.rowtag, S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
   DA(D.table, T); DA(D.cta_counts, post_grid);
   uint64_t *gid, *p0, *p1;
@@ -1162,6 +1179,7 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
   }
   CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
   CK(cudaMemsetAsync(D.cta_counts, 0, e->post_grid * sizeof(unsigned long long), s));
+  CK(cudaMemsetAsync(D.rowtag, 0, (size_t)D.n_slots * sizeof(unsigned long long), s));
   k_init<<<blocks_for(D.n_slots, 256), 256, 0, s>>>(D, n);
   CK(cudaGetLastError());
   int r = launch_post(e, s);
