@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
     ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
     ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")
+    ap.add_argument("--plain-fold", action="store_true", help="GEMM-folded form without the epilogue-fused layout (FoldedNet)")
     return ap.parse_args()
 
 
@@ -271,7 +272,7 @@ def run_ours(args):
         D.broadcast_model(model)  # a generation's weights: rank 0 -> all (NCCL); no-op at N=1
         # weights -> inference form, loaded in place into the previous generation's evaluator so the
         # captured CUDA graphs and the engine of the previous call are reused
-        evaluator = DeviceEvaluator.from_model(model, dtype, fold=not args.no_fold, reuse=state["ev"])
+        evaluator = DeviceEvaluator.from_model(model, dtype, fold=(False if args.no_fold else ("plain" if args.plain_fold else True)), reuse=state["ev"])
         state["ev"] = evaluator
         reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
         res = c4a0_rust.play_games(reqs, G, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
@@ -359,7 +360,7 @@ def run_ours(args):
         "leaf_evals_per_s": expansions_all / dev_s_max,
         "dedup": {"enabled": not args.no_dedup, "leaf_requests": expansions_all, "unique_rows": evals_all,
                   "rows_launched_incl_bucket_padding": rows_launched_all},
-        "lanes": args.lanes, "nn_form": "module" if args.no_fold else "GEMM-folded (c4a0_b200.nn.FoldedNet)",
+        "lanes": args.lanes, "nn_form": "module" if args.no_fold else ("GEMM-folded (FoldedNet)" if args.plain_fold else "GEMM-folded, epilogue-fused (FusedNet)"),
         "roofline": roofline,
         "nn_roofline": {
             "bound": "tensor", "unit": "TFLOP/s", "flops_per_eval": flops,

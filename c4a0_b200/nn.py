@@ -278,3 +278,105 @@ class FoldedNet(nn.Module):
             if name.startswith("w"):
                 total += 2 * t.shape[0] * t.shape[1]
         return total
+
+
+class FusedNet(FoldedNet):
+    """FoldedNet with every elementwise pass folded into a GEMM epilogue (default c4a0 family:
+    one residual block, both heads with at least one hidden layer).
+
+    The block output is h = relu(pre) + inp with `pre` and `inp` both affine in the 84 input planes.
+    The layer after it computes h @ W = relu(pre) @ W + inp @ W, and inp @ W is again affine in the
+    planes: inp @ W = planes @ (W_in W) + b_in W.  So with the activation buffer laid out as
+    [ relu(pre) (F columns) | planes (96 columns) ] per row,
+
+        GEMM 1   buf[:, :F] = relu(buf[:, F:] @ W1 + b1)            (bias+ReLU epilogue, strided output)
+        GEMM 2   y          = relu(buf @ [Wh ; W_in Wh] + b2)       ([B, F+96] x [F+96, 2F], epilogue)
+
+    and no tensor is touched by a stand-alone elementwise kernel before the two tiny output layers.
+    The engine writes its planes straight into columns F..F+84 of `buf` (plane_stride = F + 96,
+    plane_offset = F), so the network input needs no copy either.
+    """
+
+    def __init__(self, model: ConnectFourNet, dtype: torch.dtype = torch.bfloat16, device=None):
+        super().__init__(model, dtype=dtype, device=device)
+        if not self.supports(model):
+            raise ValueError("FusedNet needs n_residual_blocks == 1 and hidden layers in both heads")
+        self.plane_stride = self.F + self.IN_PAD
+        self.plane_offset = self.F
+        self._refuse()
+        self._strided_out_ok = None
+
+    @staticmethod
+    def supports(model: ConnectFourNet) -> bool:
+        c = model.config
+        return c.n_residual_blocks == 1 and c.n_policy_layers >= 2 and c.n_value_layers >= 2
+
+    @torch.no_grad()
+    def _refuse(self):
+        F = self.F
+        w0, b0 = self.w0.double(), self.b0.double()      # [96, 2F]: pre | inp
+        wh, bh = self.wh0.double(), self.bh0.double()    # [F, 2F]
+        w1, b1 = w0[:, :F], b0[:F]
+        w_in, b_in = w0[:, F:], b0[F:]
+        w2 = torch.cat([wh, w_in @ wh], dim=0)           # [F + 96, 2F]
+        b2 = bh + b_in @ wh
+        for name, t in (("f_w1", w1), ("f_b1", b1), ("f_w2", w2), ("f_b2", b2)):
+            t = t.to(self.dtype).contiguous()
+            if hasattr(self, name):
+                getattr(self, name).copy_(t)
+            else:
+                self.register_buffer(name, t, persistent=False)
+
+    @torch.no_grad()
+    def refresh(self, model: ConnectFourNet) -> "FusedNet":
+        # NOTE: w0/wh0 are stored in `dtype`; re-fold from the float64 source for full accuracy
+        super().refresh(model)
+        tensors, _ = self._fold(model)
+        F = self.F
+        w0, b0, wh, bh = tensors["w0"], tensors["b0"], tensors["wh0"], tensors["bh0"]
+        self.f_w1.copy_(w0[:, :F])
+        self.f_b1.copy_(b0[:F])
+        self.f_w2.copy_(torch.cat([wh, w0[:, F:] @ wh], dim=0))
+        self.f_b2.copy_(bh + b0[F:] @ wh)
+        return self
+
+    def forward(self, buf: torch.Tensor):
+        """buf: [B, F + 96]; columns F..F+84 hold the input planes (rest of the tail zero).  Columns
+        0..F are overwritten.  A [B,2,6,7] tensor is accepted too (copied into a fresh buffer)."""
+        F = self.F
+        if buf.dim() == 4:
+            planes = buf
+            buf = planes.new_zeros(planes.shape[0], F + self.IN_PAD)
+            buf[:, F : F + 84] = planes.reshape(planes.shape[0], 84)
+        x0 = buf[:, F:]
+        if buf.is_cuda:
+            if self._strided_out_ok is None:
+                self._strided_out_ok = self._probe_strided_out(buf)
+            if self._strided_out_ok:
+                torch._addmm_activation(self.f_b1, x0, self.f_w1, out=buf[:, :F])
+            else:
+                buf[:, :F] = torch._addmm_activation(self.f_b1, x0, self.f_w1)
+            y = torch._addmm_activation(self.f_b2, buf, self.f_w2)
+        else:
+            buf[:, :F] = torch.relu(torch.addmm(self.f_b1, x0, self.f_w1))
+            y = torch.relu(torch.addmm(self.f_b2, buf, self.f_w2))
+        hp, hv = y[:, :F], y[:, F:]
+        for i in range(self.n_p):
+            hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
+        for i in range(self.n_v):
+            hv = self._lin_relu(hv, getattr(self, f"wv{i}"), getattr(self, f"bv{i}"))
+        logits = torch.addmm(self.bpf, hp, self.wpf)[:, :7].float()
+        q = torch.tanh(torch.addmm(self.bvf, hv, self.wvf)[:, :2].float())
+        return torch.log_softmax(logits, dim=1), q[:, 0], q[:, 1]
+
+    def _probe_strided_out(self, buf: torch.Tensor) -> bool:
+        """Does the cuBLASLt epilogue path accept a row-strided `out`?  Checked once, numerically."""
+        try:
+            F = self.F
+            t = torch.zeros(8, F + self.IN_PAD, dtype=buf.dtype, device=buf.device)
+            t[:, F : F + 84] = (torch.arange(8 * 84, device=buf.device).reshape(8, 84) % 3 == 0).to(buf.dtype)
+            want = torch.relu(torch.addmm(self.f_b1, t[:, F:], self.f_w1))
+            torch._addmm_activation(self.f_b1, t[:, F:], self.f_w1, out=t[:, :F])
+            return bool(torch.allclose(t[:, :F].float(), want.float(), atol=2e-2, rtol=2e-2))
+        except Exception:
+            return False

@@ -57,10 +57,11 @@ class DeviceEvaluator:
     of dtype `dtype` and returns (policy [B,7], q_penalty [B], q_no_penalty [B]) cuda tensors.
     """
 
-    def __init__(self, module_or_fn, dtype: torch.dtype = torch.float32, plane_stride: int = 84):
+    def __init__(self, module_or_fn, dtype: torch.dtype = torch.float32, plane_stride: int = 84, plane_offset: int = 0):
         self.fn = module_or_fn
         self.dtype = dtype
-        self.plane_stride = plane_stride
+        self.plane_stride = plane_stride  # elements per row of the buffer the engine writes planes into
+        self.plane_offset = plane_offset  # first plane element of a row (the buffer may hold more)
         if isinstance(module_or_fn, torch.nn.Module):
             module_or_fn.eval()
 
@@ -70,7 +71,7 @@ class DeviceEvaluator:
         """ConnectFourNet -> evaluator.  fold=True uses the GEMM-folded inference form (nn.FoldedNet).
         Pass the previous generation's evaluator as `reuse` to load the new weights into it in place:
         the CUDA graphs captured over it (and the cached session) stay valid."""
-        from .nn import ConnectFourNet, FoldedNet
+        from .nn import ConnectFourNet, FoldedNet, FusedNet
 
         if fold and isinstance(model, ConnectFourNet):
             if reuse is not None and isinstance(reuse.fn, FoldedNet) and reuse.dtype == dtype:
@@ -79,6 +80,9 @@ class DeviceEvaluator:
                     return reuse
                 except ValueError:
                     pass
+            if fold != "plain" and FusedNet.supports(model):
+                net = FusedNet(model, dtype=dtype)
+                return cls(net, dtype, net.plane_stride, net.plane_offset)
             return cls(FoldedNet(model, dtype=dtype), dtype, FoldedNet.IN_PAD)
         p = next(model.parameters(), None)
         return cls(model, p.dtype if p is not None else dtype, 84)
@@ -113,8 +117,9 @@ class _Lane:
     """One engine + its NN I/O tensors + its stream."""
 
     def __init__(self, n_slots, max_requests, n_iter, c_expl, c_pen, plane_dtype, device, max_inline, stride, flags,
-                 arena_blocks):
+                 arena_blocks, offset=0):
         self.n_slots = n_slots
+        self.offset = offset
         self.engine = Engine(
             n_slots, max(1, max_requests), n_iter, c_expl, c_pen,
             L.PLANES_BF16 if plane_dtype == torch.bfloat16 else L.PLANES_F32, max_inline, device.index, stride, flags,
@@ -124,7 +129,8 @@ class _Lane:
         self.logits = torch.zeros(n_slots, 7, dtype=torch.float32, device=device)
         self.qp = torch.zeros(n_slots, dtype=torch.float32, device=device)
         self.qn = torch.zeros(n_slots, dtype=torch.float32, device=device)
-        self.engine.bind_io(self.planes.data_ptr(), self.logits.data_ptr(), self.qp.data_ptr(), self.qn.data_ptr())
+        self.engine.bind_io(self.planes.data_ptr() + offset * self.planes.element_size(), self.logits.data_ptr(),
+                            self.qp.data_ptr(), self.qn.data_ptr())
         self.stream = torch.cuda.Stream(device=device)
         self.graphs = {}  # rows -> torch.cuda.CUDAGraph
         self.graph_key = None
@@ -171,6 +177,7 @@ class SelfPlaySession:
         device: int = 0,
         max_inline_sims: int = 0,
         plane_stride: int = 84,
+        plane_offset: int = 0,
         n_lanes: Optional[int] = None,
         dedup: Optional[bool] = None,
         arena_blocks: Optional[int] = None,
@@ -189,6 +196,7 @@ class SelfPlaySession:
         self.n_slots = n_slots
         self.plane_dtype = plane_dtype
         self.plane_stride = plane_stride
+        self.plane_offset = plane_offset
         flags = 0 if dedup else L.FLAG_NO_DEDUP
         if arena_blocks is None:
             arena_blocks = DEFAULTS["arena_blocks"]
@@ -201,7 +209,7 @@ class SelfPlaySession:
         per = [(n_slots + i) // n_lanes for i in range(n_lanes)][::-1]
         self.lanes = [
             _Lane(s, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, self.device,
-                  max_inline_sims, plane_stride, flags, arena_blocks)
+                  max_inline_sims, plane_stride, flags, arena_blocks, plane_offset)
             for s in per if s > 0
         ]
 
@@ -361,7 +369,8 @@ class SelfPlaySession:
             while n_req:
                 n_rows, _, _, model = ln.engine.fetch_rows(s)
                 if n_rows:
-                    planes = ln.planes[:n_rows, :84].cpu().numpy().reshape(n_rows, 2, 6, 7)
+                    o = ln.offset
+                    planes = ln.planes[:n_rows, o : o + 84].cpu().numpy().reshape(n_rows, 2, 6, 7)
                     lg, a, b = h_logits.numpy(), h_qp.numpy(), h_qn.numpy()
                     for mid in np.unique(model):
                         rows = np.nonzero(model == mid)[0]

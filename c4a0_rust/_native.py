@@ -306,19 +306,19 @@ for _cls in (GameMetadata, Sample, GameResult, PlayGamesResult):
 _SESSION = {"key": None, "sess": None}
 
 
-def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes):
+def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes, offset=0):
     """One engine (tree arenas, NN I/O tensors, captured graphs) is kept between calls with the same
     configuration — a training loop calls play_games once per generation with identical settings."""
     from c4a0_b200 import selfplay
     from c4a0_b200.selfplay import SelfPlaySession
 
     knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks")))
-    key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes, knobs)
+    key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, offset, n_lanes, knobs)
     if _SESSION["key"] == key and _SESSION["sess"] is not None and _SESSION["cap"] >= n_req:
         return _SESSION["sess"]
     close_cached_session()
     sess = SelfPlaySession(n_slots, n_req, n_iter, c_expl, c_pen, plane_dtype=dtype, device=device,
-                           plane_stride=stride, n_lanes=n_lanes)
+                           plane_stride=stride, plane_offset=offset, n_lanes=n_lanes)
     _SESSION.update(key=key, sess=sess, cap=n_req)
     return sess
 
@@ -372,6 +372,7 @@ def play_games(
         sess = _session(
             n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
             py_eval_pos_cb.dtype, torch.cuda.current_device(), py_eval_pos_cb.plane_stride, None,
+            getattr(py_eval_pos_cb, "plane_offset", 0),
         )
         try:
             soa, info = sess.play(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb)
@@ -381,7 +382,7 @@ def play_games(
     else:
         sess = _session(
             n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
-            torch.float32, torch.cuda.current_device(), 84, 1,
+            torch.float32, torch.cuda.current_device(), 84, 1, 0,
         )
         try:
             soa, info = sess.play_callback(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb, int(max_nn_batch_size))

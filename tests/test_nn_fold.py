@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from c4a0_b200.nn import ConnectFourNet, FoldedNet, ModelConfig, default_config
+from c4a0_b200.nn import ConnectFourNet, FoldedNet, FusedNet, ModelConfig, default_config
 
 
 def _randomize_bn(model):
@@ -71,3 +71,32 @@ def test_state_dict_names_match_reference_layout():
         "fc_policy.0.0.weight", "fc_policy.0.1.running_var", "fc_policy.3.weight", "fc_value.0.0.bias", "fc_value.1.weight",
     ):
         assert k in keys, k
+
+
+def test_fused_form_equals_module_and_refreshes_in_place():
+    torch.manual_seed(21)
+    cfg = dict(n_residual_blocks=1, conv_filter_size=6, n_policy_layers=4, n_value_layers=2)
+    model = ConnectFourNet(ModelConfig(**cfg)).double().eval()
+    _randomize_bn(model)
+    x = _planes(32).double()
+    f = FusedNet(model, dtype=torch.float64)
+    assert (f.plane_stride, f.plane_offset) == (model.fc_size + 96, model.fc_size)
+    buf = torch.zeros(32, f.plane_stride, dtype=torch.float64)
+    buf[:, f.plane_offset : f.plane_offset + 84] = x.reshape(32, 84)
+    with torch.no_grad():
+        want = model(x)
+        got = f(buf)
+        got4 = f(x)
+    for a, b, c in zip(got, want, got4):
+        assert torch.allclose(a.double(), b, atol=1e-6) and torch.allclose(c.double(), b, atol=1e-6)
+    # a new generation of weights, loaded in place
+    torch.manual_seed(22)
+    model2 = ConnectFourNet(ModelConfig(**cfg)).double().eval()
+    ptr = f.f_w2.data_ptr()
+    f.refresh(model2)
+    assert f.f_w2.data_ptr() == ptr
+    buf[:, : f.plane_offset] = 0
+    with torch.no_grad():
+        for a, b in zip(f(buf), model2(x)):
+            assert torch.allclose(a.double(), b, atol=1e-6)
+    assert not FusedNet.supports(ConnectFourNet(ModelConfig(n_residual_blocks=2, conv_filter_size=2, n_policy_layers=2, n_value_layers=2)))

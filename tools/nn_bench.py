@@ -5,7 +5,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from c4a0_b200.nn import ConnectFourNet, FoldedNet, default_config  # noqa: E402
+from c4a0_b200.nn import ConnectFourNet, FoldedNet, FusedNet, default_config  # noqa: E402
 
 torch.manual_seed(1337)
 model = ConnectFourNet(default_config()).cuda().eval()
@@ -43,4 +43,8 @@ for B in (128, 1024, 4096, 8192, 16384, 65536):
         xp = torch.zeros(B, 96, device="cuda", dtype=dt)
         ms = timeit(f, xp)
         row.append(f"folded {name} {ms*1e3:8.1f} us ({B*flops/ms/1e9:7.1f} TF/s ref-flops)")
+        fu = FusedNet(model.float(), dtype=dt)
+        xb = torch.zeros(B, fu.plane_stride, device="cuda", dtype=dt)
+        ms = timeit(fu, xb)
+        row.append(f"fused {name} {ms*1e3:8.1f} us (strided out {fu._strided_out_ok})")
     print(" | ".join(row), flush=True)
