@@ -303,6 +303,8 @@ def run_ours(args):
     evals = sum(r[1].stats["nn_evals"] for r in runs)
     expansions = sum(r[1].stats["expansions"] for r in runs)
     nn_rows_launched = sum(r[1].report.get("nn_rows_launched", 0) for r in runs)
+    compactions = sum(r[1].stats.get("compactions", 0) for r in runs)
+    engine_gb = runs[-1][1].engine_bytes / 1e9
     ticks = sum(r[1].ticks for r in runs)
     depth = sum(r[1].stats["select_depth_sum"] for r in runs)
     kms = [r[1].kernel_ms for r in runs if r[1].kernel_ms]
@@ -360,6 +362,7 @@ def run_ours(args):
         "leaf_evals_per_s": expansions_all / dev_s_max,
         "dedup": {"enabled": not args.no_dedup, "leaf_requests": expansions_all, "unique_rows": evals_all,
                   "rows_launched_incl_bucket_padding": rows_launched_all},
+        "compactions_per_step": compactions / max(1, args.steps), "engine_device_gb": engine_gb,
         "lanes": args.lanes, "nn_form": "module" if args.no_fold else ("GEMM-folded (FoldedNet)" if args.plain_fold else "GEMM-folded, epilogue-fused (FusedNet)"),
         "roofline": roofline,
         "nn_roofline": {

@@ -836,8 +836,9 @@ __global__ void k_init(Dev D, uint32_t n_req) {
 // ------------------------------------------------------------------------------------------------
 // K_post (cooperative): compact the arenas that filled up, then number the leaders of the waiting
 // leaves in slot order (decoupled look-back over CTAs), pack their planes densely, publish the
-// tick's status to the host, open the next tick.  One grid-wide barrier: every leaf of this tick
-// (inserted by k_step, k_init or the compaction phase) must be in the table before leaders are read.
+// tick's status to the host, open the next tick.  Every leaf of this tick must be in the table
+// before leaders are read: those inserted by k_step / k_init are (kernel boundary); a grid-wide
+// barrier is needed only in ticks where the compaction phase ran and published leaves itself.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(POST_THREADS, 4) k_post(Dev D) {  // <= 64 registers: 592 co-resident CTAs
   cg::grid_group grid = cg::this_grid();
@@ -848,8 +849,10 @@ __global__ void __launch_bounds__(POST_THREADS, 4) k_post(Dev D) {  // <= 64 reg
   const uint32_t epoch = D.g->tick;
   const uint32_t n_movers = D.g->n_movers;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (n_movers) compact_movers(D, n_movers, epoch);
-  grid.sync();
+  if (n_movers) {  // grid-uniform: leaves published by the compaction phase need the barrier
+    compact_movers(D, n_movers, epoch);
+    grid.sync();
+  }
   Slot* S = D.slots + slot;
   bool waiting = false;
   uint64_t km = 0, kv = 0;
