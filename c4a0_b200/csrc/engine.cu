@@ -22,16 +22,16 @@
 //     the arena has room (root_block simply becomes the child's block); when a half fills up, one
 //     CTA per game copies the live subtree breadth-first into the other half.  Memory per
 //     game is 2 * arena_blocks * 160 B, with arena_blocks >= n_iterations + 2.  (The copy runs as
-//     phase 0 of k_post.)
+//     k_tail.)
 //   * The network batch is dense and de-duplicated, like the reference's NN thread builds it
-//     (self_play.rs:203-220: HashSet<Pos> per model).  One cooperative kernel per tick (k_post)
-//     inserts every waiting leaf into an epoch-tagged hash table (smallest slot wins a key),
-//     numbers the winners in slot order with a decoupled look-back scan, and lets only them write
-//     input planes, to rows 0..n_rows-1.  Every game remembers the row that holds its answer.
+//     (self_play.rs:203-220: HashSet<Pos> per model).  As soon as a game knows its next leaf it
+//     inserts (position, model) into an epoch-tagged hash table; the first game to claim a key
+//     draws the next row number from an atomic counter and writes the input planes of that row,
+//     later games with the same key just remember who leads it.  Rows are dense, 0..n_rows-1.
 //
-// One tick = k_step -> k_post, then the network on rows [0, n_rows).
+// One tick = k_step -> k_tail, then the network on rows [0, n_rows).  k_tail compacts the arenas
+// that filled up and publishes the tick's status (n_rows, finished games) to mapped host memory.
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <string.h>
@@ -45,8 +45,6 @@
 #include "c4_rng.cuh"
 #include "c4_rules.cuh"
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -80,7 +78,7 @@ struct __align__(128) Slot {
   uint32_t half;
   uint32_t req;                    // request index of the game seated here
   uint32_t n_moves;
-  uint32_t nn_row;                 // network row holding this game's answer
+  uint32_t nn_leader;              // slot that leads this game's leaf key: its rowtag names the network row
   uint32_t spare;
   unsigned long long c_sims, c_exp, c_term, c_depth;
 };
@@ -92,18 +90,19 @@ static_assert(sizeof(Slot) == 128, "slot state must be one cache line");
 constexpr int PATH_STRIDE = 48;  // <= 42 levels below a root; six entries per lane
 constexpr int MAXS = C4A0_MAX_SAMPLES;
 constexpr int STEP_THREADS = 128;
-constexpr int POST_THREADS = 256;
 enum : uint32_t { ST_IDLE = 0, ST_WAIT_NN = 1, ST_CONTINUE = 2, ST_NEED_MOVE = 3 };
 
 struct Globals {  // one instance in device memory
-  uint32_t tick;  // epoch of the hash table / scan: advanced at the end of every k_post
+  uint32_t tick;  // epoch of the hash table / scan: advanced at the end of every k_tail
   uint32_t n_req;
   uint32_t next_req;
   uint32_t n_finished;
   uint32_t n_running;
   uint32_t n_movers;
-  uint32_t n_rows;
-  uint32_t n_waiting;
+  uint32_t n_rows;      // rows of the batch the network is about to evaluate
+  uint32_t rows_acc;    // row counter of the tick being built
+  uint32_t wait_acc;    // games waiting for the network in the tick being built
+  uint32_t tail_done;   // k_tail CTA ticket
   int32_t error;
   uint32_t pad;
   unsigned long long skipped_root_sims;
@@ -115,7 +114,7 @@ struct Globals {  // one instance in device memory
   unsigned long long leaves_total;  // sum over ticks of games waiting for the network
 };
 
-struct HostStatus {  // mapped pinned host memory, written by k_post at the end of every tick
+struct HostStatus {  // mapped pinned host memory, written by k_tail at the end of every tick
   volatile uint32_t tick;
   volatile uint32_t n_rows;
   volatile uint32_t n_finished;
@@ -132,7 +131,7 @@ struct Dev {  // passed to kernels by value
   Block* blocks;    // [n_slots][2][cap]
   uint32_t* row_slot;
   uint32_t* bucket;  // [n_slots] hash-table entry of the slot's waiting leaf
-  unsigned long long* rowtag;  // [n_slots] epoch << 32 | row, written by a slot that leads its key
+  unsigned long long* rowtag;  // [n_slots] epoch << 32 | row, written by the slot that leads a key
   // per request
   const uint64_t *game_id, *p0, *p1;
   uint32_t* n_samples;
@@ -143,7 +142,6 @@ struct Dev {  // passed to kernels by value
   HostStatus* status;  // device address of the mapped host struct
   uint32_t* movers;
   unsigned long long* table;       // [table_mask+1]: epoch << 32 | leader slot
-  unsigned long long* cta_counts;  // [k_post grid]:   epoch << 32 | leaders in that CTA
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
@@ -160,37 +158,6 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
   return x ^ (x >> 31);
-}
-
-// Leaf de-duplication (self_play.rs:203-208).  Called by ONE lane per game once its slot line
-// (leaf position + model ids) has been stored.  Table entry = epoch << 32 | leader slot; an entry of
-// another epoch is empty, so the table is never cleared.  Among games with equal (position, model)
-// the smallest slot becomes the leader (atomicMin) — deterministic whatever order games arrive in.
-__device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64_t km, uint64_t kv, uint64_t kmod,
-                                             uint32_t epoch) {
-  if (!D.dedup) return;
-  __threadfence();  // the slot line must be visible before the slot can be found in the table
-  uint32_t h = (uint32_t)splitmix64(km * 0x9E3779B97F4A7C15ULL ^ splitmix64(kv ^ kmod)) & D.table_mask;
-  const unsigned long long mine = ((unsigned long long)epoch << 32) | slot;
-  for (;;) {
-    unsigned long long* e = D.table + h;
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e);
-    if ((uint32_t)(cur >> 32) != epoch) {
-      unsigned long long prev = atomicCAS(e, cur, mine);
-      if (prev == cur) break;  // first game with this key in this tick
-      cur = prev;
-      if ((uint32_t)(cur >> 32) != epoch) continue;
-    }
-    const Slot* Ld = D.slots + (uint32_t)cur;
-    const uint64_t lm = __ldcg(&Ld->leaf_mask), lv = __ldcg(&Ld->leaf_value);
-    const uint64_t lmod = (c4::popc64(lm) & 1) ? __ldcg(&Ld->model1) : __ldcg(&Ld->model0);
-    if (lm == km && lv == kv && lmod == kmod) {
-      atomicMin(e, mine);
-      break;
-    }
-    h = (h + 1) & D.table_mask;  // another key lives here: linear probing
-  }
-  D.bucket[slot] = h;
 }
 
 // NN input planes of `p` into row `row` (c4r.rs:378-392): 84 values as 16-byte vectors.
@@ -230,6 +197,47 @@ __device__ __forceinline__ void write_planes(const Dev& D, uint32_t row, Pos p) 
       uint32_t b = (uint32_t)((v < 16 ? lo >> (4 * v) : hi >> (4 * (v - 16))) & 0xfull);
       dst[v] = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
     }
+  }
+}
+
+// Leaf de-duplication + row assignment (self_play.rs:203-220).  Called by ONE lane per game once
+// its slot line (leaf position + model ids) has been stored.  Table entry = epoch << 32 | leader
+// slot; an entry of another epoch is empty, so the table is never cleared.  The first game to claim
+// a key leads it: it takes the next row of the batch and writes the planes; the others only record
+// the leader.  (Which of several equal leaves leads, and hence the order of rows, depends on
+// arrival order; rows are independent in the network, so results do not.)
+__device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64_t km, uint64_t kv, uint64_t kmod,
+                                             uint32_t epoch) {
+  uint32_t leader = slot;
+  if (D.dedup) {
+    __threadfence();  // the slot line must be visible before the slot can be found in the table
+    uint32_t h = (uint32_t)splitmix64(km * 0x9E3779B97F4A7C15ULL ^ splitmix64(kv ^ kmod)) & D.table_mask;
+    const unsigned long long mine = ((unsigned long long)epoch << 32) | slot;
+    for (;;) {
+      unsigned long long* e = D.table + h;
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(e);
+      if ((uint32_t)(cur >> 32) != epoch) {
+        unsigned long long prev = atomicCAS(e, cur, mine);
+        if (prev == cur) break;  // first game with this key in this tick: we lead
+        cur = prev;
+        if ((uint32_t)(cur >> 32) != epoch) continue;
+      }
+      const Slot* Ld = D.slots + (uint32_t)cur;
+      const uint64_t lm = __ldcg(&Ld->leaf_mask), lv = __ldcg(&Ld->leaf_value);
+      const uint64_t lmod = (c4::popc64(lm) & 1) ? __ldcg(&Ld->model1) : __ldcg(&Ld->model0);
+      if (lm == km && lv == kv && lmod == kmod) {
+        leader = (uint32_t)cur;
+        break;
+      }
+      h = (h + 1) & D.table_mask;  // another key lives here: linear probing
+    }
+  }
+  D.slots[slot].nn_leader = leader;
+  if (leader == slot) {
+    const uint32_t row = atomicAdd(&D.g->rows_acc, 1u);
+    D.rowtag[slot] = ((unsigned long long)epoch << 32) | row;
+    D.row_slot[row] = slot;
+    write_planes(D, row, Pos{km, kv});
   }
 }
 
@@ -279,7 +287,7 @@ struct Game {
   uint32_t slot, state;
   Pos root, leaf;
   uint64_t model0, model1;
-  uint32_t rootN, root_block, n_alloc, len, half, req, n_moves, nn_row;
+  uint32_t rootN, root_block, n_alloc, len, half, req, n_moves, nn_leader;
   float rootQp, rootQn;
   Block* arena;
   uint32_t* path;
@@ -323,7 +331,7 @@ __device__ __forceinline__ void load_game(const Dev& D, const Lanes& L, uint32_t
   G.half = S->half;
   G.req = S->req;
   G.n_moves = S->n_moves;
-  G.nn_row = S->nn_row;
+  G.nn_leader = S->nn_leader;
   G.c_sims = S->c_sims;
   G.c_exp = S->c_exp;
   G.c_term = S->c_term;
@@ -703,7 +711,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   const bool waiting = live && st == ST_WAIT_NN;
   bool running = live;
   if (__any_sync(FULL, waiting)) {
-    if (!apply_network(D, L, G, waiting, G.nn_row)) {
+    // the row holding this game's answer was drawn by the leader of its key during the last tick
+    const uint32_t row = waiting ? (uint32_t)D.rowtag[G.nn_leader] : 0u;
+    if (!apply_network(D, L, G, waiting, row)) {
       if (L.l == 0) D.g->error = C4A0_E_ENGINE;
       running = false;
     }
@@ -711,6 +721,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   const long long t2 = prof ? clock64() : 0;
   const uint32_t ns = run_games(D, L, G, running, st);
   const long long t3 = prof ? clock64() : 0;
+  const unsigned nwait = __popc(__ballot_sync(FULL, live && L.l == 0 && ns == ST_WAIT_NN));
+  if ((threadIdx.x & 31) == 0 && nwait) atomicAdd(&D.g->wait_acc, nwait);
   if (live && L.l == 0) {
     store_game(D, G, ns);
     if (ns == ST_NEED_MOVE) push_mover(D, slot);
@@ -732,7 +744,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
 
 // ------------------------------------------------------------------------------------------------
 // Compaction: one CTA per game whose arena half is full — copy the live subtree breadth-first into
-// the other half, then let the game carry on (phase 0 of k_post).
+// the other half, then let the game carry on (first part of k_tail).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void compact_movers(const Dev& D, uint32_t n_movers, uint32_t epoch) {
   __shared__ uint32_t sh_next, sh_head;
@@ -799,8 +811,10 @@ __device__ __forceinline__ void compact_movers(const Dev& D, uint32_t n_movers, 
       if (threadIdx.x == 0) {
         store_game(D, G, ns);
         // a second overflow is impossible right after a compaction, so ns != NEED_MOVE here
-        if (ns == ST_WAIT_NN)
+        if (ns == ST_WAIT_NN) {
+          atomicAdd(&D.g->wait_acc, 1u);
           publish_leaf(D, slot, G.leaf.mask, G.leaf.value, (c4::popc64(G.leaf.mask) & 1) ? G.model1 : G.model0, epoch);
+        }
       }
     }
     __syncthreads();
@@ -808,17 +822,18 @@ __device__ __forceinline__ void compact_movers(const Dev& D, uint32_t n_movers, 
 }
 
 // Seat the first min(n_slots, n_req) games (self_play.rs:55-58).
+__global__ void k_init_globals(Dev D, uint32_t n_req) {  // runs alone, before k_init
+  Globals z;
+  memset(&z, 0, sizeof(z));
+  z.tick = 1u;
+  z.n_req = n_req;
+  z.next_req = n_req < D.n_slots ? n_req : D.n_slots;
+  z.n_running = z.next_req;
+  *D.g = z;
+}
+
 __global__ void k_init(Dev D, uint32_t n_req) {
   uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot == 0) {
-    Globals z;
-    memset(&z, 0, sizeof(z));
-    z.tick = 1u;
-    z.n_req = n_req;
-    z.next_req = n_req < D.n_slots ? n_req : D.n_slots;
-    z.n_running = z.next_req;
-    *D.g = z;
-  }
   if (slot >= D.n_slots) return;
   Slot S;
   memset(&S, 0, sizeof(S));
@@ -830,109 +845,47 @@ __global__ void k_init(Dev D, uint32_t n_req) {
     S.model1 = D.p1[slot];
   }
   D.slots[slot] = S;
-  if (slot < n_req) publish_leaf(D, slot, 0ull, 0ull, S.model0, 1u);
+  if (slot < n_req) {
+    atomicAdd(&D.g->wait_acc, 1u);
+    publish_leaf(D, slot, 0ull, 0ull, S.model0, 1u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_post (cooperative): compact the arenas that filled up, then number the leaders of the waiting
-// leaves in slot order (decoupled look-back over CTAs), pack their planes densely, publish the
-// tick's status to the host, open the next tick.  Every leaf of this tick must be in the table
-// before leaders are read: those inserted by k_step / k_init are (kernel boundary); a grid-wide
-// barrier is needed only in ticks where the compaction phase ran and published leaves itself.
+// K_tail: compact the arenas that filled up (their games then carry on and publish their leaves),
+// and, in the last CTA to finish, close the tick: batch size, counters, status for the host.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(POST_THREADS, 4) k_post(Dev D) {  // <= 64 registers: 592 co-resident CTAs
-  cg::grid_group grid = cg::this_grid();
-  __shared__ uint32_t warp_cnt[POST_THREADS / 32];
-  __shared__ uint32_t warp_wait[POST_THREADS / 32];
-  __shared__ uint32_t sh_base;
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_CTAS = 32;
+
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail(Dev D) {
   const uint32_t epoch = D.g->tick;
   const uint32_t n_movers = D.g->n_movers;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (n_movers) {  // grid-uniform: leaves published by the compaction phase need the barrier
-    compact_movers(D, n_movers, epoch);
-    grid.sync();
-  }
-  Slot* S = D.slots + slot;
-  bool waiting = false;
-  uint64_t km = 0, kv = 0;
-  if (slot < D.n_slots && S->state == ST_WAIT_NN) {
-    waiting = true;
-    km = S->leaf_mask;
-    kv = S->leaf_value;
-  }
-  uint32_t leader = slot;
-  if (waiting && D.dedup) leader = (uint32_t)D.table[D.bucket[slot]];
-  const bool lead = waiting && leader == slot;
-  // CTA-level exclusive scan of `lead`
-  const unsigned bal = __ballot_sync(0xffffffffu, lead);
-  const unsigned balw = __ballot_sync(0xffffffffu, waiting);
-  if (lane == 0) {
-    warp_cnt[warp] = __popc(bal);
-    warp_wait[warp] = __popc(balw);
-  }
+  if (n_movers) compact_movers(D, n_movers, epoch);
   __syncthreads();
-  uint32_t before = 0, total = 0, wtotal = 0;
-#pragma unroll
-  for (int w = 0; w < POST_THREADS / 32; w++) {
-    before += (w < warp) ? warp_cnt[w] : 0u;
-    total += warp_cnt[w];
-    wtotal += warp_wait[w];
-  }
-  const uint32_t local = before + __popc(bal & ((1u << lane) - 1u));
-  // decoupled look-back over the CTAs before this one (all CTAs are co-resident)
   if (threadIdx.x == 0) {
-    sh_base = 0u;
-    *reinterpret_cast<volatile unsigned long long*>(D.cta_counts + blockIdx.x) = ((unsigned long long)epoch << 32) | total;
-    if (wtotal) atomicAdd(&D.g->leaves_total, (unsigned long long)wtotal);
-  }
-  __syncthreads();
-  uint32_t part = 0;
-  for (uint32_t j = threadIdx.x; j < blockIdx.x; j += blockDim.x) {
-    volatile unsigned long long* p = D.cta_counts + j;
-    unsigned long long v;
-    do {
-      v = *p;
-    } while ((uint32_t)(v >> 32) != epoch);
-    part += (uint32_t)v;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-  if (lane == 0 && part) atomicAdd(&sh_base, part);
-  __syncthreads();
-  const uint32_t base = sh_base;
-  uint32_t row = base + local;
-  if (lead) {
-    // followers (possibly in other CTAs) wait for this word: it carries the epoch
-    *reinterpret_cast<volatile unsigned long long*>(D.rowtag + slot) = ((unsigned long long)epoch << 32) | row;
-    D.row_slot[row] = slot;
-    write_planes(D, row, Pos{km, kv});
-  } else if (waiting) {
-    volatile unsigned long long* p = D.rowtag + leader;
-    unsigned long long v;
-    do {
-      v = *p;
-    } while ((uint32_t)(v >> 32) != epoch);
-    row = (uint32_t)v;
-  }
-  if (waiting) S->nn_row = row;
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-    // the last CTA knows the total; everybody has read `tick` and `n_movers` (before grid.sync)
     Globals* G = D.g;
-    const uint32_t rows = base + total;
     __threadfence();
-    G->n_rows = rows;
-    G->rows_total += rows;
-    HostStatus* hs = D.status;
-    hs->n_rows = rows;
-    hs->n_finished = G->n_finished;
-    hs->n_running = G->n_running;
-    hs->n_movers = n_movers;
-    hs->error = G->error;
-    __threadfence_system();
-    hs->tick = epoch;  // written last: the host spins on it
-    G->tick = epoch + 1u;  // open the next tick
-    G->n_movers = 0u;
+    const uint32_t ticket = atomicAdd(&G->tail_done, 1u);
+    if (ticket == gridDim.x - 1) {  // every CTA (and, by stream order, all of k_step) is done
+      __threadfence();
+      const uint32_t rows = atomicExch(&G->rows_acc, 0u);
+      const uint32_t waiting = atomicExch(&G->wait_acc, 0u);
+      G->n_rows = rows;
+      G->rows_total += rows;
+      G->leaves_total += waiting;
+      HostStatus* hs = D.status;
+      hs->n_rows = rows;
+      hs->n_finished = G->n_finished;
+      hs->n_running = G->n_running;
+      hs->n_movers = n_movers;
+      hs->error = G->error;
+      __threadfence_system();
+      hs->tick = epoch;      // written last: the host spins on it
+      G->tick = epoch + 1u;  // open the next tick
+      G->n_movers = 0u;
+      G->tail_done = 0u;
+    }
   }
 }
 
@@ -996,7 +949,6 @@ struct c4a0_engine {
   size_t bytes = 0;
   bool io_bound = false, have_requests = false;
   uint32_t n_req = 0;
-  uint32_t post_grid = 0;
   uint64_t steps = 0;
   unsigned long long* scratch4 = nullptr;
   uint64_t *row_mask = nullptr, *row_value = nullptr, *row_model = nullptr;
@@ -1030,19 +982,18 @@ int dalloc(c4a0_engine* e, T** p, size_t n) {
   } while (0)
 
 int launch_post(c4a0_engine* e, cudaStream_t s) {
-  Dev d = e->D;
-  void* args[] = {&d};
-  CK(cudaLaunchCooperativeKernel((void*)k_post, dim3(e->post_grid), dim3(POST_THREADS), args, 0, s));
+  k_tail<<<TAIL_CTAS, TAIL_THREADS, 0, s>>>(e->D);
+  CK(cudaGetLastError());
   return 0;
 }
 
-// Enqueue one tick.  `ev` (4 events) brackets k_step and k_post when given (ev[1] == ev[2]).
+// Enqueue one tick.  `ev` (4 events) brackets k_step and k_tail when given (ev[1] == ev[2]).
 int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
   const Dev& D = e->D;
   if (ev) CK(cudaEventRecord(ev[0], s));
   k_step<<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
   if (ev) CK(cudaEventRecord(ev[1], s));
-  if (ev) CK(cudaEventRecord(ev[2], s));  // (compaction is phase 0 of k_post)
+  if (ev) CK(cudaEventRecord(ev[2], s));  // (compaction is part of k_tail)
   int r = launch_post(e, s);
   if (r) return r;
   if (ev) CK(cudaEventRecord(ev[3], s));
@@ -1075,17 +1026,8 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   int r = c4host::no_gpu_error();
   if (r) return r;
   CK(cudaSetDevice(cfg->device));
-  // k_post is a cooperative kernel: its whole grid must be resident at once
-  int per_sm = 0, sms = 0, coop = 0;
-  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
-  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_post, POST_THREADS, 0));
-  uint32_t post_grid = blocks_for(cfg->n_slots, POST_THREADS);
-  if (!coop || (uint64_t)post_grid > (uint64_t)per_sm * sms)
-    return fail(C4A0_E_INVALID, "n_slots=%u needs %u co-resident CTAs, device allows %d", cfg->n_slots, post_grid, per_sm * sms);
   c4a0_engine* e = new c4a0_engine();
   e->cfg = *cfg;
-  e->post_grid = post_grid;
   Dev& D = e->D;
   memset(&D, 0, sizeof(D));
   D.n_slots = cfg->n_slots;
@@ -1104,7 +1046,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   D.table_mask = (uint32_t)(T - 1);
   DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S); DA(D.bucket, S); DA(D.rowtag, S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
-  DA(D.table, T); DA(D.cta_counts, post_grid);
+  DA(D.table, T);
   uint64_t *gid, *p0, *p1;
   DA(gid, R); DA(p0, R); DA(p1, R);
   D.game_id = gid; D.p0 = p0; D.p1 = p1;
@@ -1115,7 +1057,6 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   cudaError_t err = cudaMemset(D.slots, 0, S * sizeof(Slot));
   if (err == cudaSuccess) err = cudaMemset(D.g, 0, sizeof(Globals));
   if (err == cudaSuccess) err = cudaMemset(D.table, 0, T * sizeof(unsigned long long));
-  if (err == cudaSuccess) err = cudaMemset(D.cta_counts, 0, post_grid * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_globals, sizeof(Globals));
   if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_status, sizeof(HostStatus), cudaHostAllocMapped);
   if (err == cudaSuccess) {
@@ -1181,8 +1122,8 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
     CK(cudaMemsetAsync(D.s_qn, 0, (size_t)n * MAXS * 4, s));
   }
   CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
-  CK(cudaMemsetAsync(D.cta_counts, 0, e->post_grid * sizeof(unsigned long long), s));
   CK(cudaMemsetAsync(D.rowtag, 0, (size_t)D.n_slots * sizeof(unsigned long long), s));
+  k_init_globals<<<1, 1, 0, s>>>(D, n);
   k_init<<<blocks_for(D.n_slots, 256), 256, 0, s>>>(D, n);
   CK(cudaGetLastError());
   int r = launch_post(e, s);
@@ -1352,7 +1293,12 @@ int c4a0_engine_slot_info(c4a0_engine* e, uint32_t slot, c4a0_slot_info* out, vo
   out->root_q_sum_penalty = S.root_Qp;
   out->root_q_sum_no_penalty = S.root_Qn;
   out->n_blocks = S.n_alloc ? S.n_alloc - 1 : 0;
-  out->nn_row = S.nn_row;
+  unsigned long long tag = 0;
+  if (S.state == ST_WAIT_NN && S.nn_leader < e->D.n_slots) {
+    CK(cudaMemcpyAsync(&tag, e->D.rowtag + S.nn_leader, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  out->nn_row = (uint32_t)tag;
   return 0;
 }
 
@@ -1429,7 +1375,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     cudaEvent_t t0, t1;
   };
   std::vector<Lane> lanes(n_engines);
-  std::vector<cudaEvent_t> kev;  // five per sampled tick: before NN, before k_step, after k_step, k_move, k_post
+  std::vector<cudaEvent_t> kev;  // five per sampled tick: before NN, before k_step, after k_step, (same), after k_tail
   for (uint32_t i = 0; i < n_engines; i++) {
     c4a0_engine* e = engines[i];
     if (!e || !e->have_requests) return fail(C4A0_E_INVALID, "engine %u has no requests", i);

@@ -117,8 +117,9 @@ size_t c4a0_engine_device_bytes(const c4a0_engine *e);
  *   logits_dev : [n_slots][7] f32, q_penalty_dev / q_no_penalty_dev : [n_slots] f32
  *                                                                      <- pybridge.rs:175-196
  * Rows are dense: after set_requests()/step() rows [0, n_rows) hold the distinct leaf positions that
- * wait for an answer (n_rows <= n_slots, reported by poll()); the network must fill the same rows of
- * the three output buffers before the next step().  Rows >= n_rows are ignored. */
+ * wait for an answer (n_rows <= n_slots, reported by poll()), in no particular order; the network
+ * must fill the same rows of the three output buffers before the next step().  Rows >= n_rows are
+ * ignored. */
 int c4a0_engine_bind_io(c4a0_engine *e, void *planes_dev, const float *logits_dev,
                         const float *q_penalty_dev, const float *q_no_penalty_dev);
 
@@ -178,7 +179,7 @@ typedef struct {
   uint32_t kernel_samples;   /* ticks whose kernels were bracketed by events */
   double k_step_ms_sum;      /* summed device time of the apply+select kernel over those ticks */
   double k_move_ms_sum;      /* ... of the compaction kernel */
-  double k_post_ms_sum;      /* ... of the dedup / scan / pack kernel */
+  double k_post_ms_sum;      /* ... of the tail kernel (compaction + closing the tick) */
   double nn_ms_sum;          /* ... of the network graph that preceded them */
   uint64_t bucket_launches[32]; /* network launches per graph index (all engines) */
 } c4a0_run_report;
