@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
     ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
     ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")
+    ap.add_argument("--host-loop", choices=["native", "python"], default="native",
+                    help="python = eager network + per-tick polling (what ncu can follow; slower)")
     ap.add_argument("--plain-fold", action="store_true", help="GEMM-folded form without the epilogue-fused layout (FoldedNet)")
     return ap.parse_args()
 
@@ -255,6 +257,7 @@ def run_ours(args):
     model = make_model(args.width, torch.float32, device)
     selfplay.DEFAULTS["sample_kernels_every"] = args.sample_kernels_every
     selfplay.DEFAULTS["n_lanes"] = args.lanes
+    selfplay.DEFAULTS["host_loop"] = args.host_loop
     selfplay.DEFAULTS["dedup"] = not args.no_dedup
     selfplay.DEFAULTS["max_inline_sims"] = args.max_inline
     G = args.games

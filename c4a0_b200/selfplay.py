@@ -300,23 +300,24 @@ class SelfPlaySession:
             ev0.record(self.lanes[0].stream)
             ks, km, kn, ticks = 0.0, 0.0, 0, 0
             live = [hi > lo for lo, hi in ranges]
+            sizes = {id(ln): [b for b in BUCKETS if b < ln.n_slots] + [ln.n_slots] for ln in self.lanes}
+            rows = {id(ln): ln.engine.poll(ln.stream.cuda_stream).n_rows for ln in self.lanes}
             while any(live):
-                for _ in range(poll_every):
-                    for ln, alive in zip(self.lanes, live):
-                        if not alive:
-                            continue
-                        with torch.cuda.stream(ln.stream):
-                            ln.evaluate(evaluator, ln.n_slots)
-                            if sample_kernels_every and ticks % sample_kernels_every == 0:
-                                x, y = ln.engine.step_timed(ln.stream.cuda_stream)
-                                ks, km, kn = ks + x, km + y, kn + 1
-                            else:
-                                ln.engine.step(ln.stream.cuda_stream)
-                        ticks += 1
                 for i, ln in enumerate(self.lanes):
-                    if live[i]:
-                        p = ln.engine.poll(ln.stream.cuda_stream)
-                        live[i] = p.n_finished < p.n_requests
+                    if not live[i]:
+                        continue
+                    with torch.cuda.stream(ln.stream):
+                        # the smallest bucket covering the live rows, like the native loop
+                        ln.evaluate(evaluator, next(b for b in sizes[id(ln)] if b >= rows[id(ln)]))
+                        if sample_kernels_every and ticks % sample_kernels_every == 0:
+                            x, y = ln.engine.step_timed(ln.stream.cuda_stream)
+                            ks, km, kn = ks + x, km + y, kn + 1
+                        else:
+                            ln.engine.step(ln.stream.cuda_stream)
+                    ticks += 1
+                    p = ln.engine.poll(ln.stream.cuda_stream)
+                    rows[id(ln)] = p.n_rows
+                    live[i] = p.n_finished < p.n_requests
             for ln in self.lanes:
                 ln.stream.synchronize()
             ev1.record(self.lanes[0].stream)
