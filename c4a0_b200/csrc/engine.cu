@@ -390,10 +390,14 @@ __device__ __forceinline__ void backup(const Lanes& L, Game& G, bool pred, float
 }
 
 // mcts.rs:359-388: -(Qp/(N+1)) + c * (sqrt(ln(N_parent)/(N+1)) * (P + 1e-8)), f32, no contraction
+// The zero tests do not change any result (0/x = 0 keeps its sign, sqrt(+0) = +0): they keep the very
+// common zero numerators (unvisited children: Qp = 0; parents with one visit: ln 1 = 0) off the slow
+// path of the IEEE division / square root sequences.
+__device__ __forceinline__ float div_exact(float a, float b) { return a == 0.0f ? a : a / b; }  // b > 0
 __device__ __forceinline__ float uct(uint32_t n, float qs, float pr, float lnp, float c_expl) {
   float nf = (float)n + 1.0f;
-  float q = qs / nf;
-  float ex = sqrtf(lnp / nf);
+  float q = div_exact(qs, nf);
+  float ex = lnp == 0.0f ? 0.0f : sqrtf(lnp / nf);
   ex = ex * (pr + 1e-8f);
   return (-q) + (c_expl * ex);
 }
@@ -463,7 +467,7 @@ __device__ __forceinline__ bool apply_network(const Dev& D, const Lanes& L, Game
   const float mx = gmax8(x);
   const float e = ok ? c4::c4_expf(x - mx) : 0.0f;
   const float s = fold7(e);
-  const float p = ok ? e / s : 0.0f;
+  const float p = ok ? div_exact(e, s) : 0.0f;
   const uint32_t nb = G.n_alloc;
   const bool fits = nb < D.cap;
   if (pred && fits) {
@@ -524,7 +528,7 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
   // root_policy (mcts.rs:396-412): visit counts of the children, normalised
   const float cnt = (float)n_c;
   const float sum = fold7(cnt);
-  const float pol = (rb == 0u || sum == 0.0f) ? uniform : cnt / sum;
+  const float pol = (rb == 0u || sum == 0.0f) ? uniform : div_exact(cnt, sum);
   // apply_temperature (mcts.rs:439-454); T from self_play.rs:294-299
   const float T = c4::temperature_for_ply(c4::ply(G.root.mask));
   const float p0 = gshfl(pol, 0);
@@ -537,7 +541,7 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
   v = v > 1.0f ? 1.0f : v;
   const float pmx = gmax8(l < 7 ? pol : ninf);
   const float one = (l < 7 && pol == pmx) ? 1.0f : 0.0f;
-  const float v0 = one / fold7(one);
+  const float v0 = div_exact(one, fold7(one));
   float w = (T == 1.0f || alleq) ? pol : (T == 0.0f ? v0 : v);
   if (l == 7) w = 0.0f;
   // WeightedIndex::new(w) (cumulative left fold) and Uniform<f32>[0, total)
