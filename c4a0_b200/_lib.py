@@ -134,6 +134,7 @@ SIGNATURES = {
     "c4a0_engine_fetch_rows": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "c4a0_engine_run": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(RunReport)]),
     "c4a0_engine_fetch_results": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
+    "c4a0_engine_export_samples": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_int, _P, _P, _P, _P, _P]),
     "c4a0_engine_results_dev": (C.c_int, [_P] + [C.POINTER(_P)] * 6),
     "c4a0_engine_slot_info": (C.c_int, [_P, C.c_uint32, C.POINTER(SlotInfo), _P]),
     "c4a0_engine_dump_tree": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),

@@ -926,6 +926,41 @@ __global__ void k_gather_rows(Dev D, uint64_t* mask, uint64_t* value, uint64_t* 
   model[row] = leaf_model_of(*S);
 }
 
+// Training tensors straight from the sample store (what src/c4a0/training.py:317-333 builds with a
+// Python loop of Sample.to_numpy() and Sample.flip_h()): sample k of game g goes to row
+// offsets[g - first] + k; with `flip` its mirror image (c4r.rs:289-299, types.rs:115-122) goes to row
+// total + offsets[g - first] + k.  One thread per sample.
+__global__ void k_export(Dev D, uint32_t first, uint32_t n, const uint32_t* offsets, uint32_t total, int flip,
+                         float* pos, float* policy, float* qp, float* qn) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gi = t / MAXS, k = t % MAXS;
+  if (gi >= n) return;
+  const uint32_t g = first + gi;
+  if (k >= D.n_samples[g]) return;
+  const size_t si = (size_t)g * MAXS + k;
+  Pos p{D.s_mask[si], D.s_value[si]};
+  float pol[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) pol[i] = D.s_policy[si * 7 + i];
+  const float a = D.s_qp[si], b = D.s_qn[si];
+  for (int rep = 0; rep < (flip ? 2 : 1); rep++) {
+    const size_t row = (size_t)offsets[gi] + k + (rep ? total : 0u);
+    const Pos q = rep ? c4::flip_h(p) : p;
+    float4* dst = reinterpret_cast<float4*>(pos + row * 84);
+    const uint64_t mine = q.mask & q.value, theirs = q.mask & ~q.value;
+    const uint64_t lo = mine | (theirs << 42), hi = theirs >> 22;
+#pragma unroll
+    for (int v = 0; v < 21; v++) {
+      uint32_t bits = (uint32_t)((v < 16 ? lo >> (4 * v) : hi >> (4 * (v - 16))) & 0xfull);
+      dst[v] = make_float4((float)(bits & 1u), (float)((bits >> 1) & 1u), (float)((bits >> 2) & 1u), (float)((bits >> 3) & 1u));
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) policy[row * 7 + i] = rep ? pol[6 - i] : pol[i];
+    qp[row] = a;
+    qn[row] = b;
+  }
+}
+
 __global__ void k_sum_counters(Dev D, unsigned long long* out4) {
   unsigned long long a = 0, b = 0, c = 0, d = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.n_slots; i += gridDim.x * blockDim.x) {
@@ -1278,6 +1313,19 @@ int c4a0_engine_results_dev(c4a0_engine* e, uint32_t** n_samples, uint64_t** mas
   if (policy) *policy = e->D.s_policy;
   if (qp) *qp = e->D.s_qp;
   if (qn) *qn = e->D.s_qn;
+  return 0;
+}
+
+int c4a0_engine_export_samples(c4a0_engine* e, uint32_t first, uint32_t n, const uint32_t* offsets_dev,
+                               uint32_t total, int flip, float* pos_dev, float* policy_dev, float* qp_dev,
+                               float* qn_dev, void* stream) {
+  if (!e || !offsets_dev || !pos_dev || !policy_dev || !qp_dev || !qn_dev) return fail(C4A0_E_INVALID, "null argument");
+  if ((uint64_t)first + n > e->n_req) return fail(C4A0_E_INVALID, "sample range out of bounds");
+  if (((uintptr_t)pos_dev & 15u) != 0) return fail(C4A0_E_INVALID, "pos_dev must be 16-byte aligned");
+  if (n == 0) return 0;
+  k_export<<<blocks_for((size_t)n * MAXS, 256), 256, 0, (cudaStream_t)stream>>>(e->D, first, n, offsets_dev, total, flip,
+                                                                             pos_dev, policy_dev, qp_dev, qn_dev);
+  CK(cudaGetLastError());
   return 0;
 }
 

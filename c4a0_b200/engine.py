@@ -153,6 +153,12 @@ class Engine:
         L.check(self._lib.c4a0_engine_results_dev(self._h, *[C.byref(p) for p in ps]))
         return tuple(int(p.value) for p in ps)
 
+    def export_samples(self, first: int, n: int, offsets_ptr: int, total: int, flip: bool, pos_ptr: int,
+                       policy_ptr: int, qp_ptr: int, qn_ptr: int, stream: int = 0) -> None:
+        """Device-side training tensors; see c4a0_engine_export_samples in the header."""
+        L.check(self._lib.c4a0_engine_export_samples(self._h, first, n, offsets_ptr, total, int(flip), pos_ptr,
+                                                     policy_ptr, qp_ptr, qn_ptr, stream))
+
     def slot_info(self, slot: int, stream: int = 0) -> L.SlotInfo:
         info = L.SlotInfo()
         L.check(self._lib.c4a0_engine_slot_info(self._h, slot, C.byref(info), stream))

@@ -105,6 +105,18 @@ class RunInfo:
     n_lanes: int = 1
 
 
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can wrap engine-owned device memory."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _wrap_u32(ptr: int, n: int, device) -> torch.Tensor:
+    """The engine's uint32 array at `ptr` as an int32 tensor (no copy; counts are < 2^31)."""
+    return torch.as_tensor(_DevArray(ptr, n, "<i4"), device=device)
+
+
 def _sum_stats(stats: List[dict]) -> dict:
     out = {}
     for s in stats:
@@ -279,6 +291,7 @@ class SelfPlaySession:
         info = RunInfo(engine_bytes=sum(ln.engine.device_bytes for ln in self.lanes), n_lanes=len(self.lanes))
         t0 = time.perf_counter()
         ranges = self._split(n_req)
+        self._last_ranges = ranges
         for ln, (lo, hi) in zip(self.lanes, ranges):
             ln.engine.set_requests(gid[lo:hi], p0[lo:hi], p1[lo:hi], ln.stream.cuda_stream)
         if host_loop == "native":
@@ -339,6 +352,35 @@ class SelfPlaySession:
         info.wall_s = time.perf_counter() - t0
         return out, info
 
+    def export_tensors(self, augment: bool = True):
+        """All samples of the last play() as CUDA tensors (pos [S,2,6,7], policy [S,7], q_penalty [S],
+        q_no_penalty [S]) without leaving the device; augment=True appends the mirror images
+        (training.py:317-333 does both on the host, one Python object per sample)."""
+        outs = []
+        for ln, (lo, hi) in zip(self.lanes, self._last_ranges):
+            n = hi - lo
+            if n == 0:
+                continue
+            with torch.cuda.stream(ln.stream):
+                ptrs = ln.engine.results_dev()
+                # the sample counts live in the engine's store: wrap them without a copy
+                counts = _wrap_u32(ptrs[0], n, self.device).to(torch.int64)
+                offs = (torch.cumsum(counts, 0) - counts).to(torch.int32).contiguous()
+                total = int(counts.sum().item())
+                rows = total * (2 if augment else 1)
+                pos = torch.empty(rows, 2, 6, 7, dtype=torch.float32, device=self.device)
+                pol = torch.empty(rows, 7, dtype=torch.float32, device=self.device)
+                qp = torch.empty(rows, dtype=torch.float32, device=self.device)
+                qn = torch.empty(rows, dtype=torch.float32, device=self.device)
+                ln.engine.export_samples(0, n, offs.data_ptr(), total, augment, pos.data_ptr(), pol.data_ptr(),
+                                         qp.data_ptr(), qn.data_ptr(), ln.stream.cuda_stream)
+                ln.stream.synchronize()
+            outs.append((pos, pol, qp, qn))
+        if not outs:
+            z = torch.zeros(0, device=self.device)
+            return z.reshape(0, 2, 6, 7), z.reshape(0, 7), z, z
+        return tuple(torch.cat([o[i] for o in outs]) for i in range(4))
+
     # ------------------------------------------------------------------------------------------
     def play_callback(
         self,
@@ -359,6 +401,7 @@ class SelfPlaySession:
         ln = self.lanes[0]
         info = RunInfo(engine_bytes=ln.engine.device_bytes)
         n_req = len(game_id)
+        self._last_ranges = [(0, n_req)]
         t0 = time.perf_counter()
         S = ln.n_slots
         h_logits = torch.zeros(S, 7, dtype=torch.float32).pin_memory()

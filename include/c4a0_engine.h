@@ -204,6 +204,16 @@ int c4a0_engine_results_dev(c4a0_engine *e, uint32_t **n_samples_dev, uint64_t *
                             uint64_t **value_dev, float **policy_dev, float **q_penalty_dev,
                             float **q_no_penalty_dev);
 
+/* Training tensors on the device, no host round trip (replaces the per-sample Python loop of
+ * src/c4a0/training.py:317-333).  offsets_dev[i] = number of samples of games first..first+i-1 (an
+ * exclusive prefix sum of n_samples, computed by the caller), total = their sum.  Sample k of game
+ * first+i is written to row offsets_dev[i]+k of pos_dev [rows][2][6][7] f32, policy_dev [rows][7],
+ * q_penalty_dev / q_no_penalty_dev [rows]; with flip != 0 its horizontal mirror image (Sample::flip_h,
+ * types.rs:115-122) is written to row total+offsets_dev[i]+k as well, so rows = 2*total. */
+int c4a0_engine_export_samples(c4a0_engine *e, uint32_t first, uint32_t n, const uint32_t *offsets_dev,
+                               uint32_t total, int flip, float *pos_dev, float *policy_dev,
+                               float *q_penalty_dev, float *q_no_penalty_dev, void *stream);
+
 /* ---- introspection used by the parity tests -------------------------------------------- */
 typedef struct {
   uint32_t state, request, n_moves, root_visits;
