@@ -132,6 +132,7 @@ SIGNATURES = {
     "c4a0_engine_poll": (C.c_int, [_P, C.POINTER(Progress), _P]),
     "c4a0_engine_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
     "c4a0_engine_fetch_rows": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "c4a0_engine_rows_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "c4a0_engine_run": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(RunReport)]),
     "c4a0_engine_fetch_results": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "c4a0_engine_export_samples": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_int, _P, _P, _P, _P, _P]),

@@ -130,6 +130,7 @@ struct Dev {  // passed to kernels by value
   uint32_t* path;   // [n_slots][PATH_STRIDE]: (block << 3 | column) per level of the selected path
   Block* blocks;    // [n_slots][2][cap]
   uint32_t* row_slot;
+  uint64_t* row_model;  // [n_slots] model that has to evaluate the row (mcts.rs:70-76)
   uint32_t* bucket;  // [n_slots] hash-table entry of the slot's waiting leaf
   unsigned long long* rowtag;  // [n_slots] epoch << 32 | row, written by the slot that leads a key
   // per request
@@ -237,6 +238,7 @@ __device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64
     const uint32_t row = atomicAdd(&D.g->rows_acc, 1u);
     D.rowtag[slot] = ((unsigned long long)epoch << 32) | row;
     D.row_slot[row] = slot;
+    D.row_model[row] = kmod;
     write_planes(D, row, Pos{km, kv});
   }
 }
@@ -1083,7 +1085,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   size_t T = 1;
   while (T < 2 * S) T <<= 1;
   D.table_mask = (uint32_t)(T - 1);
-  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S); DA(D.bucket, S); DA(D.rowtag, S);
+  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S); DA(D.row_model, S); DA(D.bucket, S); DA(D.rowtag, S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
   DA(D.table, T);
   uint64_t *gid, *p0, *p1;
@@ -1326,6 +1328,13 @@ int c4a0_engine_export_samples(c4a0_engine* e, uint32_t first, uint32_t n, const
   k_export<<<blocks_for((size_t)n * MAXS, 256), 256, 0, (cudaStream_t)stream>>>(e->D, first, n, offsets_dev, total, flip,
                                                                              pos_dev, policy_dev, qp_dev, qn_dev);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int c4a0_engine_rows_dev(c4a0_engine* e, uint32_t** row_slot_dev, uint64_t** row_model_dev) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if (row_slot_dev) *row_slot_dev = e->D.row_slot;
+  if (row_model_dev) *row_model_dev = e->D.row_model;
   return 0;
 }
 

@@ -159,6 +159,12 @@ class Engine:
         L.check(self._lib.c4a0_engine_export_samples(self._h, first, n, offsets_ptr, total, int(flip), pos_ptr,
                                                      policy_ptr, qp_ptr, qn_ptr, stream))
 
+    def rows_dev(self) -> Tuple[int, int]:
+        """Device pointers (row_slot u32[n_slots], row_model u64[n_slots])."""
+        a, b = C.c_void_p(), C.c_void_p()
+        L.check(self._lib.c4a0_engine_rows_dev(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def slot_info(self, slot: int, stream: int = 0) -> L.SlotInfo:
         info = L.SlotInfo()
         L.check(self._lib.c4a0_engine_slot_info(self._h, slot, C.byref(info), stream))

@@ -93,6 +93,39 @@ class DeviceEvaluator:
         return self.fn(planes)
 
 
+class MultiModelEvaluator:
+    """Several networks in one batch (tournaments: `GameMetadata.player0_id != player1_id`,
+    src/c4a0/tournament.py:112-142).  The reference's NN thread serves one model per callback
+    (self_play.rs:211-220); here every model evaluates the tick's live rows and each row keeps the
+    answer of the model that has to move in it (`row_model`, mcts.rs:70-76).  All evaluators must
+    share dtype and plane layout."""
+
+    def __init__(self, evaluators):
+        self.evaluators = {int(k): v for k, v in evaluators.items()}
+        if not self.evaluators:
+            raise ValueError("no evaluators")
+        first = next(iter(self.evaluators.values()))
+        self.dtype, self.plane_stride, self.plane_offset = first.dtype, first.plane_stride, getattr(first, "plane_offset", 0)
+        for ev in self.evaluators.values():
+            if (ev.dtype, ev.plane_stride, getattr(ev, "plane_offset", 0)) != (self.dtype, self.plane_stride, self.plane_offset):
+                raise ValueError("all evaluators of a MultiModelEvaluator must share dtype and plane layout")
+
+    def __call__(self, planes: torch.Tensor, row_model: torch.Tensor):
+        """row_model: int64 view of the u64 model id per row."""
+        pol = a = b = None
+        for mid, ev in self.evaluators.items():
+            p, x, y = ev(planes)
+            key = mid if mid < (1 << 63) else mid - (1 << 64)
+            m = row_model == key
+            if pol is None:
+                pol, a, b = p.float().clone(), x.float().clone(), y.float().clone()
+            else:
+                pol = torch.where(m[:, None], p.float(), pol)
+                a = torch.where(m, x.float(), a)
+                b = torch.where(m, y.float(), b)
+        return pol, a, b
+
+
 @dataclass
 class RunInfo:
     ticks: int = 0
@@ -115,6 +148,11 @@ class _DevArray:
 def _wrap_u32(ptr: int, n: int, device) -> torch.Tensor:
     """The engine's uint32 array at `ptr` as an int32 tensor (no copy; counts are < 2^31)."""
     return torch.as_tensor(_DevArray(ptr, n, "<i4"), device=device)
+
+
+def _wrap_i64(ptr: int, n: int, device) -> torch.Tensor:
+    """The engine's uint64 array at `ptr` as an int64 tensor (no copy; same bit patterns)."""
+    return torch.as_tensor(_DevArray(ptr, n, "<i8"), device=device)
 
 
 def _sum_stats(stats: List[dict]) -> dict:
@@ -144,13 +182,17 @@ class _Lane:
         self.engine.bind_io(self.planes.data_ptr() + offset * self.planes.element_size(), self.logits.data_ptr(),
                             self.qp.data_ptr(), self.qn.data_ptr())
         self.stream = torch.cuda.Stream(device=device)
+        self.row_model = _wrap_i64(self.engine.rows_dev()[1], n_slots, device)  # engine-owned, no copy
         self.graphs = {}  # rows -> torch.cuda.CUDAGraph
         self.graph_key = None
         self.pool = None
 
     def evaluate(self, evaluator, rows: int) -> None:
         with torch.no_grad():
-            pol, a, b = evaluator(self.planes[:rows])
+            if isinstance(evaluator, MultiModelEvaluator):
+                pol, a, b = evaluator(self.planes[:rows], self.row_model[:rows])
+            else:
+                pol, a, b = evaluator(self.planes[:rows])
             self.logits[:rows].copy_(pol.reshape(rows, 7))
             self.qp[:rows].copy_(a.reshape(rows))
             self.qn[:rows].copy_(b.reshape(rows))

@@ -348,7 +348,7 @@ def play_games(
     """
     import torch
 
-    from c4a0_b200.selfplay import DeviceEvaluator, SelfPlaySession
+    from c4a0_b200.selfplay import DeviceEvaluator, MultiModelEvaluator, SelfPlaySession
 
     reqs = list(reqs)
     for r in reqs:
@@ -362,13 +362,19 @@ def play_games(
         return PlayGamesResult()
     meta = np.array([(r.game_id, r.player0_id, r.player1_id) for r in reqs], dtype=np.uint64)
     n_slots = min(len(reqs), int(max_nn_batch_size))
-    fast = isinstance(py_eval_pos_cb, (DeviceEvaluator, torch.nn.Module))
+    fast = isinstance(py_eval_pos_cb, (DeviceEvaluator, MultiModelEvaluator, torch.nn.Module))
     if fast:
         if isinstance(py_eval_pos_cb, torch.nn.Module):
             p = next(py_eval_pos_cb.parameters(), None)
             py_eval_pos_cb = DeviceEvaluator.from_model(py_eval_pos_cb, p.dtype if p is not None else torch.float32)
-        if len(np.unique(meta[:, 1:])) != 1:
-            raise ValueError("the device fast path plays one model against itself; use the numpy callback for tournaments")
+        ids = set(np.unique(meta[:, 1:]).tolist())
+        if isinstance(py_eval_pos_cb, MultiModelEvaluator):
+            missing = ids - set(py_eval_pos_cb.evaluators)
+            if missing:
+                raise ValueError(f"no evaluator for model ids {sorted(missing)}")
+        elif len(ids) != 1:
+            raise ValueError("one device evaluator plays one model against itself; pass a MultiModelEvaluator "
+                             "{model_id: evaluator} (or the numpy callback) for tournaments")
         sess = _session(
             n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
             py_eval_pos_cb.dtype, torch.cuda.current_device(), py_eval_pos_cb.plane_stride, None,

@@ -160,6 +160,11 @@ int c4a0_engine_stats(c4a0_engine *e, c4a0_stats *out, void *stream);
 int c4a0_engine_fetch_rows(c4a0_engine *e, uint32_t *n_rows, uint64_t *leaf_mask,
                            uint64_t *leaf_value, uint64_t *model_id, void *stream);
 
+/* Device views of the live rows, for evaluators that stay on the GPU: row_slot_dev[r] = the slot whose
+ * leaf is row r, row_model_dev[r] = the model id that has to evaluate it (tournaments play several
+ * models in one batch, rust/src/self_play.rs:203-220).  Valid for r < n_rows after every step(). */
+int c4a0_engine_rows_dev(c4a0_engine *e, uint32_t **row_slot_dev, uint64_t **row_model_dev);
+
 /* ---- the host loop ------------------------------------------------------------------------
  * A network evaluator as CUDA graphs: graph_exec (a cudaGraphExec_t) reads rows [0, rows) of the
  * engine's planes buffer and writes the same rows of its logits / q buffers.  Pass several sizes,

@@ -131,3 +131,38 @@ def test_training_loop_one_generation(tmp_path):
     with torch.no_grad():
         manual = float(T.loss_terms(child.eval(), *[torch.from_numpy(a) for a in val])[0])
     assert abs(manual - gen.val_loss) < 1e-4
+
+
+def test_multi_model_fast_path_equals_callback_path():
+    """Tournament request list (three models): the device fast path with a MultiModelEvaluator plays
+    the same games as the numpy-callback path serving the same three networks (N4)."""
+    import c4a0_rust as R
+    from c4a0_b200.selfplay import DeviceEvaluator, MultiModelEvaluator
+
+    nets = {}
+    for mid in (0, 5, 2**63 + 9):
+        g = torch.Generator().manual_seed(mid % 1000 + 1)
+        W = (torch.randn(84, generator=g) * 2).cuda()
+        V = torch.randn(84, generator=g).cuda()
+
+        def net(planes, W=W, V=V):
+            x = planes[:, :84].float()
+            q = torch.tanh((x * V).sum(1))
+            return (x * W).view(-1, 7, 12).sum(2), q, q * 0.25
+
+        nets[mid] = net
+    ids = list(nets)
+    reqs = [R.GameMetadata(100 + i, ids[i % 3], ids[(i + 1) % 3]) for i in range(90)]
+
+    def cb(model_id, pos):
+        with torch.no_grad():
+            pol, a, b = nets[model_id](torch.from_numpy(pos).cuda().reshape(len(pos), 84))
+        return pol.cpu().numpy(), a.cpu().numpy(), b.cpu().numpy()
+
+    slow = R.play_games(reqs, 64, 16, 3.0, 0.01, cb)
+    fast = R.play_games(reqs, 64, 16, 3.0, 0.01, MultiModelEvaluator({m: DeviceEvaluator(f, torch.float32, 96) for m, f in nets.items()}))
+    for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
+        assert np.array_equal(getattr(slow._soa, f), getattr(fast._soa, f)), f
+    assert {g.player0_score() for g in fast.results} <= {0.0, 0.5, 1.0}
+    with pytest.raises(ValueError):
+        R.play_games(reqs, 64, 16, 3.0, 0.01, MultiModelEvaluator({0: DeviceEvaluator(nets[0], torch.float32, 96)}))
