@@ -101,6 +101,7 @@ class RunReport(C.Structure):
         ("k_post_ms_sum", C.c_double),
         ("nn_ms_sum", C.c_double),
         ("bucket_launches", C.c_uint64 * 32),
+        ("tail_launches", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -103,6 +103,8 @@ struct Globals {  // one instance in device memory
   uint32_t rows_acc;    // row counter of the tick being built
   uint32_t wait_acc;    // games waiting for the network in the tick being built
   uint32_t tail_done;   // k_tail CTA ticket
+  uint32_t step_done;   // k_step CTA ticket
+  uint32_t tail_pending;  // k_step left compaction work (and the closing of the tick) to k_tail
   int32_t error;
   uint32_t pad;
   unsigned long long skipped_root_sims;
@@ -121,6 +123,7 @@ struct HostStatus {  // mapped pinned host memory, written by k_tail at the end 
   volatile uint32_t n_running;
   volatile uint32_t n_movers;
   volatile int32_t error;
+  volatile uint32_t need_tail;  // == epoch: k_step finished but many arenas need compaction, launch k_tail
 };
 
 struct Dev {  // passed to kernels by value
@@ -694,6 +697,90 @@ __device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
   D.movers[i] = slot;
 }
 
+constexpr uint32_t INLINE_COMPACTIONS = 4;  // up to this many, k_step's last CTA compacts by itself
+
+// ------------------------------------------------------------------------------------------------
+// Compaction: the CTA copies the live subtree of one game breadth-first into the other half of its
+// arena (level by level; a level's blocks are contiguous in the destination).  The game resumes in
+// the next tick (state CONTINUE).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void compact_one(const Dev& D, uint32_t slot) {
+  __shared__ uint32_t sh_next, sh_head;
+  Slot* S = D.slots + slot;
+  const uint32_t half = S->half;
+  const uint32_t src_root = S->root_block;
+  Block* src = arena_of(D, slot, half);
+  Block* dst = arena_of(D, slot, half ^ 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sh_head = 1u;
+    sh_next = src_root ? 2u : 1u;
+  }
+  if (src_root && threadIdx.x < 10)
+    reinterpret_cast<uint4*>(dst + 1)[threadIdx.x] = reinterpret_cast<const uint4*>(src + src_root)[threadIdx.x];
+  __syncthreads();
+  for (;;) {
+    const uint32_t head = sh_head, tail = sh_next;  // blocks [head, tail) form one tree level
+    __syncthreads();
+    if (head == tail) break;
+    if (tail > D.cap) {  // cannot happen for a well-formed tree; never run off the arena
+      if (threadIdx.x == 0) D.g->error = C4A0_E_ENGINE;
+      break;
+    }
+    const uint32_t nwork = (tail - head) * 8u;
+    for (uint32_t w = threadIdx.x; w < nwork; w += blockDim.x) {
+      uint32_t b = head + (w >> 3), c = w & 7u;
+      if (c == 7u) continue;
+      uint32_t s = dst[b].child[c];  // still an index into src
+      if (s) {
+        uint32_t j = atomicAdd(&sh_next, 1u);
+        const uint4* from = reinterpret_cast<const uint4*>(src + s);
+        uint4* to = reinterpret_cast<uint4*>(dst + j);
+#pragma unroll
+        for (int q = 0; q < 10; q++) to[q] = from[q];
+        dst[b].child[c] = j;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sh_head = tail;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // the live subtree holds at most N_root blocks, so the fresh half has room until the next move
+    S->root_block = src_root ? 1u : 0u;
+    S->half = half ^ 1u;
+    S->n_alloc = sh_next;
+    S->path_len = 0u;
+    S->state = ST_CONTINUE;
+    atomicAdd(&D.g->compacted_blocks, (unsigned long long)(sh_next - 1u));
+    atomicAdd(&D.g->compactions, 1ull);
+  }
+  __syncthreads();
+}
+
+// Close the tick (one thread, after every game of the tick is done): batch size, counters, status
+// for the host, next epoch.
+__device__ __forceinline__ void close_tick(const Dev& D, uint32_t epoch, uint32_t n_movers) {
+  Globals* G = D.g;
+  __threadfence();
+  const uint32_t rows = atomicExch(&G->rows_acc, 0u);
+  const uint32_t waiting = atomicExch(&G->wait_acc, 0u);
+  G->n_rows = rows;
+  G->rows_total += rows;
+  G->leaves_total += waiting;
+  HostStatus* hs = D.status;
+  hs->n_rows = rows;
+  hs->n_finished = G->n_finished;
+  hs->n_running = G->n_running;
+  hs->n_movers = n_movers;
+  hs->error = G->error;
+  __threadfence_system();
+  hs->tick = epoch;      // written last: the host spins on it
+  G->tick = epoch + 1u;  // open the next tick
+  G->n_movers = 0u;
+  G->tail_pending = 0u;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K_step: the tick of every game.
 // ------------------------------------------------------------------------------------------------
@@ -712,7 +799,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   const uint32_t st = G.state;
   if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction after a compaction (cannot happen, kept for safety)
   const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
-  if (!__any_sync(FULL, live)) return;
+  const uint32_t epoch = D.g->tick;
+  if (__any_sync(FULL, live)) {  // (no early return: every warp takes part in closing the tick below)
   const long long t1 = prof ? clock64() : 0;
   const bool waiting = live && st == ST_WAIT_NN;
   bool running = live;
@@ -733,7 +821,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     store_game(D, G, ns);
     if (ns == ST_NEED_MOVE) push_mover(D, slot);
     if (ns == ST_WAIT_NN)
-      publish_leaf(D, slot, G.leaf.mask, G.leaf.value, (c4::popc64(G.leaf.mask) & 1) ? G.model1 : G.model0, D.g->tick);
+      publish_leaf(D, slot, G.leaf.mask, G.leaf.value, (c4::popc64(G.leaf.mask) & 1) ? G.model1 : G.model0, epoch);
     if (prof) {  // cycles of this game's warp per phase (c4a0_engine_debug_phases)
       uint32_t* o = D.dbg + (size_t)slot * 8;
       o[0] = (uint32_t)(t1 - t0);         // load slot state
@@ -746,84 +834,27 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
       o[7] = (uint32_t)(clock64() - t0);  // whole tick
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Compaction: one CTA per game whose arena half is full — copy the live subtree breadth-first into
-// the other half, then let the game carry on (first part of k_tail).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void compact_movers(const Dev& D, uint32_t n_movers, uint32_t epoch) {
-  __shared__ uint32_t sh_next, sh_head;
-  for (uint32_t m = blockIdx.x; m < n_movers; m += gridDim.x) {
-    const uint32_t slot = D.movers[m];
-    Slot* S = D.slots + slot;
-    const uint32_t half = S->half;
-    const uint32_t src_root = S->root_block;
-    Block* src = arena_of(D, slot, half);
-    Block* dst = arena_of(D, slot, half ^ 1u);
-    if (threadIdx.x == 0) {
-      sh_head = 1u;
-      sh_next = src_root ? 2u : 1u;
+  }
+  // ---- the last CTA to finish closes the tick (or hands it to k_tail) ---------------------------
+  __shared__ uint32_t sh_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    sh_last = atomicAdd(&D.g->step_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (sh_last) {
+    __threadfence();
+    const uint32_t n_movers = *reinterpret_cast<volatile uint32_t*>(&D.g->n_movers);
+    if (threadIdx.x == 0) D.g->step_done = 0u;
+    if (n_movers <= INLINE_COMPACTIONS) {
+      for (uint32_t m = 0; m < n_movers; m++) compact_one(D, *reinterpret_cast<volatile uint32_t*>(D.movers + m));
+      if (threadIdx.x == 0) close_tick(D, epoch, n_movers);
+    } else if (threadIdx.x == 0) {  // a burst of compactions: one CTA per arena in k_tail
+      D.g->tail_pending = 1u;
+      __threadfence_system();
+      D.status->need_tail = epoch;
     }
-    if (src_root && threadIdx.x < 10)
-      reinterpret_cast<uint4*>(dst + 1)[threadIdx.x] = reinterpret_cast<const uint4*>(src + src_root)[threadIdx.x];
-    __syncthreads();
-    for (;;) {
-      const uint32_t head = sh_head, tail = sh_next;  // blocks [head, tail) form one tree level
-      __syncthreads();
-      if (head == tail) break;
-      if (tail > D.cap) {  // cannot happen for a well-formed tree; never run off the arena
-        if (threadIdx.x == 0) D.g->error = C4A0_E_ENGINE;
-        break;
-      }
-      const uint32_t nwork = (tail - head) * 8u;
-      for (uint32_t w = threadIdx.x; w < nwork; w += blockDim.x) {
-        uint32_t b = head + (w >> 3), c = w & 7u;
-        if (c == 7u) continue;
-        uint32_t s = dst[b].child[c];  // still an index into src
-        if (s) {
-          uint32_t j = atomicAdd(&sh_next, 1u);
-          const uint4* from = reinterpret_cast<const uint4*>(src + s);
-          uint4* to = reinterpret_cast<uint4*>(dst + j);
-#pragma unroll
-          for (int q = 0; q < 10; q++) to[q] = from[q];
-          dst[b].child[c] = j;
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) sh_head = tail;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      S->root_block = src_root ? 1u : 0u;
-      S->half = half ^ 1u;
-      S->n_alloc = sh_next;
-      S->path_len = 0u;
-      atomicAdd(&D.g->compacted_blocks, (unsigned long long)(sh_next - 1u));
-      atomicAdd(&D.g->compactions, 1ull);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {  // warp 0; its first 8 lanes carry the game on
-      // the live subtree holds at most N_root blocks, so the fresh half always has room again
-      const Lanes L = make_lanes();
-      const bool live = threadIdx.x < 8;
-      Game G;
-      if (live) {
-        load_game(D, L, slot, G);
-      } else {
-        memset(&G, 0, sizeof(G));
-      }
-      const uint32_t ns = run_games(D, L, G, live, ST_CONTINUE);
-      if (threadIdx.x == 0) {
-        store_game(D, G, ns);
-        // a second overflow is impossible right after a compaction, so ns != NEED_MOVE here
-        if (ns == ST_WAIT_NN) {
-          atomicAdd(&D.g->wait_acc, 1u);
-          publish_leaf(D, slot, G.leaf.mask, G.leaf.value, (c4::popc64(G.leaf.mask) & 1) ? G.model1 : G.model0, epoch);
-        }
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -835,6 +866,7 @@ __global__ void k_init_globals(Dev D, uint32_t n_req) {  // runs alone, before k
   z.n_req = n_req;
   z.next_req = n_req < D.n_slots ? n_req : D.n_slots;
   z.n_running = z.next_req;
+  z.tail_pending = 1u;  // k_tail closes the seating 'tick'
   *D.g = z;
 }
 
@@ -858,40 +890,27 @@ __global__ void k_init(Dev D, uint32_t n_req) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_tail: compact the arenas that filled up (their games then carry on and publish their leaves),
-// and, in the last CTA to finish, close the tick: batch size, counters, status for the host.
+// K_tail: only does something when k_step left the tick open (many arenas filled up at once, or
+// right after k_init): one CTA per arena to compact, the last CTA to finish closes the tick.
 // ------------------------------------------------------------------------------------------------
 constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_CTAS = 32;
+constexpr int TAIL_CTAS = 148;
 
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(Dev D) {
+  __shared__ uint32_t sh_last;
+  if (*reinterpret_cast<volatile uint32_t*>(&D.g->tail_pending) == 0u) return;  // grid-uniform
   const uint32_t epoch = D.g->tick;
   const uint32_t n_movers = D.g->n_movers;
-  if (n_movers) compact_movers(D, n_movers, epoch);
+  for (uint32_t m = blockIdx.x; m < n_movers; m += gridDim.x) compact_one(D, D.movers[m]);
   __syncthreads();
   if (threadIdx.x == 0) {
-    Globals* G = D.g;
     __threadfence();
-    const uint32_t ticket = atomicAdd(&G->tail_done, 1u);
-    if (ticket == gridDim.x - 1) {  // every CTA (and, by stream order, all of k_step) is done
-      __threadfence();
-      const uint32_t rows = atomicExch(&G->rows_acc, 0u);
-      const uint32_t waiting = atomicExch(&G->wait_acc, 0u);
-      G->n_rows = rows;
-      G->rows_total += rows;
-      G->leaves_total += waiting;
-      HostStatus* hs = D.status;
-      hs->n_rows = rows;
-      hs->n_finished = G->n_finished;
-      hs->n_running = G->n_running;
-      hs->n_movers = n_movers;
-      hs->error = G->error;
-      __threadfence_system();
-      hs->tick = epoch;      // written last: the host spins on it
-      G->tick = epoch + 1u;  // open the next tick
-      G->n_movers = 0u;
-      G->tail_done = 0u;
-    }
+    sh_last = atomicAdd(&D.g->tail_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (sh_last && threadIdx.x == 0) {  // every CTA (and, by stream order, all of k_step) is done
+    D.g->tail_done = 0u;
+    close_tick(D, epoch, n_movers);
   }
 }
 
@@ -1028,15 +1047,20 @@ int launch_post(c4a0_engine* e, cudaStream_t s) {
   return 0;
 }
 
-// Enqueue one tick.  `ev` (4 events) brackets k_step and k_tail when given (ev[1] == ev[2]).
-int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev) {
+// Enqueue one tick.  `ev` (4 events) brackets k_step and k_tail when given (ev[1] == ev[2]).  k_step
+// closes the tick by itself unless a burst of arenas needs compaction; with_tail enqueues k_tail
+// unconditionally (it returns at once when there is nothing to do) so that callers that cannot look
+// at the status word in between (engine_step(), CUDA-graph capture) always get a closed tick.
+int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev, bool with_tail) {
   const Dev& D = e->D;
   if (ev) CK(cudaEventRecord(ev[0], s));
   k_step<<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
   if (ev) CK(cudaEventRecord(ev[1], s));
-  if (ev) CK(cudaEventRecord(ev[2], s));  // (compaction is part of k_tail)
-  int r = launch_post(e, s);
-  if (r) return r;
+  if (ev) CK(cudaEventRecord(ev[2], s));
+  if (with_tail) {
+    int r = launch_post(e, s);
+    if (r) return r;
+  }
   if (ev) CK(cudaEventRecord(ev[3], s));
   CK(cudaGetLastError());
   e->steps++;
@@ -1179,7 +1203,7 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
 int c4a0_engine_step(c4a0_engine* e, void* stream) {
   if (!e) return fail(C4A0_E_INVALID, "null engine");
   if (!e->have_requests) return fail(C4A0_E_INVALID, "set_requests() must precede step()");
-  return launch_tick(e, (cudaStream_t)stream, nullptr);
+  return launch_tick(e, (cudaStream_t)stream, nullptr, true);
 }
 
 int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* ms_move) {
@@ -1188,7 +1212,7 @@ int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* 
   cudaStream_t s = (cudaStream_t)stream;
   if (!e->ev[0])
     for (int i = 0; i < 4; i++) CK(cudaEventCreate(&e->ev[i]));
-  int r = launch_tick(e, s, e->ev);
+  int r = launch_tick(e, s, e->ev, true);
   if (r) return r;
   CK(cudaStreamSynchronize(s));
   float a = 0, b = 0;
@@ -1208,7 +1232,7 @@ int c4a0_engine_debug_phases(c4a0_engine* e, void* stream, uint32_t* out8_per_sl
   CK(cudaMalloc((void**)&d, n * 4));
   CK(cudaMemsetAsync(d, 0, n * 4, s));
   e->D.dbg = d;
-  int r = launch_tick(e, s, nullptr);
+  int r = launch_tick(e, s, nullptr, true);
   e->D.dbg = nullptr;
   if (!r) {
     cudaError_t err = cudaMemcpyAsync(out8_per_slot, d, n * 4, cudaMemcpyDeviceToHost, s);
@@ -1483,7 +1507,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     out->nn_launches++;
     out->bucket_launches[k < 31 ? k : 31]++;
     out->nn_rows_launched += g[k].rows;
-    int r = launch_tick(L.e, L.s, ev ? ev + 1 : nullptr);
+    int r = launch_tick(L.e, L.s, ev ? ev + 1 : nullptr, false);
     if (r) return r;
     L.expect++;
     out->ticks++;
@@ -1503,7 +1527,19 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     if (!L.done) {
       // wait for the tick's status (k_scan wrote it through mapped memory)
       uint64_t spins = 0;
+      bool tail_launched = false;
       while (L.e->h_status->tick != L.expect) {
+        if (!tail_launched && L.e->h_status->need_tail == L.expect) {
+          // k_step left the tick open: a burst of arenas to compact -> one CTA per arena
+          std::atomic_thread_fence(std::memory_order_acquire);
+          if (launch_post(L.e, L.s)) {
+            rc = C4A0_E_CUDA;
+            break;
+          }
+          tail_launched = true;
+          out->tail_launches++;
+          continue;
+        }
         if (++spins > 2000) {
           if (cudaStreamQuery(L.s) == cudaSuccess && L.e->h_status->tick != L.expect) {
             rc = fail(C4A0_E_CUDA, "tick status never arrived (stream idle)");

@@ -184,9 +184,10 @@ typedef struct {
   uint32_t kernel_samples;   /* ticks whose kernels were bracketed by events */
   double k_step_ms_sum;      /* summed device time of the apply+select kernel over those ticks */
   double k_move_ms_sum;      /* ... of the compaction kernel */
-  double k_post_ms_sum;      /* ... of the tail kernel (compaction + closing the tick) */
+  double k_post_ms_sum;      /* ... of the tail kernel where it was enqueued with the tick (engine_step) */
   double nn_ms_sum;          /* ... of the network graph that preceded them */
   uint64_t bucket_launches[32]; /* network launches per graph index (all engines) */
+  uint64_t tail_launches;    /* ticks that needed the separate compaction kernel */
 } c4a0_run_report;
 
 /* Plays every engine's requests to completion: what self_play() does between spawning its threads
