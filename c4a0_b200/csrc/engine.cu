@@ -1528,6 +1528,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
       // wait for the tick's status (k_scan wrote it through mapped memory)
       uint64_t spins = 0;
       bool tail_launched = false;
+      const auto wait0 = std::chrono::steady_clock::now();
       while (L.e->h_status->tick != L.expect) {
         if (!tail_launched && L.e->h_status->need_tail == L.expect) {
           // k_step left the tick open: a burst of arenas to compact -> one CTA per arena
@@ -1541,8 +1542,20 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
           continue;
         }
         if (++spins > 2000) {
-          if (cudaStreamQuery(L.s) == cudaSuccess && L.e->h_status->tick != L.expect) {
-            rc = fail(C4A0_E_CUDA, "tick status never arrived (stream idle)");
+          // never spin forever: a faulted kernel, an idle stream or a stalled device ends the run
+          cudaError_t q = cudaStreamQuery(L.s);
+          if (q == cudaSuccess) {
+            if (L.e->h_status->tick != L.expect && L.e->h_status->need_tail != L.expect) {
+              rc = fail(C4A0_E_CUDA, "tick status never arrived (stream idle)");
+              break;
+            }
+          } else if (q != cudaErrorNotReady) {
+            rc = fail(C4A0_E_CUDA, "stream failed while waiting for the tick: %s", cudaGetErrorString(q));
+            break;
+          }
+          if ((spins & 0xfff) == 0 &&
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - wait0).count() > 60.0) {
+            rc = fail(C4A0_E_CUDA, "no tick status for 60 s");
             break;
           }
           std::this_thread::yield();
