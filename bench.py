@@ -330,7 +330,7 @@ def run_ours(args):
     sims_per_launch = sims / max(1, ticks)
     peak, peak_src = measured_peak_gbs()
     roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "peak_source": peak_src, "kernel": "k_step (apply network outputs + backup + UCT select + plane pack)"}
+                "peak_source": peak_src, "kernel": "k_step (network answer -> softmax/expand/backup, move, UCT select, dedup + plane pack, tick close)"}
     if kms:
         k_step_ms = float(np.mean([k["k_step"] for k in kms]))
         k_move_ms = float(np.mean([k["k_move"] for k in kms]))
@@ -361,7 +361,9 @@ def run_ours(args):
             "sims_per_s": sims_all / e2e_s_max, "api": "c4a0_rust.play_games(list[GameMetadata], ...) -> PlayGamesResult",
             "wall_ms_per_step": 1e3 * wall_max / max(1, args.steps),
         },
-        "gpu_launches": int(5 * ticks + 4 * args.steps * args.lanes),
+        # our kernels inside the timed region: k_step once per tick, k_tail where a tick needed it,
+        # k_init_globals + k_init + k_tail per call, k_sum_counters per call
+        "gpu_launches": int(ticks + sum(r[1].report.get("tail_launches", 0) for r in runs) + 4 * args.steps * args.lanes),
         "leaf_evals_per_s": expansions_all / dev_s_max,
         "dedup": {"enabled": not args.no_dedup, "leaf_requests": expansions_all, "unique_rows": evals_all,
                   "rows_launched_incl_bucket_padding": rows_launched_all},
