@@ -102,6 +102,8 @@ class RunReport(C.Structure):
         ("nn_ms_sum", C.c_double),
         ("bucket_launches", C.c_uint64 * 32),
         ("tail_launches", C.c_uint64),
+        ("host_wait_ms", C.c_double),
+        ("host_launch_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:

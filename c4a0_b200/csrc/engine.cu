@@ -1529,6 +1529,13 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
       uint64_t spins = 0;
       bool tail_launched = false;
       const auto wait0 = std::chrono::steady_clock::now();
+      struct WaitTimer {
+        std::chrono::steady_clock::time_point t0;
+        double* acc;
+        ~WaitTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+      };
+      {
+      WaitTimer wt{wait0, &out->host_wait_ms};
       while (L.e->h_status->tick != L.expect) {
         if (!tail_launched && L.e->h_status->need_tail == L.expect) {
           // k_step left the tick open: a burst of arenas to compact -> one CTA per arena
@@ -1561,6 +1568,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
           std::this_thread::yield();
         }
       }
+      }
       if (rc) break;
       std::atomic_thread_fence(std::memory_order_acquire);
       if (L.e->h_status->error) {
@@ -1575,7 +1583,9 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
         rc = fail(C4A0_E_INVALID, "max_ticks reached before all games finished");
         break;
       } else {
+        const auto l0 = std::chrono::steady_clock::now();
         rc = launch_round(cur);
+        out->host_launch_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - l0).count();
       }
     }
     cur = (cur + 1) % n_engines;

@@ -188,6 +188,8 @@ typedef struct {
   double nn_ms_sum;          /* ... of the network graph that preceded them */
   uint64_t bucket_launches[32]; /* network launches per graph index (all engines) */
   uint64_t tail_launches;    /* ticks that needed the separate compaction kernel */
+  double host_wait_ms;       /* host time spent waiting for tick status (the GPU is busy) */
+  double host_launch_ms;     /* host time spent enqueuing network graphs and tick kernels */
 } c4a0_run_report;
 
 /* Plays every engine's requests to completion: what self_play() does between spawning its threads
