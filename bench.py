@@ -377,7 +377,8 @@ def run_ours(args):
         },
         "host_loop": {"wait_ms_per_step": sum(r[1].report.get("host_wait_ms", 0.0) for r in runs) / max(1, args.steps),
                       "launch_ms_per_step": sum(r[1].report.get("host_launch_ms", 0.0) for r in runs) / max(1, args.steps),
-                      "tail_launches_per_step": sum(r[1].report.get("tail_launches", 0) for r in runs) / max(1, args.steps)},
+                      "tail_launches_per_step": sum(r[1].report.get("tail_launches", 0) for r in runs) / max(1, args.steps),
+                      "nn_relaunches_per_step": sum(r[1].report.get("nn_relaunches", 0) for r in runs) / max(1, args.steps)},
         "clocks": clk,
         "bucket_launches": [int(sum(r[1].report.get("bucket_launches", [0] * 32)[i] for r in runs)) for i in range(20)],
         "ticks_per_step": ticks / max(1, args.steps),

@@ -104,6 +104,7 @@ class RunReport(C.Structure):
         ("tail_launches", C.c_uint64),
         ("host_wait_ms", C.c_double),
         ("host_launch_ms", C.c_double),
+        ("nn_relaunches", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

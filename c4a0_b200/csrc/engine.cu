@@ -1455,12 +1455,13 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   struct Lane {
     c4a0_engine* e;
     cudaStream_t s;
-    uint32_t expect;   // status tick the host waits for next
+    uint32_t expect;     // status tick the host waits for next
+    uint32_t spec_rows;  // rows covered by the network graph already enqueued behind that tick
     bool done;
     cudaEvent_t t0, t1;
   };
   std::vector<Lane> lanes(n_engines);
-  std::vector<cudaEvent_t> kev;  // five per sampled tick: before NN, before k_step, after k_step, (same), after k_tail
+  std::vector<cudaEvent_t> kev;  // three per sampled tick: before k_step, after k_step, after the network
   for (uint32_t i = 0; i < n_engines; i++) {
     c4a0_engine* e = engines[i];
     if (!e || !e->have_requests) return fail(C4A0_E_INVALID, "engine %u has no requests", i);
@@ -1471,7 +1472,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     }
     if (graphs[i][n_graphs[i] - 1].rows < e->D.n_slots)
       return fail(C4A0_E_INVALID, "the largest network graph must cover n_slots rows");
-    lanes[i] = Lane{e, (cudaStream_t)streams[i], e->h_status->tick, e->n_req == 0, nullptr, nullptr};
+    lanes[i] = Lane{e, (cudaStream_t)streams[i], e->h_status->tick, 0u, e->n_req == 0, nullptr, nullptr};
     CK(cudaEventCreate(&lanes[i].t0));
     CK(cudaEventCreate(&lanes[i].t1));
   }
@@ -1484,22 +1485,9 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   };
   auto wall0 = std::chrono::steady_clock::now();
   int rc = 0;
-  // prime: the planes of the initial roots are already packed (set_requests) -> first network call
-  // one tick of engine i: the network on the rows packed by the previous tick, then the tree kernels
-  auto launch_round = [&](uint32_t i) -> int {
+  // the network on rows [0, >= rows): the smallest captured graph that covers them
+  auto launch_nn = [&](uint32_t i, uint32_t rows, uint32_t* covered) -> int {
     Lane& L = lanes[i];
-    cudaEvent_t* ev = nullptr;
-    if (time_kernels_every && (L.e->steps % time_kernels_every) == 0 && kev.size() < 5 * 4096) {
-      size_t b = kev.size();
-      for (int q = 0; q < 5; q++) {
-        cudaEvent_t x;
-        CK(cudaEventCreate(&x));
-        kev.push_back(x);
-      }
-      ev = &kev[b];
-      CK(cudaEventRecord(ev[0], L.s));
-    }
-    uint32_t rows = L.e->h_status->n_rows;
     const c4a0_nn_graph* g = graphs[i];
     uint32_t k = 0;
     while (k + 1 < n_graphs[i] && g[k].rows < rows) k++;
@@ -1507,8 +1495,35 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     out->nn_launches++;
     out->bucket_launches[k < 31 ? k : 31]++;
     out->nn_rows_launched += g[k].rows;
-    int r = launch_tick(L.e, L.s, ev ? ev + 1 : nullptr, false);
+    if (covered) *covered = g[k].rows;
+    return 0;
+  };
+  // One round for engine i whose last closed tick packed `rows` rows (and whose network answers for
+  // them are in flight or done): the next tick, then — without waiting for that tick's row count —
+  // the network for it, sized from the current count plus a margin.  The host round trip (status
+  // over PCIe, cudaGraphLaunch) then overlaps the network instead of idling the GPU; if the tick
+  // turns out to need more rows than guessed, the network is simply run again at the right size.
+  auto launch_round = [&](uint32_t i, uint32_t rows) -> int {
+    Lane& L = lanes[i];
+    cudaEvent_t* ev = nullptr;
+    if (time_kernels_every && (L.e->steps % time_kernels_every) == 0 && kev.size() < 3 * 4096) {
+      size_t b = kev.size();
+      for (int q = 0; q < 3; q++) {
+        cudaEvent_t x;
+        CK(cudaEventCreate(&x));
+        kev.push_back(x);
+      }
+      ev = &kev[b];
+      CK(cudaEventRecord(ev[0], L.s));
+    }
+    int r = launch_tick(L.e, L.s, nullptr, false);
     if (r) return r;
+    if (ev) CK(cudaEventRecord(ev[1], L.s));
+    const uint32_t margin = rows / 16 > 32 ? rows / 16 : 32;
+    const uint32_t guess = rows + margin < L.e->D.n_slots ? rows + margin : L.e->D.n_slots;
+    r = launch_nn(i, guess, &L.spec_rows);
+    if (r) return r;
+    if (ev) CK(cudaEventRecord(ev[2], L.s));
     L.expect++;
     out->ticks++;
     return 0;
@@ -1517,7 +1532,9 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     Lane& L = lanes[i];
     CK(cudaEventRecord(L.t0, L.s));
     if (L.done) continue;
-    rc = launch_round(i);
+    // the planes of the initial roots are already packed (set_requests): their network first
+    rc = launch_nn(i, L.e->h_status->n_rows, nullptr);
+    if (!rc) rc = launch_round(i, L.e->h_status->n_rows);
   }
   uint32_t remaining = 0;
   for (auto& L : lanes) remaining += L.done ? 0 : 1;
@@ -1525,20 +1542,14 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   while (remaining && !rc) {
     Lane& L = lanes[cur];
     if (!L.done) {
-      // wait for the tick's status (k_scan wrote it through mapped memory)
+      // wait for the tick's status (written through mapped memory when the tick closes)
       uint64_t spins = 0;
       bool tail_launched = false;
       const auto wait0 = std::chrono::steady_clock::now();
-      struct WaitTimer {
-        std::chrono::steady_clock::time_point t0;
-        double* acc;
-        ~WaitTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
-      };
-      {
-      WaitTimer wt{wait0, &out->host_wait_ms};
       while (L.e->h_status->tick != L.expect) {
         if (!tail_launched && L.e->h_status->need_tail == L.expect) {
-          // k_step left the tick open: a burst of arenas to compact -> one CTA per arena
+          // k_step left the tick open: a burst of arenas to compact -> one CTA per arena.  (k_tail
+          // publishes no leaves, so the network already enqueued behind k_step stays valid.)
           std::atomic_thread_fence(std::memory_order_acquire);
           if (launch_post(L.e, L.s)) {
             rc = C4A0_E_CUDA;
@@ -1568,7 +1579,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
           std::this_thread::yield();
         }
       }
-      }
+      out->host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wait0).count();
       if (rc) break;
       std::atomic_thread_fence(std::memory_order_acquire);
       if (L.e->h_status->error) {
@@ -1584,7 +1595,12 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
         break;
       } else {
         const auto l0 = std::chrono::steady_clock::now();
-        rc = launch_round(cur);
+        const uint32_t rows = L.e->h_status->n_rows;
+        if (rows > L.spec_rows) {  // the guess was too small: evaluate again, all live rows
+          rc = launch_nn(cur, rows, nullptr);
+          out->nn_relaunches++;
+        }
+        if (!rc) rc = launch_round(cur, rows);
         out->host_launch_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - l0).count();
       }
     }
@@ -1602,22 +1618,22 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
       if (cudaEventElapsedTime(&ms, L.t0, L.t1) == cudaSuccess && ms > mx) mx = ms;
     }
     out->device_ms = mx;
-    double sum[4] = {0, 0, 0, 0};
+    double sum[2] = {0, 0};
     uint32_t n = 0;
-    for (size_t q = 0; q + 4 < kev.size(); q += 5) {
-      float d[4];
-      bool ok = true;
-      for (int k = 0; k < 4; k++) ok = ok && cudaEventElapsedTime(&d[k], kev[q + k], kev[q + k + 1]) == cudaSuccess;
-      if (ok) {
-        for (int k = 0; k < 4; k++) sum[k] += d[k];
+    for (size_t q = 0; q + 2 < kev.size(); q += 3) {
+      float d[2];
+      if (cudaEventElapsedTime(&d[0], kev[q], kev[q + 1]) == cudaSuccess &&
+          cudaEventElapsedTime(&d[1], kev[q + 1], kev[q + 2]) == cudaSuccess) {
+        sum[0] += d[0];
+        sum[1] += d[1];
         n++;
       }
     }
     out->kernel_samples = n;
-    out->nn_ms_sum = sum[0];
-    out->k_step_ms_sum = sum[1];
-    out->k_move_ms_sum = sum[2];
-    out->k_post_ms_sum = sum[3];
+    out->k_step_ms_sum = sum[0];
+    out->nn_ms_sum = sum[1];
+    out->k_move_ms_sum = 0;
+    out->k_post_ms_sum = 0;
   }
   out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   cleanup();

@@ -190,12 +190,14 @@ typedef struct {
   uint64_t tail_launches;    /* ticks that needed the separate compaction kernel */
   double host_wait_ms;       /* host time spent waiting for tick status (the GPU is busy) */
   double host_launch_ms;     /* host time spent enqueuing network graphs and tick kernels */
+  uint64_t nn_relaunches;    /* ticks whose network was run again because more rows than guessed were live */
 } c4a0_run_report;
 
 /* Plays every engine's requests to completion: what self_play() does between spawning its threads
  * and collecting done_queue (self_play.rs:60-129).  engines[i] runs on streams[i] with graphs[i]
- * (n_graphs[i] entries).  With two engines the tree tick and host round trip of one overlap the
- * network of the other.  time_kernels_every = k > 0 brackets the tree kernels of every k-th tick
+ * (n_graphs[i] entries).  The network of a tick is enqueued right behind the tick's kernel, sized
+ * from the previous tick's row count plus a margin, so the host round trip overlaps it; a tick that
+ * packed more rows than guessed gets its network run again (nn_relaunches).  time_kernels_every = k > 0 brackets the tree kernels of every k-th tick
  * with CUDA events (no synchronisation).  max_ticks = 0 means no limit. */
 int c4a0_engine_run(c4a0_engine *const *engines, uint32_t n_engines,
                     const c4a0_nn_graph *const *graphs, const uint32_t *n_graphs,
