@@ -34,6 +34,7 @@
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -1485,6 +1486,9 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   };
   auto wall0 = std::chrono::steady_clock::now();
   int rc = 0;
+  // guess for the next tick's rows = this tick's rows * (1 + 2^-spec_shift): rows drift slowly
+  uint32_t spec_shift = 6;
+  if (const char* env = getenv("C4A0_SPEC_SHIFT")) spec_shift = (uint32_t)atoi(env) & 31u;
   // the network on rows [0, >= rows): the smallest captured graph that covers them
   auto launch_nn = [&](uint32_t i, uint32_t rows, uint32_t* covered) -> int {
     Lane& L = lanes[i];
@@ -1519,7 +1523,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     int r = launch_tick(L.e, L.s, nullptr, false);
     if (r) return r;
     if (ev) CK(cudaEventRecord(ev[1], L.s));
-    const uint32_t margin = rows / 16 > 32 ? rows / 16 : 32;
+    const uint32_t margin = (rows >> spec_shift) > 16 ? (rows >> spec_shift) : 16;
     const uint32_t guess = rows + margin < L.e->D.n_slots ? rows + margin : L.e->D.n_slots;
     r = launch_nn(i, guess, &L.spec_rows);
     if (r) return r;
