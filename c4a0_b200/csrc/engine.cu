@@ -29,8 +29,10 @@
 //     draws the next row number from an atomic counter and writes the input planes of that row,
 //     later games with the same key just remember who leads it.  Rows are dense, 0..n_rows-1.
 //
-// One tick = k_step -> k_tail, then the network on rows [0, n_rows).  k_tail compacts the arenas
-// that filled up and publishes the tick's status (n_rows, finished games) to mapped host memory.
+// One tick = k_step, then the network on rows [0, n_rows).  The last CTA of k_step to finish closes
+// the tick: it compacts the (few) arenas that filled up and publishes the tick's status (n_rows,
+// finished games) to mapped host memory.  Only a burst of compactions is handed to a second kernel,
+// k_tail (one CTA per arena), which the host launches when the status word asks for it.
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -1487,7 +1489,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   auto wall0 = std::chrono::steady_clock::now();
   int rc = 0;
   // guess for the next tick's rows = this tick's rows * (1 + 2^-spec_shift): rows drift slowly
-  uint32_t spec_shift = 6;
+  uint32_t spec_shift = 8;
   if (const char* env = getenv("C4A0_SPEC_SHIFT")) spec_shift = (uint32_t)atoi(env) & 31u;
   // the network on rows [0, >= rows): the smallest captured graph that covers them
   auto launch_nn = [&](uint32_t i, uint32_t rows, uint32_t* covered) -> int {
