@@ -6,9 +6,10 @@
 // struct-of-arrays trees in HBM:
 //
 //   * A tree is a bump-allocated array of 160-byte BLOCKS.  A block belongs to one expanded node
-//     and holds the statistics of its 7 children column-wise (N[8], Qp[8], Qn[8], P[8], child[8]),
-//     i.e. exactly the fields UCT selection reads for one level (mcts.rs:359-388), fetched as
-//     16-byte vectors.  Node positions are never stored: selection replays the moves on bitboards.
+//     and holds its 7 children: one 16-byte record {N, Qp, Qn, P} per child plus child[8] block
+//     indices, i.e. exactly the fields UCT selection reads for one level (mcts.rs:359-388) — one
+//     vector load per lane — and a backup updates a child with one 16-byte read-modify-write.
+//     Node positions are never stored: selection replays the moves on bitboards.
 //   * Eight lanes own one game for a whole tick (k_step; four games per warp, warp-uniform control
 //     flow): they consume the network's answer (mask + softmax + expand + backup, mcts.rs:83-155),
 //     play the move when the root reached n_iterations (temperature + seeded sample + re-root,
@@ -58,11 +59,14 @@ using c4host::fail;
 // ------------------------------------------------------------------------------------------------
 // Data layout
 // ------------------------------------------------------------------------------------------------
+struct __align__(16) ChildStat {  // one 16-byte vector per child: a backup touches one sector
+  uint32_t N;  // visit_count            (mcts.rs:335)
+  float Qp;    // q_sum_penalty          (mcts.rs:336)
+  float Qn;    // q_sum_no_penalty       (mcts.rs:337)
+  float P;     // initial_policy_value   (mcts.rs:338)
+};
 struct __align__(32) Block {
-  uint32_t N[8];      // visit_count of child c            (mcts.rs:335)
-  float Qp[8];        // q_sum_penalty of child c          (mcts.rs:336)
-  float Qn[8];        // q_sum_no_penalty of child c       (mcts.rs:337)
-  float P[8];         // initial_policy_value of child c   (mcts.rs:338)
+  ChildStat rec[8];   // child c of the node (entry 7 is padding)
   uint32_t child[8];  // block index of child c's own block, 0 = child not expanded
 };
 static_assert(sizeof(Block) == 160, "block must be ten 16-byte vectors");
@@ -384,9 +388,12 @@ __device__ __forceinline__ void backup(const Lanes& L, Game& G, bool pred, float
         Block* B = G.arena + (e >> 3);
         const uint32_t c = e & 7u;
         const bool neg = ((G.len - 1 - j) & 1u) != 0;
-        B->N[c] += 1u;
-        B->Qp[c] += neg ? -qp : qp;
-        B->Qn[c] += neg ? -qn : qn;
+        uint4* rp = reinterpret_cast<uint4*>(&B->rec[c]);  // one 16-byte read-modify-write
+        uint4 r = *rp;
+        r.x += 1u;
+        r.y = __float_as_uint(__uint_as_float(r.y) + (neg ? -qp : qp));
+        r.z = __float_as_uint(__uint_as_float(r.z) + (neg ? -qn : qn));
+        *rp = r;
       }
     }
     const bool neg = (G.len & 1u) != 0;
@@ -427,9 +434,10 @@ __device__ __forceinline__ Pos select_leaf(const Dev& D, const Lanes& L, Game& G
     float qs = 0.0f, pr = 0.0f;
     if (act) {
       const Block* B = G.arena + b;
-      n = B->N[L.l];
-      qs = B->Qp[L.l];
-      pr = B->P[L.l];
+      const uint4 r = *reinterpret_cast<const uint4*>(&B->rec[L.l]);
+      n = r.x;
+      qs = __uint_as_float(r.y);
+      pr = __uint_as_float(r.w);
       ch = B->child[L.l];
     }
     const unsigned legal = c4::legal_mask(pos.mask);
@@ -481,10 +489,7 @@ __device__ __forceinline__ bool apply_network(const Dev& D, const Lanes& L, Game
   if (pred && fits) {
     G.n_alloc = nb + 1u;
     Block* B = G.arena + nb;  // expand_leaf: one new block holding the 7 children
-    B->N[L.l] = 0u;
-    B->Qp[L.l] = 0.0f;
-    B->Qn[L.l] = 0.0f;
-    B->P[L.l] = p;
+    *reinterpret_cast<uint4*>(&B->rec[L.l]) = make_uint4(0u, 0u, 0u, __float_as_uint(p));
     B->child[L.l] = 0u;
     if (G.len == 0) G.root_block = nb;
     G.depth += G.len;
@@ -528,9 +533,10 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
   float q_p = 0.0f, q_n = 0.0f;
   if (rb) {
     const Block* RB = G.arena + rb;
-    n_c = RB->N[l];
-    q_p = RB->Qp[l];
-    q_n = RB->Qn[l];
+    const uint4 r = *reinterpret_cast<const uint4*>(&RB->rec[l]);
+    n_c = r.x;
+    q_p = __uint_as_float(r.y);
+    q_n = __uint_as_float(r.z);
     ch = RB->child[l];
   }
   // root_policy (mcts.rs:396-412): visit counts of the children, normalised
@@ -1408,10 +1414,10 @@ struct Dumper {
         continue;
       }
       put(B.child[c] ? 2u : 1u);
-      put(B.N[c]);
-      put(c4::f32_bits(B.Qp[c]));
-      put(c4::f32_bits(B.Qn[c]));
-      put(c4::f32_bits(B.P[c]));
+      put(B.rec[c].N);
+      put(c4::f32_bits(B.rec[c].Qp));
+      put(c4::f32_bits(B.rec[c].Qn));
+      put(c4::f32_bits(B.rec[c].P));
       if (B.child[c]) children(B.child[c], c4::make_move(pos, c));
     }
   }
