@@ -333,13 +333,10 @@ def run_ours(args):
                 "peak_source": peak_src, "kernel": "k_step (network answer -> softmax/expand/backup, move, UCT select, dedup + plane pack, tick close)"}
     if kms:
         k_step_ms = float(np.mean([k["k_step"] for k in kms]))
-        k_move_ms = float(np.mean([k["k_move"] for k in kms]))
         achieved = bytes_per_sim * sims_per_launch / (k_step_ms * 1e-3) / 1e9
         roofline.update(
             achieved=achieved, frac=achieved / peak, bytes_per_sim=bytes_per_sim, sims_per_launch=sims_per_launch,
-            avg_launch_ms=k_step_ms, k_move_avg_launch_ms=k_move_ms,
-            k_post_avg_launch_ms=float(np.mean([k.get("k_post", 0.0) for k in kms])),
-            nn_graph_avg_ms=float(np.mean([k.get("nn", 0.0) for k in kms])), launches_timed=int(sum(k["samples"] for k in kms)),
+            avg_launch_ms=k_step_ms, nn_graph_avg_ms=float(np.mean([k.get("nn", 0.0) for k in kms])), launches_timed=int(sum(k["samples"] for k in kms)),
             select_depth=d, expand_frac=e,
         )
         tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")

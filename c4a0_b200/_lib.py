@@ -93,18 +93,17 @@ class RunReport(C.Structure):
         ("ticks", C.c_uint64),
         ("nn_launches", C.c_uint64),
         ("nn_rows_launched", C.c_uint64),
+        ("nn_relaunches", C.c_uint64),
+        ("tail_launches", C.c_uint64),
         ("device_ms", C.c_double),
         ("wall_ms", C.c_double),
-        ("kernel_samples", C.c_uint32),
-        ("k_step_ms_sum", C.c_double),
-        ("k_move_ms_sum", C.c_double),
-        ("k_post_ms_sum", C.c_double),
-        ("nn_ms_sum", C.c_double),
-        ("bucket_launches", C.c_uint64 * 32),
-        ("tail_launches", C.c_uint64),
         ("host_wait_ms", C.c_double),
         ("host_launch_ms", C.c_double),
-        ("nn_relaunches", C.c_uint64),
+        ("kernel_samples", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("k_step_ms_sum", C.c_double),
+        ("nn_ms_sum", C.c_double),
+        ("bucket_launches", C.c_uint64 * 32),
     ]
 
     def as_dict(self) -> dict:

@@ -86,7 +86,7 @@ struct __align__(128) Slot {
   uint32_t req;                    // request index of the game seated here
   uint32_t n_moves;
   uint32_t nn_leader;              // slot that leads this game's leaf key: its rowtag names the network row
-  uint32_t spare;
+  uint32_t reserved;
   unsigned long long c_sims, c_exp, c_term, c_depth;
 };
 __host__ __device__ inline uint64_t leaf_model_of(const Slot& S) {
@@ -1215,7 +1215,7 @@ int c4a0_engine_step(c4a0_engine* e, void* stream) {
   return launch_tick(e, (cudaStream_t)stream, nullptr, true);
 }
 
-int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* ms_move) {
+int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* ms_tail) {
   if (!e) return fail(C4A0_E_INVALID, "null engine");
   if (!e->have_requests) return fail(C4A0_E_INVALID, "set_requests() must precede step()");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1226,9 +1226,9 @@ int c4a0_engine_step_timed(c4a0_engine* e, void* stream, float* ms_step, float* 
   CK(cudaStreamSynchronize(s));
   float a = 0, b = 0;
   CK(cudaEventElapsedTime(&a, e->ev[0], e->ev[1]));
-  CK(cudaEventElapsedTime(&b, e->ev[1], e->ev[2]));
+  CK(cudaEventElapsedTime(&b, e->ev[2], e->ev[3]));
   if (ms_step) *ms_step = a;
-  if (ms_move) *ms_move = b;
+  if (ms_tail) *ms_tail = b;
   return 0;
 }
 
@@ -1644,8 +1644,6 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     out->kernel_samples = n;
     out->k_step_ms_sum = sum[0];
     out->nn_ms_sum = sum[1];
-    out->k_move_ms_sum = 0;
-    out->k_post_ms_sum = 0;
   }
   out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   cleanup();

@@ -91,7 +91,7 @@ class Engine:
         L.check(self._lib.c4a0_engine_step(self._h, stream))
 
     def step_timed(self, stream: int = 0) -> Tuple[float, float]:
-        """step() bracketed by CUDA events: (ms of the apply+select kernel, ms of the move kernel)."""
+        """step() bracketed by CUDA events: (ms of k_step, ms of k_tail)."""
         a, b = C.c_float(), C.c_float()
         L.check(self._lib.c4a0_engine_step_timed(self._h, stream, C.byref(a), C.byref(b)))
         return a.value, b.value

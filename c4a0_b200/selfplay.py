@@ -132,7 +132,7 @@ class RunInfo:
     wall_s: float = 0.0
     device_s: float = 0.0  # CUDA-event time of the search (first network launch .. last game finished)
     stats: dict = field(default_factory=dict)
-    kernel_ms: dict = field(default_factory=dict)  # sampled k_step / k_move durations
+    kernel_ms: dict = field(default_factory=dict)  # sampled per-tick device times: k_step, network graph (and k_tail in the python loop)
     engine_bytes: int = 0
     report: dict = field(default_factory=dict)
     n_lanes: int = 1
@@ -347,8 +347,7 @@ class SelfPlaySession:
             info.device_s = rep["device_ms"] / 1e3
             if rep["kernel_samples"]:
                 n = rep["kernel_samples"]
-                info.kernel_ms = {"k_step": rep["k_step_ms_sum"] / n, "k_move": rep["k_move_ms_sum"] / n,
-                                  "k_post": rep["k_post_ms_sum"] / n, "nn": rep["nn_ms_sum"] / n, "samples": n}
+                info.kernel_ms = {"k_step": rep["k_step_ms_sum"] / n, "nn": rep["nn_ms_sum"] / n, "samples": n}
         elif host_loop == "python":
             ev0 = torch.cuda.Event(enable_timing=True)
             ev1 = torch.cuda.Event(enable_timing=True)
@@ -380,7 +379,7 @@ class SelfPlaySession:
             info.device_s = ev0.elapsed_time(ev1) / 1e3
             info.ticks = ticks
             if kn:
-                info.kernel_ms = {"k_step": ks / kn, "k_move": km / kn, "samples": kn}
+                info.kernel_ms = {"k_step": ks / kn, "k_tail": km / kn, "samples": kn}
         else:
             raise ValueError("host_loop must be 'native' or 'python'")
         info.stats = _sum_stats([ln.engine.stats(ln.stream.cuda_stream) for ln in self.lanes])

@@ -136,10 +136,9 @@ int c4a0_engine_set_requests(c4a0_engine *e, const uint64_t *game_id, const uint
  * (mcts.rs:160-183); the distinct waiting leaves are then packed as rows [0, n_rows) of planes_dev. */
 int c4a0_engine_step(c4a0_engine *e, void *stream);
 
-/* step() with CUDA events around its two kernels (synchronises): device milliseconds of the
- * apply+select kernel and of the move/re-root kernel.  Used by bench.py to sample kernel time inside
- * the timed region; not capturable. */
-int c4a0_engine_step_timed(c4a0_engine *e, void *stream, float *ms_step_kernel, float *ms_move_kernel);
+/* step() with CUDA events around its kernels (synchronises): device milliseconds of k_step (the
+ * whole tick of every game) and of k_tail (compaction bursts; ~0 otherwise).  Not capturable. */
+int c4a0_engine_step_timed(c4a0_engine *e, void *stream, float *ms_step_kernel, float *ms_tail_kernel);
 
 /* Developer aid: runs one step() with cycle counters inside the tick kernel and returns 8 words per
  * slot {load cycles, apply cycles, simulations, run cycles (moves + selection + terminal backups),
@@ -178,19 +177,18 @@ typedef struct {
 typedef struct {
   uint64_t ticks;            /* tree ticks launched, all engines */
   uint64_t nn_launches;      /* network graphs launched */
-  uint64_t nn_rows_launched; /* sum of their row counts (>= nn_evals: bucket padding) */
+  uint64_t nn_rows_launched; /* sum of their row counts (>= nn_evals: bucket padding, re-launches) */
+  uint64_t nn_relaunches;    /* ticks whose network was run again because more rows than guessed were live */
+  uint64_t tail_launches;    /* ticks that needed the separate compaction kernel */
   double device_ms;          /* CUDA-event time, first network launch .. last game finished (max over engines) */
   double wall_ms;
-  uint32_t kernel_samples;   /* ticks whose kernels were bracketed by events */
-  double k_step_ms_sum;      /* summed device time of the apply+select kernel over those ticks */
-  double k_move_ms_sum;      /* ... of the compaction kernel */
-  double k_post_ms_sum;      /* ... of the tail kernel where it was enqueued with the tick (engine_step) */
-  double nn_ms_sum;          /* ... of the network graph that preceded them */
-  uint64_t bucket_launches[32]; /* network launches per graph index (all engines) */
-  uint64_t tail_launches;    /* ticks that needed the separate compaction kernel */
   double host_wait_ms;       /* host time spent waiting for tick status (the GPU is busy) */
   double host_launch_ms;     /* host time spent enqueuing network graphs and tick kernels */
-  uint64_t nn_relaunches;    /* ticks whose network was run again because more rows than guessed were live */
+  uint32_t kernel_samples;   /* ticks whose kernels were bracketed by CUDA events */
+  uint32_t reserved;
+  double k_step_ms_sum;      /* summed device time of k_step over those ticks */
+  double nn_ms_sum;          /* ... of the network graph enqueued behind it */
+  uint64_t bucket_launches[32]; /* network launches per graph index (all engines) */
 } c4a0_run_report;
 
 /* Plays every engine's requests to completion: what self_play() does between spawning its threads

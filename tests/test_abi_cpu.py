@@ -35,7 +35,7 @@ def test_struct_sizes_match_the_header():
     assert C.sizeof(L.Config) == 11 * 4
     assert C.sizeof(L.Progress) == 7 * 4
     assert C.sizeof(L.Stats) == 12 * 8
-    assert C.sizeof(L.RunReport) == 3 * 8 + 2 * 8 + 8 + 4 * 8 + 32 * 8 + 8 + 16 + 8
+    assert C.sizeof(L.RunReport) == 5 * 8 + 4 * 8 + 8 + 2 * 8 + 32 * 8
     assert C.sizeof(L.NNGraph) == 16
 
 

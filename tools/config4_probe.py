@@ -51,6 +51,6 @@ e = st["expansions"] / max(1, st["sims"])
 bps = 92 * d + 24 * (d + 1) + 16 + 84 * 2 + 36 + 168 * e
 spl = st["sims"] / ticks
 print({"ticks": ticks, "ms_per_tick": ms / ticks, "sims": st["sims"], "sims_per_s": st["sims"] / ms * 1e3, "rows_now": p.n_rows,
-       "finished": p.n_finished, "k_step_ms": ks / kn, "k_move_ms": km / kn, "depth": d, "bytes_per_sim": bps,
+       "finished": p.n_finished, "k_step_ms": ks / kn, "k_tail_ms": km / kn, "depth": d, "bytes_per_sim": bps,
        "k_step_GBps": bps * spl / (ks / kn * 1e-3) / 1e9, "compactions": st["compactions"]})
 print("max mem allocated by torch %.1f GB" % (torch.cuda.max_memory_allocated() / 1e9))

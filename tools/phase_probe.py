@@ -35,7 +35,7 @@ with torch.cuda.stream(ln.stream):
             print("   slowest game: %.1f us at 1.9 GHz" % (a[:, 7].max() / 1900))
             x, y = ln.engine.step_timed(s)
             ln.evaluate(ev, n)
-            print("   step_timed: k_step %.1f us k_move %.1f us" % (x * 1e3, y * 1e3))
+            print("   step_timed: k_step %.1f us k_tail %.1f us" % (x * 1e3, y * 1e3))
         else:
             ln.engine.step(s)
         if tick % 500 == 0 and ln.engine.poll(s).n_finished == n:

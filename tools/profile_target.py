@@ -1,5 +1,5 @@
 """Target for ncu: runs the tree kernels alone (synthetic hash evaluator) at the bench workload so
-that steady-state launches of k_step / k_move / k_scan / k_pack can be captured.
+that steady-state launches of k_step / k_tail can be captured.
 
     ncu ... python tools/profile_target.py --games 16384 --sims 600 --ticks 2600
 """
