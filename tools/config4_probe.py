@@ -20,7 +20,8 @@ torch.manual_seed(1337)
 model = ConnectFourNet(ModelConfig(n_residual_blocks=1, conv_filter_size=width, n_policy_layers=4, n_value_layers=2)).cuda().eval()
 ev = DeviceEvaluator.from_model(model, torch.bfloat16)
 t0 = time.time()
-sess = SelfPlaySession(n, n, sims, 6.6, 0.01, plane_dtype=torch.bfloat16, plane_stride=96, n_lanes=1)
+sess = SelfPlaySession(n, n, sims, 6.6, 0.01, plane_dtype=torch.bfloat16, plane_stride=ev.plane_stride,
+                       plane_offset=ev.plane_offset, n_lanes=1)
 ln = sess.lanes[0]
 print("engine bytes %.1f GB, create %.1f s, arena_blocks/half %d" % (ln.engine.device_bytes / 1e9, time.time() - t0, ln.engine.cfg.arena_blocks), flush=True)
 ids = np.arange(n)

@@ -14,7 +14,8 @@ n, sims = int(sys.argv[1]) if len(sys.argv) > 1 else 16384, 600
 torch.manual_seed(1337)
 model = ConnectFourNet(default_config()).cuda().eval()
 ev = DeviceEvaluator.from_model(model, torch.bfloat16)
-sess = SelfPlaySession(n, n, sims, 6.6, 0.01, plane_dtype=torch.bfloat16, plane_stride=96, n_lanes=1)
+sess = SelfPlaySession(n, n, sims, 6.6, 0.01, plane_dtype=torch.bfloat16, plane_stride=ev.plane_stride,
+                       plane_offset=ev.plane_offset, n_lanes=1)
 ln = sess.lanes[0]
 ids = np.arange(n)
 z = np.zeros(n, np.uint64)
