@@ -349,8 +349,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": positions_all / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.nn_dtype, "data": "synthetic",
-        "config": workload_config(args, world),
+        "scaling": "weak", "vs_baseline": None, "dtype": args.nn_dtype, "tree_dtype": "f32 (bit-exact with the reference), u64 bitboards",
+        "data": "synthetic", "config": workload_config(args, world),
         "sims_per_s": sims_all / dev_s_max, "nn_evals_per_s": evals_all / dev_s_max,
         "e2e": {
             "value": positions_all / e2e_s_max, "unit": UNIT,

@@ -323,6 +323,10 @@ class SelfPlaySession:
 
         host_loop = "native": bucketed CUDA graphs driven by the C++ loop (c4a0_engine_run);
                     "python": eager network calls and engine.step() from Python (any callable)."""
+        want = (getattr(evaluator, "plane_stride", self.plane_stride), getattr(evaluator, "plane_offset", self.plane_offset))
+        if want != (self.plane_stride, self.plane_offset):
+            raise ValueError(f"evaluator expects plane layout (stride, offset) = {want}, the session was built with "
+                             f"{(self.plane_stride, self.plane_offset)}")
         host_loop = DEFAULTS["host_loop"] if host_loop is None else host_loop
         poll_every = DEFAULTS["poll_every"] if poll_every is None else poll_every
         sample_kernels_every = DEFAULTS["sample_kernels_every"] if sample_kernels_every is None else sample_kernels_every
