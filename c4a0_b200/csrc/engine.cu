@@ -37,6 +37,7 @@
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -93,6 +94,11 @@ __host__ __device__ inline uint64_t leaf_model_of(const Slot& S) {
   return (c4::popc64(S.leaf_mask) & 1) ? S.model1 : S.model0;
 }
 static_assert(sizeof(Slot) == 128, "slot state must be one cache line");
+// load_game()/store_game() move the line as 16-byte vectors: V[0] root, V[1] leaf, V[2] models,
+// V[3] root statistics, V[4] allocator/state, V[5] request/moves/leader, V[6..7] counters
+static_assert(offsetof(Slot, leaf_mask) == 16 && offsetof(Slot, model0) == 32 && offsetof(Slot, root_N) == 48 &&
+                  offsetof(Slot, n_alloc) == 64 && offsetof(Slot, req) == 80 && offsetof(Slot, c_sims) == 96,
+              "Slot layout changed: update the vector views");
 
 constexpr int PATH_STRIDE = 48;  // <= 42 levels below a root; six entries per lane
 constexpr int MAXS = C4A0_MAX_SAMPLES;
@@ -298,14 +304,13 @@ __device__ __forceinline__ float gmax8(float v) {
 struct Game {
   uint32_t slot, state;
   Pos root, leaf;
-  uint64_t model0, model1;
   uint32_t rootN, root_block, n_alloc, len, half, req, n_moves, nn_leader;
   float rootQp, rootQn;
   Block* arena;
   uint32_t* path;
   uint32_t pr[6];  // this lane's share of the selected path: entries l, l+8, ..., l+40
-  uint32_t sims, exps, term, depth;
-  unsigned long long c_sims, c_exp, c_term, c_depth;  // the slot's running totals
+  uint32_t sims, exps, term, depth;  // this tick's contribution to the slot's counters
+  bool reseated;                     // a new game took the slot during this tick (model ids change)
 };
 
 __device__ __forceinline__ uint32_t pr_get(const uint32_t (&pr)[6], uint32_t k) {
@@ -320,59 +325,62 @@ __device__ __forceinline__ void pr_set(uint32_t (&pr)[6], uint32_t k, uint32_t v
 }
 
 // One dependent memory round trip: the slot line (same address for the 8 lanes = one broadcast
-// transaction) and this lane's path entries are fetched together.
+// transaction per 16-byte vector) and this lane's path entries are fetched together.  Only what a
+// tick needs in registers is loaded: the model ids and the counter totals stay in memory.
 __device__ __forceinline__ void load_game(const Dev& D, const Lanes& L, uint32_t slot, Game& G) {
-  const Slot* S = D.slots + slot;
+  const uint4* V = reinterpret_cast<const uint4*>(D.slots + slot);
   G.slot = slot;
   G.path = D.path + (size_t)slot * PATH_STRIDE;
 #pragma unroll
   for (int k = 0; k < 6; k++) G.pr[k] = G.path[L.l + 8 * k];
-  G.state = S->state;
-  G.root.mask = S->root_mask;
-  G.root.value = S->root_value;
-  G.leaf.mask = S->leaf_mask;
-  G.leaf.value = S->leaf_value;
-  G.model0 = S->model0;
-  G.model1 = S->model1;
-  G.rootN = S->root_N;
-  G.rootQp = S->root_Qp;
-  G.rootQn = S->root_Qn;
-  G.root_block = S->root_block;
-  G.n_alloc = S->n_alloc;
-  G.len = S->path_len;
-  G.half = S->half;
-  G.req = S->req;
-  G.n_moves = S->n_moves;
-  G.nn_leader = S->nn_leader;
-  G.c_sims = S->c_sims;
-  G.c_exp = S->c_exp;
-  G.c_term = S->c_term;
-  G.c_depth = S->c_depth;
+  const uint4 v0 = V[0], v1 = V[1], v3 = V[3], v4 = V[4], v5 = V[5];
+  G.root.mask = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
+  G.root.value = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
+  G.leaf.mask = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
+  G.leaf.value = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
+  G.rootN = v3.x;
+  G.rootQp = __uint_as_float(v3.y);
+  G.rootQn = __uint_as_float(v3.z);
+  G.root_block = v3.w;
+  G.n_alloc = v4.x;
+  G.len = v4.y;
+  G.state = v4.z;
+  G.half = v4.w;
+  G.req = v5.x;
+  G.n_moves = v5.y;
+  G.nn_leader = v5.z;
   G.arena = arena_of(D, slot, G.half);
   G.sims = G.exps = G.term = G.depth = 0;
+  G.reseated = false;
 }
-__device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t state) {  // one lane
+// One lane writes the line back (five 16-byte vectors) and adds the tick's counters to the totals.
+__device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t state) {
   Slot* S = D.slots + G.slot;
-  S->root_mask = G.root.mask;
-  S->root_value = G.root.value;
-  S->leaf_mask = G.leaf.mask;
-  S->leaf_value = G.leaf.value;
-  S->model0 = G.model0;
-  S->model1 = G.model1;
-  S->root_N = G.rootN;
-  S->root_Qp = G.rootQp;
-  S->root_Qn = G.rootQn;
-  S->root_block = G.root_block;
-  S->n_alloc = G.n_alloc;
-  S->path_len = G.len;
-  S->state = state;
-  S->half = G.half;
-  S->req = G.req;
-  S->n_moves = G.n_moves;
-  S->c_sims = G.c_sims + G.sims;
-  S->c_exp = G.c_exp + G.exps;
-  S->c_term = G.c_term + G.term;
-  S->c_depth = G.c_depth + G.depth;
+  uint4* V = reinterpret_cast<uint4*>(S);
+  V[0] = make_uint4((uint32_t)G.root.mask, (uint32_t)(G.root.mask >> 32), (uint32_t)G.root.value, (uint32_t)(G.root.value >> 32));
+  V[1] = make_uint4((uint32_t)G.leaf.mask, (uint32_t)(G.leaf.mask >> 32), (uint32_t)G.leaf.value, (uint32_t)(G.leaf.value >> 32));
+  if (G.reseated) {
+    S->model0 = D.p0[G.req];
+    S->model1 = D.p1[G.req];
+  }
+  V[3] = make_uint4(G.rootN, __float_as_uint(G.rootQp), __float_as_uint(G.rootQn), G.root_block);
+  V[4] = make_uint4(G.n_alloc, G.len, state, G.half);
+  V[5] = make_uint4(G.req, G.n_moves, G.nn_leader, 0u);
+  if (G.sims) {
+    ulonglong2* C = reinterpret_cast<ulonglong2*>(&S->c_sims);
+    ulonglong2 a = C[0], b = C[1];
+    a.x += G.sims;
+    a.y += G.exps;
+    b.x += G.term;
+    b.y += G.depth;
+    C[0] = a;
+    C[1] = b;
+  }
+}
+// the model that has to evaluate the slot's stored leaf (mcts.rs:70-76); read after store_game()
+__device__ __forceinline__ uint64_t stored_leaf_model(const Dev& D, const Game& G) {
+  const Slot* S = D.slots + G.slot;
+  return (c4::popc64(G.leaf.mask) & 1) ? S->model1 : S->model0;
 }
 
 // mcts.rs:137-155 — add (qp, qn) at the leaf, alternate the sign towards the root.  The path nodes
@@ -505,8 +513,7 @@ __device__ __forceinline__ bool apply_network(const Dev& D, const Lanes& L, Game
 }
 
 __device__ __forceinline__ void seat_game(const Dev& D, Game& G, uint32_t r) {
-  G.model0 = D.p0[r];
-  G.model1 = D.p1[r];
+  G.reseated = true;
   G.root = Pos{0ull, 0ull};
   G.rootN = 0u;
   G.rootQp = 0.0f;
@@ -830,7 +837,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     store_game(D, G, ns);
     if (ns == ST_NEED_MOVE) push_mover(D, slot);
     if (ns == ST_WAIT_NN)
-      publish_leaf(D, slot, G.leaf.mask, G.leaf.value, (c4::popc64(G.leaf.mask) & 1) ? G.model1 : G.model0, epoch);
+      publish_leaf(D, slot, G.leaf.mask, G.leaf.value, stored_leaf_model(D, G), epoch);
     if (prof) {  // cycles of this game's warp per phase (c4a0_engine_debug_phases)
       uint32_t* o = D.dbg + (size_t)slot * 8;
       o[0] = (uint32_t)(t1 - t0);         // load slot state
