@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--sample-kernels-every", type=int, default=53)
     ap.add_argument("--lanes", type=int, default=1, help="engines per GPU (2 = tree ticks overlap the other half's network)")
     ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
+    ap.add_argument("--no-eval-cache", action="store_true",
+                    help="send every leaf to the network even if this job has evaluated the position before")
+    ap.add_argument("--eval-cache-entries", type=int, default=0, help="entries of the evaluation cache (0 = engine default)")
     ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
     ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")
     ap.add_argument("--host-loop", choices=["native", "python"], default="native",
@@ -260,6 +263,8 @@ def run_ours(args):
     selfplay.DEFAULTS["host_loop"] = args.host_loop
     selfplay.DEFAULTS["dedup"] = not args.no_dedup
     selfplay.DEFAULTS["max_inline_sims"] = args.max_inline
+    selfplay.DEFAULTS["eval_cache"] = not args.no_eval_cache
+    selfplay.DEFAULTS["eval_cache_entries"] = args.eval_cache_entries
     G = args.games
     ids = range(rank * G, (rank + 1) * G)  # weak scaling: every rank plays its own G games
 
@@ -307,6 +312,8 @@ def run_ours(args):
     expansions = sum(r[1].stats["expansions"] for r in runs)
     nn_rows_launched = sum(r[1].report.get("nn_rows_launched", 0) for r in runs)
     compactions = sum(r[1].stats.get("compactions", 0) for r in runs)
+    cache_hits = sum(r[1].stats.get("cache_hits", 0) for r in runs)
+    cache_inserts = sum(r[1].stats.get("cache_inserts", 0) for r in runs)
     engine_gb = runs[-1][1].engine_bytes / 1e9
     ticks = sum(r[1].ticks for r in runs)
     depth = sum(r[1].stats["select_depth_sum"] for r in runs)
@@ -364,6 +371,9 @@ def run_ours(args):
         "leaf_evals_per_s": expansions_all / dev_s_max,
         "dedup": {"enabled": not args.no_dedup, "leaf_requests": expansions_all, "unique_rows": evals_all,
                   "rows_launched_incl_bucket_padding": rows_launched_all},
+        # rank 0's counters; the table is emptied at the start of every step (= every play_games call)
+        "eval_cache": {"enabled": not args.no_eval_cache, "hits": cache_hits, "inserts": cache_inserts,
+                       "hit_rate_of_expansions": cache_hits / max(1, expansions)},
         "compactions_per_step": compactions / max(1, args.steps), "engine_device_gb": engine_gb,
         "lanes": args.lanes, "nn_form": "module" if args.no_fold else ("GEMM-folded (FoldedNet)" if args.plain_fold else "GEMM-folded, epilogue-fused (FusedNet)"),
         "roofline": roofline,

@@ -19,6 +19,7 @@ ROW_IDLE, ROW_WAIT_NN, ROW_CONTINUE, ROW_NEED_MOVE = 0, 1, 2, 3
 MATH_LOGF, MATH_EXPF = 0, 1
 E_INVALID, E_CUDA, E_NOMEM, E_ENGINE = -1, -2, -3, -4
 FLAG_NO_DEDUP = 1
+FLAG_EVAL_CACHE = 2
 
 
 class Config(C.Structure):
@@ -34,6 +35,7 @@ class Config(C.Structure):
         ("plane_stride", C.c_uint32),
         ("flags", C.c_uint32),
         ("arena_blocks", C.c_uint32),
+        ("eval_cache_entries", C.c_uint32),
     ]
 
 
@@ -63,6 +65,8 @@ class Stats(C.Structure):
         ("steps", C.c_uint64),
         ("compacted_blocks", C.c_uint64),
         ("compactions", C.c_uint64),
+        ("cache_hits", C.c_uint64),
+        ("cache_inserts", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -174,7 +178,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)  # AttributeError here == the library does not export the header
         fn.restype = res
         fn.argtypes = args
-    if L.c4a0_abi_version() != 1:
+    if L.c4a0_abi_version() != 2:
         raise ImportError("libc4a0_engine.so ABI version mismatch; rebuild with c4a0_b200/build.py")
     _lib = L
     return L

@@ -72,6 +72,25 @@ struct __align__(32) Block {
 };
 static_assert(sizeof(Block) == 160, "block must be ten 16-byte vectors");
 
+// Evaluation cache (C4A0_FLAG_EVAL_CACHE): one network answer per 64-byte entry, direct mapped.
+//   tag = job << 33 | dying << 32 | tick.  `job` counts set_requests() calls, so entries of earlier
+//   jobs are simply stale.  An entry is READABLE in tick e iff job matches, dying == 0 and tick < e.
+//   State changes go through one atomicCAS on the tag and never touch a payload that a reader of
+//   the same tick could accept:
+//     claim (stale, or dying since an earlier tick)  -> {job, 0, e + 1}; the claimer writes the key
+//          now and the payload when its answer arrives in tick e + 1; readable from tick e + 2
+//     kill  (readable, other key)                    -> {job, 1, e}; payload untouched; claimable
+//          from tick e + 1 (always-replace with one tick of delay)
+struct __align__(64) EvalEntry {
+  uint64_t key;            // pos_key(): 49 bits that identify the position
+  unsigned long long tag;
+  uint64_t model;
+  float qp, qn;
+  float logit[7];
+  uint32_t pad;
+};
+static_assert(sizeof(EvalEntry) == 64, "an entry is two sectors");
+
 // Everything a game needs besides its tree, one 128-byte line per slot.
 struct __align__(128) Slot {
   uint64_t root_mask, root_value;
@@ -87,7 +106,7 @@ struct __align__(128) Slot {
   uint32_t req;                    // request index of the game seated here
   uint32_t n_moves;
   uint32_t nn_leader;              // slot that leads this game's leaf key: its rowtag names the network row
-  uint32_t reserved;
+  uint32_t cache_own;              // 1 + the evaluation-cache entry this game claimed for its waiting leaf, 0 = none
   unsigned long long c_sims, c_exp, c_term, c_depth;
 };
 __host__ __device__ inline uint64_t leaf_model_of(const Slot& S) {
@@ -127,6 +146,8 @@ struct Globals {  // one instance in device memory
   unsigned long long compactions;
   unsigned long long rows_total;    // sum over ticks of n_rows (positions actually evaluated)
   unsigned long long leaves_total;  // sum over ticks of games waiting for the network
+  unsigned long long cache_hits;    // leaves answered by the evaluation cache
+  unsigned long long cache_inserts; // entries claimed for a network answer
 };
 
 struct HostStatus {  // mapped pinned host memory, written by k_tail at the end of every tick
@@ -159,6 +180,8 @@ struct Dev {  // passed to kernels by value
   HostStatus* status;  // device address of the mapped host struct
   uint32_t* movers;
   unsigned long long* table;       // [table_mask+1]: epoch << 32 | leader slot
+  EvalEntry* cache;                // [cache_mask+1] evaluation cache, nullptr = off
+  uint32_t cache_mask, job;
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
@@ -310,6 +333,7 @@ struct Game {
   uint32_t* path;
   uint32_t pr[6];  // this lane's share of the selected path: entries l, l+8, ..., l+40
   uint32_t sims, exps, term, depth;  // this tick's contribution to the slot's counters
+  uint32_t cache_own, hits, claims;  // evaluation cache: entry owed a payload (+1); this tick's hits / claims
   bool reseated;                     // a new game took the slot during this tick (model ids change)
 };
 
@@ -349,8 +373,10 @@ __device__ __forceinline__ void load_game(const Dev& D, const Lanes& L, uint32_t
   G.req = v5.x;
   G.n_moves = v5.y;
   G.nn_leader = v5.z;
+  G.cache_own = v5.w;
   G.arena = arena_of(D, slot, G.half);
   G.sims = G.exps = G.term = G.depth = 0;
+  G.hits = G.claims = 0;
   G.reseated = false;
 }
 // One lane writes the line back (five 16-byte vectors) and adds the tick's counters to the totals.
@@ -365,7 +391,7 @@ __device__ __forceinline__ void store_game(const Dev& D, const Game& G, uint32_t
   }
   V[3] = make_uint4(G.rootN, __float_as_uint(G.rootQp), __float_as_uint(G.rootQn), G.root_block);
   V[4] = make_uint4(G.n_alloc, G.len, state, G.half);
-  V[5] = make_uint4(G.req, G.n_moves, G.nn_leader, 0u);
+  V[5] = make_uint4(G.req, G.n_moves, G.nn_leader, G.cache_own);
   if (G.sims) {
     ulonglong2* C = reinterpret_cast<ulonglong2*>(&S->c_sims);
     ulonglong2 a = C[0], b = C[1];
@@ -480,14 +506,15 @@ __device__ __forceinline__ Pos select_leaf(const Dev& D, const Lanes& L, Game& G
   return pos;
 }
 
-// mask_policy + softmax + expand_leaf + backup for the leaf the network just evaluated
-// (c4r.rs:272-286, mcts.rs:416-434, 114-132, 137-155).  Returns false for a game whose arena
-// overflowed (engine bug; reported).
-__device__ __forceinline__ bool apply_network(const Dev& D, const Lanes& L, Game& G, bool pred, uint32_t row) {
+// mask_policy + softmax + expand_leaf + backup for a leaf whose evaluation (x = this lane's logit,
+// vq, vn) has arrived from the network or from the evaluation cache (c4r.rs:272-286,
+// mcts.rs:416-434, 114-132, 137-155).  Returns false for a game whose arena overflowed (engine bug;
+// reported).
+__device__ __forceinline__ bool apply_answer(const Dev& D, const Lanes& L, Game& G, bool pred, float xin, float vq,
+                                             float vn) {
   const unsigned legal = c4::legal_mask(G.leaf.mask);
   const bool ok = pred && L.l < 7 && ((legal >> L.l) & 1u);
-  const float x = ok ? D.logits[(size_t)row * 7 + L.l] : -c4::f32_inf();
-  const float vq = pred ? D.qp[row] : 0.0f, vn = pred ? D.qn[row] : 0.0f;
+  const float x = ok ? xin : -c4::f32_inf();
   const float mx = gmax8(x);
   const float e = ok ? c4::c4_expf(x - mx) : 0.0f;
   const float s = fold7(e);
@@ -508,8 +535,61 @@ __device__ __forceinline__ bool apply_network(const Dev& D, const Lanes& L, Game
   const uint32_t last = G.len ? G.len - 1u : 0u;
   const uint32_t e2 = gshfl(pr_get(G.pr, last >> 3), (int)(last & 7u));
   if (pred && fits && G.len != 0u && L.l == 0) G.arena[e2 >> 3].child[e2 & 7u] = nb;
-  backup(L, G, pred && fits, vq, vn);
+  backup(L, G, pred && fits, pred ? vq : 0.0f, pred ? vn : 0.0f);
   return !pred || fits;
+}
+
+// ---- evaluation cache ---------------------------------------------------------------------------
+// 49 bits that identify a position: the side-to-move's stones plus one marker bit on the first
+// empty cell of every column (row 6 for a full column).  Stones obey gravity, so the marker is the
+// highest set bit of its column and the key decodes uniquely.
+__device__ __forceinline__ uint64_t pos_key(Pos p) {
+  const uint64_t rows7 = (1ull << 49) - 1ull;
+  return p.value | ((((p.mask << 7) | 0x7full) & ~p.mask) & rows7);
+}
+constexpr unsigned long long TAG_DYING = 1ull << 32;
+
+// The game's freshly selected, non-terminal leaf: answered from the cache (-> true, values in
+// x/vq/vn) or not.  On a miss lane 0 may claim the entry for the answer the network will deliver
+// next tick (G.cache_own), or mark a readable entry of another key for replacement.
+__device__ __forceinline__ bool cache_lookup(const Dev& D, const Lanes& L, Game& G, bool pred, Pos leaf, uint64_t model,
+                                             uint32_t epoch, float& x, float& vq, float& vn) {
+  const uint64_t key = pos_key(leaf);
+  const uint32_t h = (uint32_t)splitmix64(key ^ (model * 0x9E3779B97F4A7C15ULL)) & D.cache_mask;
+  bool hit = false;
+  if (pred) {
+    EvalEntry* E = D.cache + h;
+    const uint4 a = *reinterpret_cast<const uint4*>(E);        // key, tag
+    const uint4 b = *(reinterpret_cast<const uint4*>(E) + 1);  // model, qp, qn
+    const float lg = E->logit[L.l < 7 ? L.l : 6];
+    const uint64_t ekey = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    const unsigned long long tag = (unsigned long long)a.z | ((unsigned long long)a.w << 32);
+    const uint64_t emodel = (uint64_t)b.x | ((uint64_t)b.y << 32);
+    const bool mine = (uint32_t)(tag >> 33) == D.job;
+    const bool dying = (tag & TAG_DYING) != 0ull;
+    const bool old = (uint32_t)tag < epoch;  // the last state change happened in an earlier tick
+    const bool same = ekey == key && emodel == model;
+    hit = mine && !dying && old && same;
+    if (hit) {
+      x = lg;
+      vq = __uint_as_float(b.z);
+      vn = __uint_as_float(b.w);
+      G.hits++;
+    } else if (L.l == 0) {
+      const unsigned long long jb = (unsigned long long)D.job << 33;
+      if (!mine || (dying && old)) {
+        if (atomicCAS(&E->tag, tag, jb | (unsigned long long)(epoch + 1u)) == tag) {
+          E->key = key;
+          E->model = model;
+          G.cache_own = h + 1u;
+          G.claims++;
+        }
+      } else if (!dying && old && !same) {
+        atomicCAS(&E->tag, tag, jb | TAG_DYING | (unsigned long long)epoch);
+      }
+    }
+  }
+  return hit;
 }
 
 __device__ __forceinline__ void seat_game(const Dev& D, Game& G, uint32_t r) {
@@ -661,12 +741,30 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
   return result;
 }
 
+// the model that has to evaluate `leaf` for the game in G (mcts.rs:70-76)
+__device__ __forceinline__ uint64_t model_to_play(const Dev& D, const Game& G, Pos leaf) {
+  const bool odd = (c4::popc64(leaf.mask) & 1) != 0;
+  if (G.reseated) return odd ? D.p1[G.req] : D.p0[G.req];
+  const Slot* S = D.slots + G.slot;
+  return odd ? S->model1 : S->model0;
+}
+
 // Advance the (up to four) games of this warp until each needs the network (WAIT_NN), has used its
-// in-kernel budget of terminal-leaf simulations (CONTINUE), needs its tree compacted (NEED_MOVE) or
-// holds no game (IDLE).  `running` marks the lanes of live games; returns the new state.
-__device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game& G, bool running, uint32_t state) {
+// in-kernel budget of simulations that need no network row (CONTINUE), needs its tree compacted
+// (NEED_MOVE) or holds no game (IDLE).  `running` marks the lanes of live games, `pend` those that
+// hold an evaluation (x, vq, vn) of their leaf G.leaf that still has to be applied: the network's
+// answer on entry, an evaluation-cache hit later on.  Returns the new state.
+__device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game& G, bool running, uint32_t state,
+                                              uint32_t epoch, bool pend, float x, float vq, float vn) {
   uint32_t inl = 0;
   for (;;) {
+    if (__any_sync(FULL, pend)) {
+      if (!apply_answer(D, L, G, pend, x, vq, vn)) {
+        if (L.l == 0) D.g->error = C4A0_E_ENGINE;
+        running = false;
+      }
+      pend = false;
+    }
     const bool need_move = running && G.rootN >= D.n_iter;  // self_play.rs:283: after every simulation
     if (__any_sync(FULL, need_move)) {
       const int r = play_move(D, L, G, need_move);
@@ -689,8 +787,14 @@ __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game
     float tqp, tqn;
     const int t = c4::terminal_value(leaf, D.c_pen, &tqp, &tqn);
     const bool term = running && t != c4::NONE;
-    if (running && t == c4::NONE) {
-      G.leaf = leaf;
+    const bool ask = running && t == c4::NONE;
+    if (ask) G.leaf = leaf;
+    if (D.cache != nullptr && __any_sync(FULL, ask)) {
+      // a position this job has evaluated before: the stored answer is applied in this tick
+      pend = cache_lookup(D, L, G, ask, leaf, ask ? model_to_play(D, G, leaf) : 0ull, epoch, x, vq, vn);
+      if (pend) inl++;
+    }
+    if (ask && !pend) {
       running = false;
       state = ST_WAIT_NN;
     }
@@ -819,20 +923,32 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   if (__any_sync(FULL, live)) {  // (no early return: every warp takes part in closing the tick below)
   const long long t1 = prof ? clock64() : 0;
   const bool waiting = live && st == ST_WAIT_NN;
-  bool running = live;
-  if (__any_sync(FULL, waiting)) {
-    // the row holding this game's answer was drawn by the leader of its key during the last tick
-    const uint32_t row = waiting ? (uint32_t)D.rowtag[G.nn_leader] : 0u;
-    if (!apply_network(D, L, G, waiting, row)) {
-      if (L.l == 0) D.g->error = C4A0_E_ENGINE;
-      running = false;
+  // the row holding this game's answer was drawn by the leader of its key during the last tick
+  float x = 0.0f, vq = 0.0f, vn = 0.0f;
+  if (waiting) {
+    const uint32_t row = (uint32_t)D.rowtag[G.nn_leader];
+    x = D.logits[(size_t)row * 7 + (L.l < 7 ? L.l : 6)];
+    vq = D.qp[row];
+    vn = D.qn[row];
+    if (G.cache_own) {  // the evaluation-cache entry this game claimed when it asked: now readable from the next tick on
+      EvalEntry* E = D.cache + (G.cache_own - 1u);
+      if (L.l < 7)
+        E->logit[L.l] = x;
+      else
+        *reinterpret_cast<float2*>(&E->qp) = make_float2(vq, vn);
     }
   }
+  G.cache_own = 0u;
   const long long t2 = prof ? clock64() : 0;
-  const uint32_t ns = run_games(D, L, G, running, st);
+  const uint32_t ns = run_games(D, L, G, live, st, epoch, waiting, x, vq, vn);
   const long long t3 = prof ? clock64() : 0;
   const unsigned nwait = __popc(__ballot_sync(FULL, live && L.l == 0 && ns == ST_WAIT_NN));
   if ((threadIdx.x & 31) == 0 && nwait) atomicAdd(&D.g->wait_acc, nwait);
+  if (D.cache != nullptr) {
+    const unsigned nh = __reduce_add_sync(FULL, L.l == 0 ? G.hits : 0u), nc = __reduce_add_sync(FULL, L.l == 0 ? G.claims : 0u);
+    if ((threadIdx.x & 31) == 0 && nh) atomicAdd(&D.g->cache_hits, (unsigned long long)nh);
+    if ((threadIdx.x & 31) == 0 && nc) atomicAdd(&D.g->cache_inserts, (unsigned long long)nc);
+  }
   if (live && L.l == 0) {
     store_game(D, G, ns);
     if (ns == ST_NEED_MOVE) push_mover(D, slot);
@@ -841,10 +957,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     if (prof) {  // cycles of this game's warp per phase (c4a0_engine_debug_phases)
       uint32_t* o = D.dbg + (size_t)slot * 8;
       o[0] = (uint32_t)(t1 - t0);         // load slot state
-      o[1] = (uint32_t)(t2 - t1);         // softmax + expand + backup
+      o[1] = (uint32_t)(t2 - t1);         // fetch the network's answer
       o[2] = G.sims;                      // simulations this tick
-      o[3] = (uint32_t)(t3 - t2);         // moves + selection passes + terminal backups
-      o[4] = G.term;                      // ... of which terminal-leaf simulations
+      o[3] = (uint32_t)(t3 - t2);         // softmax/expand/backup, moves, selection passes, in-kernel simulations
+      o[4] = G.term + G.hits;             // ... of which needed no network row (terminal leaf, cache hit)
       o[5] = G.len;                       // depth of the selected leaf
       o[6] = (uint32_t)(clock64() - t3);  // store
       o[7] = (uint32_t)(clock64() - t0);  // whole tick
@@ -1115,7 +1231,8 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   D.n_iter = cfg->n_mcts_iterations;
   // index 0 is unused; a tree holds at most n_iter expanded nodes, so n_iter + 2 always suffices
   D.cap = cfg->arena_blocks ? cfg->arena_blocks : cfg->n_mcts_iterations + 2;
-  D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : 2;
+  const bool use_cache = (cfg->flags & C4A0_FLAG_EVAL_CACHE) != 0;
+  D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : (use_cache ? 4 : 2);
   D.plane_bf16 = cfg->plane_dtype == C4A0_PLANES_BF16;
   D.plane_stride = cfg->plane_stride ? cfg->plane_stride : 84;
   D.dedup = (cfg->flags & C4A0_FLAG_NO_DEDUP) ? 0u : 1u;
@@ -1135,7 +1252,28 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   DA(D.s_policy, R * MAXS * 7); DA(D.s_qp, R * MAXS); DA(D.s_qn, R * MAXS);
   DA(D.g, 1); DA(D.movers, S);
   DA(e->scratch4, 4); DA(e->row_mask, S); DA(e->row_value, S); DA(e->row_model, S);
+  size_t CE = 0;
+  if (use_cache) {
+    // default: room for 8 entries per simulation of one move of every resident game (a job evaluates a
+    // few times that many distinct positions; later answers replace earlier ones), at most a quarter of
+    // the memory that is still free
+    size_t want = cfg->eval_cache_entries ? cfg->eval_cache_entries : S * (size_t)cfg->n_mcts_iterations * 8;
+    if (want < 1024) want = cfg->eval_cache_entries ? (want < 2 ? 2 : want) : 1024;
+    CE = 1;
+    while (CE < want && CE < ((size_t)1 << 31)) CE <<= 1;
+    if (!cfg->eval_cache_entries) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        c4a0_engine_destroy(e);
+        return fail(C4A0_E_CUDA, "cudaMemGetInfo failed");
+      }
+      while (CE > 1024 && CE * sizeof(EvalEntry) > free_b / 4) CE >>= 1;
+    }
+    D.cache_mask = (uint32_t)(CE - 1);
+    DA(D.cache, CE);
+  }
   cudaError_t err = cudaMemset(D.slots, 0, S * sizeof(Slot));
+  if (err == cudaSuccess && CE) err = cudaMemset(D.cache, 0, CE * sizeof(EvalEntry));
   if (err == cudaSuccess) err = cudaMemset(D.g, 0, sizeof(Globals));
   if (err == cudaSuccess) err = cudaMemset(D.table, 0, T * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMallocHost((void**)&e->h_globals, sizeof(Globals));
@@ -1204,6 +1342,11 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
   }
   CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
   CK(cudaMemsetAsync(D.rowtag, 0, (size_t)D.n_slots * sizeof(unsigned long long), s));
+  D.job = (D.job + 1u) & 0x7fffffffu;  // entries of the evaluation cache written by earlier jobs become stale
+  if (D.job == 0u) {                   // (after 2^31 jobs: start over with an empty table)
+    D.job = 1u;
+    if (D.cache) CK(cudaMemsetAsync(D.cache, 0, ((size_t)D.cache_mask + 1) * sizeof(EvalEntry), s));
+  }
   k_init_globals<<<1, 1, 0, s>>>(D, n);
   k_init<<<blocks_for(D.n_slots, 256), 256, 0, s>>>(D, n);
   CK(cudaGetLastError());
@@ -1307,6 +1450,8 @@ int c4a0_engine_stats(c4a0_engine* e, c4a0_stats* out, void* stream) {
   out->steps = e->steps;
   out->compacted_blocks = g.compacted_blocks;
   out->compactions = g.compactions;
+  out->cache_hits = g.cache_hits;
+  out->cache_inserts = g.cache_inserts;
   return 0;
 }
 

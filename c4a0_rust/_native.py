@@ -306,19 +306,20 @@ for _cls in (GameMetadata, Sample, GameResult, PlayGamesResult):
 _SESSION = {"key": None, "sess": None}
 
 
-def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes, offset=0):
+def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes, offset=0, eval_cache=False):
     """One engine (tree arenas, NN I/O tensors, captured graphs) is kept between calls with the same
     configuration — a training loop calls play_games once per generation with identical settings."""
     from c4a0_b200 import selfplay
     from c4a0_b200.selfplay import SelfPlaySession
 
-    knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks")))
-    key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, offset, n_lanes, knobs)
+    knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks", "eval_cache_entries")))
+    key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, offset, n_lanes, knobs, eval_cache)
     if _SESSION["key"] == key and _SESSION["sess"] is not None and _SESSION["cap"] >= n_req:
         return _SESSION["sess"]
     close_cached_session()
     sess = SelfPlaySession(n_slots, n_req, n_iter, c_expl, c_pen, plane_dtype=dtype, device=device,
-                           plane_stride=stride, plane_offset=offset, n_lanes=n_lanes)
+                           plane_stride=stride, plane_offset=offset, n_lanes=n_lanes, eval_cache=eval_cache,
+                           eval_cache_entries=selfplay.DEFAULTS["eval_cache_entries"])
     _SESSION.update(key=key, sess=sess, cap=n_req)
     return sess
 
@@ -348,7 +349,8 @@ def play_games(
     """
     import torch
 
-    from c4a0_b200.selfplay import DeviceEvaluator, MultiModelEvaluator, SelfPlaySession
+    from c4a0_b200 import selfplay
+    from c4a0_b200.selfplay import DeviceEvaluator, MultiModelEvaluator
 
     reqs = list(reqs)
     for r in reqs:
@@ -378,7 +380,7 @@ def play_games(
         sess = _session(
             n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
             py_eval_pos_cb.dtype, torch.cuda.current_device(), py_eval_pos_cb.plane_stride, None,
-            getattr(py_eval_pos_cb, "plane_offset", 0),
+            getattr(py_eval_pos_cb, "plane_offset", 0), bool(selfplay.DEFAULTS["eval_cache"]),
         )
         try:
             soa, info = sess.play(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define C4A0_ABI_VERSION 1
+#define C4A0_ABI_VERSION 2
 #define C4A0_N_ROWS 6               /* lib.rs:29 */
 #define C4A0_N_COLS 7               /* lib.rs:28 */
 #define C4A0_BUF_N_CHANNELS 2       /* lib.rs:30 */
@@ -63,18 +63,30 @@ typedef struct {
   float c_exploration;
   float c_ply_penalty;
   uint32_t plane_dtype;        /* C4A0_PLANES_F32 | C4A0_PLANES_BF16 */
-  uint32_t max_inline_sims;    /* terminal-leaf simulations a game may run inside one step (0 = 2) */
+  uint32_t max_inline_sims;    /* simulations that need no network row (terminal leaf, evaluation-cache hit) a game may
+                                  run inside one step (0 = default: 2, or 4 with the evaluation cache) */
   int32_t device;              /* CUDA device ordinal */
   uint32_t plane_stride;       /* elements between consecutive rows of planes_dev (0 = 84; a multiple of
                                   4, >= 84; elements 84.. of a row are never written) */
   uint32_t flags;              /* C4A0_FLAG_* */
   uint32_t arena_blocks;       /* tree blocks (160 B) per arena half per game; 0 = n_mcts_iterations + 2,
                                   the minimum.  Larger halves make re-rooting copy-free until a half fills. */
+  uint32_t eval_cache_entries; /* with C4A0_FLAG_EVAL_CACHE: entries (96 B each) of the evaluation cache, rounded
+                                  up to a power of two; 0 = sized from n_slots * n_mcts_iterations and the
+                                  free device memory */
 } c4a0_config;
 
 /* Evaluate every waiting leaf even when several games wait on the same (position, model); by default
  * equal leaves share one network row, as the reference's NN thread does (self_play.rs:203-208). */
 #define C4A0_FLAG_NO_DEDUP 1u
+/* Keep every network answer of the current set_requests() job in a device table keyed by (position,
+ * model) and answer later requests for the same key from it, inside the tick, instead of sending the
+ * leaf to the network again (transpositions within a tree, the same position reached by other games
+ * or again after a move).  Off by default because it assumes what the reference does not: that the
+ * evaluator is a pure function of (model, position) for the duration of the job.  With such an
+ * evaluator the games are identical with and without the cache; only n_rows per tick and the
+ * number of ticks shrink.  The table is emptied by every set_requests(). */
+#define C4A0_FLAG_EVAL_CACHE 2u
 
 typedef struct {
   uint32_t n_requests;   /* games submitted */
@@ -100,6 +112,8 @@ typedef struct {
   uint64_t steps;              /* c4a0_engine_step() calls since set_requests() */
   uint64_t compacted_blocks;   /* tree blocks copied when an arena half filled up */
   uint64_t compactions;        /* number of such copies (re-roots that fit the arena copy nothing) */
+  uint64_t cache_hits;         /* leaves answered from the evaluation cache (C4A0_FLAG_EVAL_CACHE) */
+  uint64_t cache_inserts;      /* network answers stored in it */
 } c4a0_stats;
 
 const char *c4a0_last_error(void);

@@ -26,15 +26,15 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in L.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.c4a0_abi_version() == 1
+    assert lib.c4a0_abi_version() == 2
 
 
 def test_struct_sizes_match_the_header():
     from c4a0_b200 import _lib as L
 
-    assert C.sizeof(L.Config) == 11 * 4
+    assert C.sizeof(L.Config) == 12 * 4
     assert C.sizeof(L.Progress) == 7 * 4
-    assert C.sizeof(L.Stats) == 12 * 8
+    assert C.sizeof(L.Stats) == 14 * 8
     assert C.sizeof(L.RunReport) == 5 * 8 + 4 * 8 + 8 + 2 * 8 + 32 * 8
     assert C.sizeof(L.NNGraph) == 16
 
