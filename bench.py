@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-eval-cache", action="store_true",
                     help="send every leaf to the network even if this job has evaluated the position before")
     ap.add_argument("--eval-cache-entries", type=int, default=0, help="entries of the evaluation cache (0 = engine default)")
+    ap.add_argument("--no-ablation", action="store_true", help="skip the extra step without the evaluation cache")
     ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
     ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")
     ap.add_argument("--host-loop", choices=["native", "python"], default="native",
@@ -390,6 +391,22 @@ def run_ours(args):
         "bucket_launches": [int(sum(r[1].report.get("bucket_launches", [0] * 32)[i] for r in runs)) for i in range(20)],
         "ticks_per_step": ticks / max(1, args.steps),
     }
+    if world == 1 and not args.no_eval_cache and not args.no_ablation:
+        # the same job with every leaf sent to the network (untimed warm-up step first: new engine, new graphs)
+        try:
+            selfplay.DEFAULTS["eval_cache"] = False
+            one_step()
+            torch.cuda.synchronize()
+            dt, info, n_pos, _ = one_step()
+            line["without_eval_cache"] = {
+                "value": n_pos / info.device_s, "unit": UNIT, "ms_per_step": 1e3 * info.device_s, "steps": 1,
+                "e2e_value": n_pos / dt, "ticks_per_step": info.ticks, "nn_rows": info.stats["nn_evals"],
+            }
+        except Exception as exc:
+            line["without_eval_cache"] = {"value": None, "error": str(exc)}
+        finally:
+            selfplay.DEFAULTS["eval_cache"] = True
+            c4a0_rust._native.close_cached_session()
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)

@@ -14,7 +14,7 @@ from . import build as _build
 
 N_ROWS, N_COLS, BUF_N_CHANNELS, PLANE_LEN, MAX_SAMPLES = 6, 7, 2, 84, 43
 PLANES_F32, PLANES_BF16 = 0, 1
-EVAL_UNIFORM, EVAL_HASH = 0, 1
+EVAL_UNIFORM, EVAL_HASH, EVAL_HASH_FLAT = 0, 1, 2
 ROW_IDLE, ROW_WAIT_NN, ROW_CONTINUE, ROW_NEED_MOVE = 0, 1, 2, 3
 MATH_LOGF, MATH_EXPF = 0, 1
 E_INVALID, E_CUDA, E_NOMEM, E_ENGINE = -1, -2, -3, -4

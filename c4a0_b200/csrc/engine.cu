@@ -1063,11 +1063,13 @@ __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float*
   uint64_t h = splitmix64(mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(value ^ model));
   for (int k = 0; k < 7; k++) {
     uint64_t hk = splitmix64(h + (uint64_t)k);
-    logits[(size_t)row * 7 + k] = (float)(uint32_t)(hk >> 48) * (1.0f / 8192.0f) - 4.0f;
+    const float lg = (float)(uint32_t)(hk >> 48) * (1.0f / 8192.0f) - 4.0f;
+    logits[(size_t)row * 7 + k] = kind == C4A0_EVAL_HASH_FLAT ? lg * 0.0625f : lg;
   }
   uint64_t hq = splitmix64(h + 7);
-  qp[row] = ((float)(uint32_t)((hq >> 48) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * 0.75f;
-  qn[row] = ((float)(uint32_t)((hq >> 32) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * 0.75f;
+  const float qs = kind == C4A0_EVAL_HASH_FLAT ? 0.1f : 0.75f;
+  qp[row] = ((float)(uint32_t)((hq >> 48) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * qs;
+  qn[row] = ((float)(uint32_t)((hq >> 32) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * qs;
 }
 
 __global__ void k_gather_rows(Dev D, uint64_t* mask, uint64_t* value, uint64_t* model) {
@@ -1404,7 +1406,7 @@ int c4a0_engine_debug_phases(c4a0_engine* e, void* stream, uint32_t* out8_per_sl
 
 int c4a0_engine_eval_builtin(c4a0_engine* e, int kind, void* stream) {
   if (!e || !e->io_bound) return fail(C4A0_E_INVALID, "engine not bound");
-  if (kind != C4A0_EVAL_UNIFORM && kind != C4A0_EVAL_HASH) return fail(C4A0_E_INVALID, "bad evaluator kind");
+  if (kind != C4A0_EVAL_UNIFORM && kind != C4A0_EVAL_HASH && kind != C4A0_EVAL_HASH_FLAT) return fail(C4A0_E_INVALID, "bad evaluator kind");
   k_eval_builtin<<<blocks_for(e->D.n_slots, 256), 256, 0, (cudaStream_t)stream>>>(e->D, kind, e->b_logits, e->b_qp, e->b_qn);
   CK(cudaGetLastError());
   return 0;

@@ -48,7 +48,9 @@ enum { C4A0_PLANES_F32 = 0, C4A0_PLANES_BF16 = 1 };
 
 /* Synthetic evaluators that stand in for the network in parity tests and kernel benchmarks
  * (the reference's tests do the same: mcts.rs:469-485, self_play.rs:386-403). */
-enum { C4A0_EVAL_UNIFORM = 0, C4A0_EVAL_HASH = 1 };
+/* C4A0_EVAL_HASH_FLAT: the hash evaluator scaled to what a freshly initialised network answers (logits
+ * within +-0.25, values within +-0.1): broad trees, for profiling the tree kernels at the bench's shape. */
+enum { C4A0_EVAL_UNIFORM = 0, C4A0_EVAL_HASH = 1, C4A0_EVAL_HASH_FLAT = 2 };
 
 /* Row (= slot) states as reported by c4a0_engine_fetch_rows(). */
 enum { C4A0_ROW_IDLE = 0, C4A0_ROW_WAIT_NN = 1, C4A0_ROW_CONTINUE = 2, C4A0_ROW_NEED_MOVE = 3 };
