@@ -182,6 +182,8 @@ struct Dev {  // passed to kernels by value
   unsigned long long* table;       // [table_mask+1]: epoch << 32 | leader slot
   EvalEntry* cache;                // [cache_mask+1] evaluation cache, nullptr = off
   uint32_t cache_mask, job;
+  const float* ln_tab;             // [ln_n] c4_logf((float)i): visit counts are small integers
+  uint32_t ln_n;
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
@@ -475,7 +477,8 @@ __device__ __forceinline__ Pos select_leaf(const Dev& D, const Lanes& L, Game& G
       ch = B->child[L.l];
     }
     const unsigned legal = c4::legal_mask(pos.mask);
-    const float lnp = c4::c4_logf((float)np);  // ln(parent visits), mcts.rs:378-379
+    // ln(parent visits), mcts.rs:378-379; the table holds the same function's values
+    const float lnp = np < D.ln_n ? __ldg(D.ln_tab + np) : c4::c4_logf((float)np);
     const float u = uct(n, qs, pr, lnp, D.c_expl);
     const bool ok = act && L.l < 7 && ((legal >> L.l) & 1u);
     const uint32_t key = ok ? ordkey(u) : 0u;
@@ -990,6 +993,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   }
 }
 
+__global__ void k_ln_table(float* tab, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tab[i] = c4::c4_logf((float)i);
+}
+
 // Seat the first min(n_slots, n_req) games (self_play.rs:55-58).
 __global__ void k_init_globals(Dev D, uint32_t n_req) {  // runs alone, before k_init
   Globals z;
@@ -1274,7 +1282,15 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
     D.cache_mask = (uint32_t)(CE - 1);
     DA(D.cache, CE);
   }
-  cudaError_t err = cudaMemset(D.slots, 0, S * sizeof(Slot));
+  {  // a node is selected through with at most n_iter visits
+    float* tab = nullptr;
+    D.ln_n = cfg->n_mcts_iterations < (1u << 20) ? cfg->n_mcts_iterations + 2 : (1u << 20);
+    DA(tab, D.ln_n);
+    k_ln_table<<<blocks_for(D.ln_n, 256), 256>>>(tab, D.ln_n);
+    D.ln_tab = tab;
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemset(D.slots, 0, S * sizeof(Slot));
   if (err == cudaSuccess && CE) err = cudaMemset(D.cache, 0, CE * sizeof(EvalEntry));
   if (err == cudaSuccess) err = cudaMemset(D.g, 0, sizeof(Globals));
   if (err == cudaSuccess) err = cudaMemset(D.table, 0, T * sizeof(unsigned long long));
@@ -1284,6 +1300,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
     memset((void*)e->h_status, 0, sizeof(HostStatus));
     err = cudaHostGetDevicePointer((void**)&D.status, (void*)e->h_status, 0);
   }
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();  // the fills above ran on the default stream
   if (err != cudaSuccess) {
     c4a0_engine_destroy(e);
     return fail(C4A0_E_CUDA, "engine init failed: %s", cudaGetErrorString(err));
