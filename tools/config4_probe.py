@@ -21,7 +21,7 @@ model = ConnectFourNet(ModelConfig(n_residual_blocks=1, conv_filter_size=width, 
 ev = DeviceEvaluator.from_model(model, torch.bfloat16)
 t0 = time.time()
 sess = SelfPlaySession(n, n, sims, 6.6, 0.01, plane_dtype=torch.bfloat16, plane_stride=ev.plane_stride,
-                       plane_offset=ev.plane_offset, n_lanes=1)
+                       plane_offset=ev.plane_offset, n_lanes=1, eval_cache="--cache" in sys.argv)
 ln = sess.lanes[0]
 print("engine bytes %.1f GB, create %.1f s, arena_blocks/half %d" % (ln.engine.device_bytes / 1e9, time.time() - t0, ln.engine.cfg.arena_blocks), flush=True)
 ids = np.arange(n)

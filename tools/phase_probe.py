@@ -15,17 +15,17 @@ torch.manual_seed(1337)
 model = ConnectFourNet(default_config()).cuda().eval()
 ev = DeviceEvaluator.from_model(model, torch.bfloat16)
 sess = SelfPlaySession(n, n, sims, 6.6, 0.01, plane_dtype=torch.bfloat16, plane_stride=ev.plane_stride,
-                       plane_offset=ev.plane_offset, n_lanes=1)
+                       plane_offset=ev.plane_offset, n_lanes=1, eval_cache="--no-cache" not in sys.argv)
 ln = sess.lanes[0]
 ids = np.arange(n)
 z = np.zeros(n, np.uint64)
-names = ["load", "apply", "sims", "run", "term_sims", "depth", "store", "total"]
+names = ["load", "fetch_answer", "sims", "run", "inline_sims", "depth", "store", "total"]
 with torch.cuda.stream(ln.stream):
     s = ln.stream.cuda_stream
     ln.engine.set_requests(ids, z, z, s)
     for tick in range(1, 20001):
         ln.evaluate(ev, n)
-        if tick in (300, 700, 1500, 3000, 5000, 8000, 11000, 14000):
+        if tick in (300, 700, 1500, 3000, 5000, 7000, 9000, 10500):
             d = ln.engine.debug_phases(s).astype(np.int64)
             act = d[:, 7] > 0
             a = d[act]
