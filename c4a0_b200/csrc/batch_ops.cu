@@ -10,6 +10,8 @@
 #include "c4_math.cuh"
 #include "c4_rng.cuh"
 #include "c4_rules.cuh"
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace c4host {
@@ -100,9 +102,55 @@ __global__ void k_sample(const float* policy, const float* temperature, const ui
   column[i] = c4::weighted_sample7(t, seed[i]);
 }
 
+// nn.py:116-130 — log_softmax(policy), tanh(values), written where the engine reads them
+template <typename T>
+__device__ __forceinline__ float head_ld(const T* p);
+template <>
+__device__ __forceinline__ float head_ld<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float head_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__global__ void k_head_epilogue(const T* __restrict__ pol, const T* __restrict__ val, uint32_t ldp, uint32_t ldv,
+                                uint32_t rows, float* __restrict__ logits, float* __restrict__ qp, float* __restrict__ qn) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float x[7];
+  float mx = -c4::f32_inf();
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    x[k] = head_ld(pol + (size_t)r * ldp + k);
+    mx = fmaxf(mx, x[k]);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 7; k++) s += expf(x[k] - mx);
+  const float lse = mx + logf(s);
+#pragma unroll
+  for (int k = 0; k < 7; k++) logits[(size_t)r * 7 + k] = x[k] - lse;
+  qp[r] = tanhf(head_ld(val + (size_t)r * ldv));
+  qn[r] = tanhf(head_ld(val + (size_t)r * ldv + 1));
+}
+
 }  // namespace
 
 extern "C" {
+
+int c4a0_head_epilogue(const void* policy_head, const void* value_head, uint32_t dtype, uint32_t ld_policy,
+                       uint32_t ld_value, uint32_t rows, float* logits, float* qp, float* qn, void* stream) {
+  if (!policy_head || !value_head || !logits || !qp || !qn) return fail(C4A0_E_INVALID, "null argument");
+  if (dtype > C4A0_PLANES_BF16 || ld_policy < 7 || ld_value < 2) return fail(C4A0_E_INVALID, "bad head layout");
+  if (rows == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (rows + 127u) / 128u;
+  if (dtype == C4A0_PLANES_BF16)
+    k_head_epilogue<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)policy_head, (const __nv_bfloat16*)value_head,
+                                                        ld_policy, ld_value, rows, logits, qp, qn);
+  else
+    k_head_epilogue<float><<<grid, 128, 0, s>>>((const float*)policy_head, (const float*)value_head, ld_policy, ld_value,
+                                                rows, logits, qp, qn);
+  CK(cudaGetLastError());
+  return 0;
+}
 
 const char* c4a0_last_error(void) { return c4host::last_error(); }
 int c4a0_abi_version(void) { return C4A0_ABI_VERSION; }

@@ -130,6 +130,31 @@ def _bn_scale_shift(bn, repeat: int = 1):
     return s.repeat_interleave(repeat), t.repeat_interleave(repeat)
 
 
+def _output_stage(pol: torch.Tensor, val: torch.Tensor, out=None):
+    """log_softmax over the 7 policy outputs, tanh of the two values (reference nn.py:116-130) from the
+    last linear layers' outputs `pol` [B, >=7] and `val` [B, >=2].  With out = (logits [B,7] f32,
+    q_penalty [B] f32, q_no_penalty [B] f32) on CUDA, one kernel of the engine library writes them in
+    place (c4a0_head_epilogue) and `out` is returned."""
+    if out is None:
+        logits = pol[:, :7].float()
+        q = torch.tanh(val[:, :2].float())
+        return torch.log_softmax(logits, dim=1), q[:, 0], q[:, 1]
+    from . import _lib as L
+
+    logits, qp, qn = out
+    rows = pol.shape[0]
+    ok = (pol.is_cuda and pol.dtype == val.dtype and pol.dtype in (torch.float32, torch.bfloat16)
+          and pol.stride(1) == 1 and val.stride(1) == 1
+          and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == rows for t in out))
+    if not ok:
+        raise ValueError("output buffers must be contiguous float32 CUDA tensors with one row per input row")
+    L.check(L.lib().c4a0_head_epilogue(
+        pol.data_ptr(), val.data_ptr(), L.PLANES_BF16 if pol.dtype == torch.bfloat16 else L.PLANES_F32,
+        pol.stride(0), val.stride(0), rows, logits.data_ptr(), qp.data_ptr(), qn.data_ptr(),
+        torch.cuda.current_stream(pol.device).cuda_stream))
+    return out
+
+
 class FoldedNet(nn.Module):
     """Inference-only restatement of a trained/initialised `ConnectFourNet` as dense GEMMs.
 
@@ -247,7 +272,7 @@ class FoldedNet(nn.Module):
             return torch._addmm_activation(b, x, w)  # cuBLASLt bias+ReLU epilogue
         return torch.relu(torch.addmm(b, x, w))
 
-    def forward(self, planes: torch.Tensor):
+    def forward(self, planes: torch.Tensor, out=None):
         """planes: [B, IN_PAD] (engine layout, zero padded) or [B,2,6,7]."""
         if planes.dim() == 4:
             x0 = planes.new_zeros(planes.shape[0], self.IN_PAD)
@@ -268,9 +293,7 @@ class FoldedNet(nn.Module):
             hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
         for i in range(self.n_v):
             hv = self._lin_relu(hv, getattr(self, f"wv{i}"), getattr(self, f"bv{i}"))
-        logits = torch.addmm(self.bpf, hp, self.wpf)[:, :7].float()
-        q = torch.tanh(torch.addmm(self.bvf, hv, self.wvf)[:, :2].float())
-        return torch.log_softmax(logits, dim=1), q[:, 0], q[:, 1]
+        return _output_stage(torch.addmm(self.bpf, hp, self.wpf), torch.addmm(self.bvf, hv, self.wvf), out)
 
     def flops_per_position(self) -> int:
         total = 0
@@ -340,7 +363,7 @@ class FusedNet(FoldedNet):
         self.f_b2.copy_(bh + b0[F:] @ wh)
         return self
 
-    def forward(self, buf: torch.Tensor):
+    def forward(self, buf: torch.Tensor, out=None):
         """buf: [B, F + 96]; columns F..F+84 hold the input planes (rest of the tail zero).  Columns
         0..F are overwritten.  A [B,2,6,7] tensor is accepted too (copied into a fresh buffer)."""
         F = self.F
@@ -365,9 +388,7 @@ class FusedNet(FoldedNet):
             hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
         for i in range(self.n_v):
             hv = self._lin_relu(hv, getattr(self, f"wv{i}"), getattr(self, f"bv{i}"))
-        logits = torch.addmm(self.bpf, hp, self.wpf)[:, :7].float()
-        q = torch.tanh(torch.addmm(self.bvf, hv, self.wvf)[:, :2].float())
-        return torch.log_softmax(logits, dim=1), q[:, 0], q[:, 1]
+        return _output_stage(torch.addmm(self.bpf, hp, self.wpf), torch.addmm(self.bvf, hv, self.wvf), out)
 
     def _probe_strided_out(self, buf: torch.Tensor) -> bool:
         """Does the cuBLASLt epilogue path accept a row-strided `out`?  Checked once, numerically."""

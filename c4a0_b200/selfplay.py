@@ -95,6 +95,20 @@ class DeviceEvaluator:
             planes = planes.view(-1, 2, 6, 7)
         return self.fn(planes)
 
+    def into(self, planes: torch.Tensor, logits: torch.Tensor, qp: torch.Tensor, qn: torch.Tensor) -> None:
+        """Evaluate `planes` and leave the answers in the engine's buffers.  The folded network forms
+        write them with one fused output kernel (nn._output_stage); anything else is copied."""
+        from .nn import FoldedNet
+
+        rows = planes.shape[0]
+        if isinstance(self.fn, FoldedNet):
+            self.fn(planes, out=(logits, qp, qn))
+            return
+        pol, a, b = self(planes)
+        logits.copy_(pol.reshape(rows, 7))
+        qp.copy_(a.reshape(rows))
+        qn.copy_(b.reshape(rows))
+
 
 class MultiModelEvaluator:
     """Several networks in one batch (tournaments: `GameMetadata.player0_id != player1_id`,
@@ -194,6 +208,9 @@ class _Lane:
         with torch.no_grad():
             if isinstance(evaluator, MultiModelEvaluator):
                 pol, a, b = evaluator(self.planes[:rows], self.row_model[:rows])
+            elif isinstance(evaluator, DeviceEvaluator):
+                evaluator.into(self.planes[:rows], self.logits[:rows], self.qp[:rows], self.qn[:rows])
+                return
             else:
                 pol, a, b = evaluator(self.planes[:rows])
             self.logits[:rows].copy_(pol.reshape(rows, 7))

@@ -272,6 +272,17 @@ int c4a0_softmax_batch(int device, const float *logits, const uint32_t *legal, f
 int c4a0_sample_batch(int device, const float *policy, const float *temperature,
                       const uint64_t *seed, float *tempered, int32_t *column, size_t n);
 
+/* Output stage of the network (src/c4a0/nn.py:116-130: log_softmax over the 7 policy outputs, tanh of
+ * the two value outputs), straight into the buffers bound with c4a0_engine_bind_io(): one kernel
+ * instead of the casts, slices, softmax, tanh and copies PyTorch would launch, which is what a tick
+ * with a small batch spends a third of its network time on.  All pointers are DEVICE pointers; the
+ * kernel is enqueued on `stream` (capturable into a CUDA graph).
+ *   policy_head [rows][ld_policy], value_head [rows][ld_value]: the last linear layers' outputs
+ *   (>= 7 and >= 2 valid columns), dtype C4A0_PLANES_F32 or C4A0_PLANES_BF16. */
+int c4a0_head_epilogue(const void *policy_head, const void *value_head, uint32_t dtype,
+                       uint32_t ld_policy, uint32_t ld_value, uint32_t rows, float *logits_dev,
+                       float *q_penalty_dev, float *q_no_penalty_dev, void *stream);
+
 /* The same math compiled for the host (no GPU needed); used to pin the restated logf/expf and the
  * sampler against libm / the oracle in the CPU test-suite. */
 void c4a0_host_logf(const float *in, float *out, size_t n);
