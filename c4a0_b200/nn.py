@@ -328,8 +328,6 @@ class FusedNet(FoldedNet):
         self.plane_offset = self.F
         self._refuse()
         self._strided_out_ok = None
-        self.side_streams = True  # value head on a second stream (a parallel branch once captured in a graph)
-        self._side = {}
 
     @staticmethod
     def supports(model: ConnectFourNet) -> bool:
@@ -386,25 +384,6 @@ class FusedNet(FoldedNet):
             buf[:, :F] = torch.relu(torch.addmm(self.f_b1, x0, self.f_w1))
             y = torch.relu(torch.addmm(self.f_b2, buf, self.f_w2))
         hp, hv = y[:, :F], y[:, F:]
-        if buf.is_cuda and self.side_streams:
-            # the value head (shorter) runs beside the policy head: in a captured graph the two are
-            # parallel branches, which takes a launch off the critical path of a small batch
-            cur = torch.cuda.current_stream(buf.device)
-            side = self._side.get(buf.device)
-            if side is None:
-                side = self._side[buf.device] = torch.cuda.Stream(device=buf.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                for i in range(self.n_v):
-                    hv = self._lin_relu(hv, getattr(self, f"wv{i}"), getattr(self, f"bv{i}"))
-                val = torch.addmm(self.bvf, hv, self.wvf)
-            for i in range(self.n_p):
-                hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
-            pol = torch.addmm(self.bpf, hp, self.wpf)
-            cur.wait_stream(side)
-            val.record_stream(cur)
-            y.record_stream(side)
-            return _output_stage(pol, val, out)
         for i in range(self.n_p):
             hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
         for i in range(self.n_v):
