@@ -367,8 +367,10 @@ def run_ours(args):
             "wall_ms_per_step": 1e3 * wall_max / max(1, args.steps),
         },
         # our kernels inside the timed region: k_step once per tick, k_tail where a tick needed it,
-        # k_init_globals + k_init + k_tail per call, k_sum_counters per call
-        "gpu_launches": int(ticks + sum(r[1].report.get("tail_launches", 0) for r in runs) + 4 * args.steps * args.lanes),
+        # k_init_globals + k_init + k_tail per call, k_sum_counters per call, and k_head_epilogue (the
+        # network's output stage) once per network graph launch when the folded forms are used
+        "gpu_launches": int(ticks + sum(r[1].report.get("tail_launches", 0) for r in runs) + 4 * args.steps * args.lanes
+                            + (0 if args.no_fold else sum(r[1].report.get("nn_launches", 0) for r in runs))),
         "leaf_evals_per_s": expansions_all / dev_s_max,
         "dedup": {"enabled": not args.no_dedup, "leaf_requests": expansions_all, "unique_rows": evals_all,
                   "rows_launched_incl_bucket_padding": rows_launched_all},
