@@ -169,7 +169,9 @@ struct Dev {  // passed to kernels by value
   uint32_t* row_slot;
   uint64_t* row_model;  // [n_slots] model that has to evaluate the row (mcts.rs:70-76)
   uint32_t* bucket;  // [n_slots] hash-table entry of the slot's waiting leaf
-  unsigned long long* rowtag;  // [n_slots] epoch << 32 | row, written by the slot that leads a key
+  unsigned long long* rowtag;  // [2][n_slots] epoch << 32 | row, written by the slot that leads a key; the half is
+                               // the epoch's parity: a leader may publish its next leaf while followers of its last
+                               // one (warps that start later in the same tick) still look its row up
   // per request
   const uint64_t *game_id, *p0, *p1;
   uint32_t* n_samples;
@@ -277,7 +279,7 @@ __device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64
   D.slots[slot].nn_leader = leader;
   if (leader == slot) {
     const uint32_t row = atomicAdd(&D.g->rows_acc, 1u);
-    D.rowtag[slot] = ((unsigned long long)epoch << 32) | row;
+    D.rowtag[(size_t)(epoch & 1u) * D.n_slots + slot] = ((unsigned long long)epoch << 32) | row;
     D.row_slot[row] = slot;
     D.row_model[row] = kmod;
     write_planes(D, row, Pos{km, kv});
@@ -929,7 +931,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   // the row holding this game's answer was drawn by the leader of its key during the last tick
   float x = 0.0f, vq = 0.0f, vn = 0.0f;
   if (waiting) {
-    const uint32_t row = (uint32_t)D.rowtag[G.nn_leader];
+    const uint32_t row = (uint32_t)D.rowtag[(size_t)((epoch - 1u) & 1u) * D.n_slots + G.nn_leader];  // published last tick
     x = D.logits[(size_t)row * 7 + (L.l < 7 ? L.l : 6)];
     vq = D.qp[row];
     vn = D.qn[row];
@@ -1252,7 +1254,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   size_t T = 1;
   while (T < 2 * S) T <<= 1;
   D.table_mask = (uint32_t)(T - 1);
-  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S); DA(D.row_model, S); DA(D.bucket, S); DA(D.rowtag, S);
+  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S); DA(D.row_model, S); DA(D.bucket, S); DA(D.rowtag, 2 * S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
   DA(D.table, T);
   uint64_t *gid, *p0, *p1;
@@ -1360,7 +1362,7 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
     CK(cudaMemsetAsync(D.s_qn, 0, (size_t)n * MAXS * 4, s));
   }
   CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
-  CK(cudaMemsetAsync(D.rowtag, 0, (size_t)D.n_slots * sizeof(unsigned long long), s));
+  CK(cudaMemsetAsync(D.rowtag, 0, 2 * (size_t)D.n_slots * sizeof(unsigned long long), s));
   D.job = (D.job + 1u) & 0x7fffffffu;  // entries of the evaluation cache written by earlier jobs become stale
   if (D.job == 0u) {                   // (after 2^31 jobs: start over with an empty table)
     D.job = 1u;
@@ -1560,7 +1562,10 @@ int c4a0_engine_slot_info(c4a0_engine* e, uint32_t slot, c4a0_slot_info* out, vo
   out->n_blocks = S.n_alloc ? S.n_alloc - 1 : 0;
   unsigned long long tag = 0;
   if (S.state == ST_WAIT_NN && S.nn_leader < e->D.n_slots) {
-    CK(cudaMemcpyAsync(&tag, e->D.rowtag + S.nn_leader, 8, cudaMemcpyDeviceToHost, s));
+    uint32_t tick = 0;  // the open tick; the leaf was published in the one before
+    CK(cudaMemcpyAsync(&tick, &e->D.g->tick, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(&tag, e->D.rowtag + (size_t)((tick - 1u) & 1u) * e->D.n_slots + S.nn_leader, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }
   out->nn_row = (uint32_t)tag;

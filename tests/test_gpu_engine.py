@@ -325,3 +325,33 @@ def test_native_host_loop_two_lanes_equals_python_loop_one_lane():
         sess.close()
     for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
         assert np.array_equal(getattr(res[0], f), getattr(res[1], f)), f
+
+
+_BIG_ORACLE = {}
+
+
+@pytest.mark.parametrize("cache", [0, 1], ids=["nocache", "cache"])
+def test_more_games_than_one_wave_of_k_step(cache):
+    """40,000 resident games do not fit the GPU at once (one wave of k_step holds ~16,500): warps that
+    start late in a tick still have to find the network row of a leaf whose leading game, in an earlier
+    wave, has already published its next leaf."""
+    _need_gpu()
+    from c4a0_b200 import _lib as L
+
+    n_games, n_iter, c_expl, c_pen = 40000, 6, 6.6, 0.01
+    reqs = [(7 * i + 1, 0, 0) for i in range(n_games)]
+    e, io = _make_engine(n_games, n_games, n_iter, c_expl, c_pen, flags=L.FLAG_EVAL_CACHE if cache else 0)
+    e.set_requests([r[0] for r in reqs], [0] * n_games, [0] * n_games)
+    _run_builtin(e, 1, poll_every=8)
+    got = e.fetch_results()
+    key = (n_games, n_iter)
+    if key not in _BIG_ORACLE:
+        exp = oracle.self_play(reqs, n_games, n_iter, c_expl, c_pen, evaluator="hash")
+        _BIG_ORACLE[key] = (exp.stats, exp.records())
+    ostats, rec = _BIG_ORACLE[key]
+    st = e.stats()
+    assert st["samples"] == ostats["samples"] and st["moves"] == ostats["moves"]
+    assert st["nn_evals"] < st["leaf_requests"]  # equal leaves shared rows: there were followers
+    for i in range(0, n_games, 7):
+        assert _records(got, i) == rec[i], f"game {i}"
+    e.close()
