@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
     ap.add_argument("--no-eval-cache", action="store_true",
                     help="send every leaf to the network even if this job has evaluated the position before")
+    ap.add_argument("--no-speculate", action="store_true", help="do not top small batches up with children of expanded leaves")
+    ap.add_argument("--spec-rows", type=int, default=0, help="rows a small batch is topped up to (0 = engine default)")
     ap.add_argument("--eval-cache-entries", type=int, default=0, help="entries of the evaluation cache (0 = engine default)")
     ap.add_argument("--no-ablation", action="store_true", help="skip the extra step without the evaluation cache")
     ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
@@ -266,6 +268,8 @@ def run_ours(args):
     selfplay.DEFAULTS["max_inline_sims"] = args.max_inline
     selfplay.DEFAULTS["eval_cache"] = not args.no_eval_cache
     selfplay.DEFAULTS["eval_cache_entries"] = args.eval_cache_entries
+    selfplay.DEFAULTS["speculate"] = not args.no_speculate
+    selfplay.DEFAULTS["spec_rows"] = args.spec_rows
     G = args.games
     ids = range(rank * G, (rank + 1) * G)  # weak scaling: every rank plays its own G games
 
@@ -315,6 +319,7 @@ def run_ours(args):
     compactions = sum(r[1].stats.get("compactions", 0) for r in runs)
     cache_hits = sum(r[1].stats.get("cache_hits", 0) for r in runs)
     cache_inserts = sum(r[1].stats.get("cache_inserts", 0) for r in runs)
+    spec_rows = sum(r[1].stats.get("spec_rows", 0) for r in runs)
     engine_gb = runs[-1][1].engine_bytes / 1e9
     ticks = sum(r[1].ticks for r in runs)
     depth = sum(r[1].stats["select_depth_sum"] for r in runs)
@@ -376,7 +381,8 @@ def run_ours(args):
                   "rows_launched_incl_bucket_padding": rows_launched_all},
         # rank 0's counters; the table is emptied at the start of every step (= every play_games call)
         "eval_cache": {"enabled": not args.no_eval_cache, "hits": cache_hits, "inserts": cache_inserts,
-                       "hit_rate_of_expansions": cache_hits / max(1, expansions)},
+                       "hit_rate_of_expansions": cache_hits / max(1, expansions),
+                       "speculate": not (args.no_eval_cache or args.no_speculate), "speculative_rows": spec_rows},
         "compactions_per_step": compactions / max(1, args.steps), "engine_device_gb": engine_gb,
         "lanes": args.lanes, "nn_form": "module" if args.no_fold else ("GEMM-folded (FoldedNet)" if args.plain_fold else "GEMM-folded, epilogue-fused (FusedNet)"),
         "roofline": roofline,

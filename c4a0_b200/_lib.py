@@ -20,6 +20,7 @@ MATH_LOGF, MATH_EXPF = 0, 1
 E_INVALID, E_CUDA, E_NOMEM, E_ENGINE = -1, -2, -3, -4
 FLAG_NO_DEDUP = 1
 FLAG_EVAL_CACHE = 2
+FLAG_SPECULATE = 4
 
 
 class Config(C.Structure):
@@ -36,6 +37,7 @@ class Config(C.Structure):
         ("flags", C.c_uint32),
         ("arena_blocks", C.c_uint32),
         ("eval_cache_entries", C.c_uint32),
+        ("spec_rows", C.c_uint32),
     ]
 
 
@@ -67,6 +69,7 @@ class Stats(C.Structure):
         ("compactions", C.c_uint64),
         ("cache_hits", C.c_uint64),
         ("cache_inserts", C.c_uint64),
+        ("spec_rows", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -148,6 +148,12 @@ struct Globals {  // one instance in device memory
   unsigned long long leaves_total;  // sum over ticks of games waiting for the network
   unsigned long long cache_hits;    // leaves answered by the evaluation cache
   unsigned long long cache_inserts; // entries claimed for a network answer
+  unsigned long long spec_total;    // rows evaluated speculatively (children of expanded leaves)
+  // speculation (C4A0_FLAG_SPECULATE): spare rows of a small batch evaluate children of expanded leaves
+  uint32_t spec_budget;    // speculative rows this tick may draw (set when the previous tick closed)
+  uint32_t spec_acc;       // ... drawn so far (may overshoot the budget; the excess is dropped)
+  uint32_t spec_ok;        // ... that became rows of the batch being built
+  uint32_t spec_count[2];  // entries of spec_list[parity] written in the tick of that parity
 };
 
 struct HostStatus {  // mapped pinned host memory, written by k_tail at the end of every tick
@@ -166,7 +172,7 @@ struct Dev {  // passed to kernels by value
   Slot* slots;
   uint32_t* path;   // [n_slots][PATH_STRIDE]: (block << 3 | column) per level of the selected path
   Block* blocks;    // [n_slots][2][cap]
-  uint32_t* row_slot;
+  uint32_t* row_slot;   // [n_slots] slot whose leaf is the row; 0xffffffff for a speculative row
   uint64_t* row_model;  // [n_slots] model that has to evaluate the row (mcts.rs:70-76)
   uint32_t* bucket;  // [n_slots] hash-table entry of the slot's waiting leaf
   unsigned long long* rowtag;  // [2][n_slots] epoch << 32 | row, written by the slot that leads a key; the half is
@@ -186,6 +192,10 @@ struct Dev {  // passed to kernels by value
   uint32_t cache_mask, job;
   const float* ln_tab;             // [ln_n] c4_logf((float)i): visit counts are small integers
   uint32_t ln_n;
+  uint32_t spec_cap;               // rows a batch may be topped up to with speculative evaluations, 0 = off
+  uint32_t max_inline_spec;        // in-kernel simulation budget while speculation is running
+  uint2* spec_list;                // [2][spec_cap] (row, cache entry) of the speculative rows of a batch
+  uint64_t *row_mask, *row_value;  // [n_slots] position of every row of the batch being built
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
@@ -282,6 +292,8 @@ __device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64
     D.rowtag[(size_t)(epoch & 1u) * D.n_slots + slot] = ((unsigned long long)epoch << 32) | row;
     D.row_slot[row] = slot;
     D.row_model[row] = kmod;
+    D.row_mask[row] = km;
+    D.row_value[row] = kv;
     write_planes(D, row, Pos{km, kv});
   }
 }
@@ -597,6 +609,72 @@ __device__ __forceinline__ bool cache_lookup(const Dev& D, const Lanes& L, Game&
   return hit;
 }
 
+// the model that has to evaluate `leaf` for the game in G (mcts.rs:70-76)
+__device__ __forceinline__ uint64_t model_to_play(const Dev& D, const Game& G, Pos leaf) {
+  const bool odd = (c4::popc64(leaf.mask) & 1) != 0;
+  if (G.reseated) return odd ? D.p1[G.req] : D.p0[G.req];
+  const Slot* S = D.slots + G.slot;
+  return odd ? S->model1 : S->model0;
+}
+
+// Speculation: the leaf G.leaf has just been expanded.  While the batch being built is small, its
+// spare rows evaluate the children of such leaves ahead of time: lane c looks child c up and, if the
+// position is neither cached nor already on its way, claims its cache entry exactly like a game that
+// misses (tag tick = e + 1) and draws a row of the batch for it.  Nobody waits for these rows; the
+// answers are moved into the claimed entries during the next tick (spec_collect) and are readable
+// from tick e + 2, when selection may arrive at the child and finds it answered.
+__device__ __forceinline__ void speculate_children(const Dev& D, const Lanes& L, const Game& G, bool pred, uint32_t epoch,
+                                                   uint32_t budget) {
+  const unsigned legal = c4::legal_mask(G.leaf.mask);
+  const int c = L.l < 7 ? L.l : 0;
+  const Pos child = c4::make_move(G.leaf, c);
+  float tq0, tq1;
+  const bool want = pred && L.l < 7 && ((legal >> c) & 1u) && c4::terminal_value(child, D.c_pen, &tq0, &tq1) == c4::NONE;
+  if (!want) return;
+  const uint64_t model = model_to_play(D, G, child);
+  const uint64_t key = pos_key(child);
+  const uint32_t h = (uint32_t)splitmix64(key ^ (model * 0x9E3779B97F4A7C15ULL)) & D.cache_mask;
+  EvalEntry* E = D.cache + h;
+  const unsigned long long tag = *reinterpret_cast<volatile unsigned long long*>(&E->tag);
+  const bool mine = (uint32_t)(tag >> 33) == D.job;
+  const bool dying = (tag & TAG_DYING) != 0ull;
+  const bool old = (uint32_t)tag < epoch;
+  if (mine && !(dying && old)) return;  // cached, on its way, or another position lives here (never evicted for a guess)
+  Globals* g = D.g;
+  const uint32_t s = atomicAdd(&g->spec_acc, 1u);
+  if (s >= budget) return;
+  uint2 item = make_uint2(0xffffffffu, 0u);
+  if (atomicCAS(&E->tag, tag, ((unsigned long long)D.job << 33) | (unsigned long long)(epoch + 1u)) == tag) {
+    E->key = key;
+    E->model = model;
+    const uint32_t row = atomicAdd(&g->rows_acc, 1u);
+    atomicAdd(&g->spec_ok, 1u);
+    D.row_slot[row] = 0xffffffffu;
+    D.row_model[row] = model;
+    D.row_mask[row] = child.mask;
+    D.row_value[row] = child.value;
+    write_planes(D, row, child);
+    item = make_uint2(row, h);
+  }
+  D.spec_list[(size_t)(epoch & 1u) * D.spec_cap + s] = item;
+}
+
+// The answers of last tick's speculative rows go into the cache entries claimed for them (any time
+// during this tick: the entries become readable in the next one).  Grid-stride over the list.
+__device__ __forceinline__ void spec_collect(const Dev& D, uint32_t epoch) {
+  const uint32_t par = (epoch - 1u) & 1u;
+  const uint32_t n = D.g->spec_count[par];
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint2 it = D.spec_list[(size_t)par * D.spec_cap + k];
+    if (it.x == 0xffffffffu) continue;
+    EvalEntry* E = D.cache + it.y;
+#pragma unroll
+    for (int i = 0; i < 7; i++) E->logit[i] = D.logits[(size_t)it.x * 7 + i];
+    E->qp = D.qp[it.x];
+    E->qn = D.qn[it.x];
+  }
+}
+
 __device__ __forceinline__ void seat_game(const Dev& D, Game& G, uint32_t r) {
   G.reseated = true;
   G.root = Pos{0ull, 0ull};
@@ -746,28 +824,23 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
   return result;
 }
 
-// the model that has to evaluate `leaf` for the game in G (mcts.rs:70-76)
-__device__ __forceinline__ uint64_t model_to_play(const Dev& D, const Game& G, Pos leaf) {
-  const bool odd = (c4::popc64(leaf.mask) & 1) != 0;
-  if (G.reseated) return odd ? D.p1[G.req] : D.p0[G.req];
-  const Slot* S = D.slots + G.slot;
-  return odd ? S->model1 : S->model0;
-}
-
 // Advance the (up to four) games of this warp until each needs the network (WAIT_NN), has used its
 // in-kernel budget of simulations that need no network row (CONTINUE), needs its tree compacted
 // (NEED_MOVE) or holds no game (IDLE).  `running` marks the lanes of live games, `pend` those that
 // hold an evaluation (x, vq, vn) of their leaf G.leaf that still has to be applied: the network's
 // answer on entry, an evaluation-cache hit later on.  Returns the new state.
 __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game& G, bool running, uint32_t state,
-                                              uint32_t epoch, bool pend, float x, float vq, float vn) {
+                                              uint32_t epoch, uint32_t spec_budget, bool pend, float x, float vq, float vn) {
   uint32_t inl = 0;
+  const uint32_t max_inline = spec_budget ? D.max_inline_spec : D.max_inline;
   for (;;) {
     if (__any_sync(FULL, pend)) {
-      if (!apply_answer(D, L, G, pend, x, vq, vn)) {
+      const bool ok = apply_answer(D, L, G, pend, x, vq, vn);
+      if (!ok) {
         if (L.l == 0) D.g->error = C4A0_E_ENGINE;
         running = false;
       }
+      if (spec_budget) speculate_children(D, L, G, pend && ok, epoch, spec_budget);
       pend = false;
     }
     const bool need_move = running && G.rootN >= D.n_iter;  // self_play.rs:283: after every simulation
@@ -783,7 +856,7 @@ __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game
       }
       continue;
     }
-    if (running && inl >= D.max_inline) {
+    if (running && inl >= max_inline) {
       running = false;
       state = ST_CONTINUE;
     }
@@ -893,6 +966,23 @@ __device__ __forceinline__ void close_tick(const Dev& D, uint32_t epoch, uint32_
   G->n_rows = rows;
   G->rows_total += rows;
   G->leaves_total += waiting;
+  if (D.spec_cap) {
+    // this tick's speculative rows, and how many the next tick may add: a batch whose rows asked for by
+    // games fill at most half of spec_cap is topped up to spec_cap (rows can never exceed n_slots: every
+    // live game may ask for one)
+    const uint32_t budget = G->spec_budget;
+    const uint32_t acc = atomicExch(&G->spec_acc, 0u), ok = atomicExch(&G->spec_ok, 0u);
+    G->spec_count[epoch & 1u] = acc < budget ? acc : budget;
+    G->spec_total += ok;
+    const uint32_t asked = rows - ok;
+    uint32_t next = 0u;
+    if (asked * 2u <= D.spec_cap) {
+      next = D.spec_cap - asked;
+      const uint32_t room = D.n_slots - G->n_running;
+      next = next < room ? next : room;
+    }
+    G->spec_budget = next;
+  }
   HostStatus* hs = D.status;
   hs->n_rows = rows;
   hs->n_finished = G->n_finished;
@@ -925,6 +1015,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction after a compaction (cannot happen, kept for safety)
   const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
   const uint32_t epoch = D.g->tick;
+  const uint32_t spec_budget = D.spec_cap ? D.g->spec_budget : 0u;
   if (__any_sync(FULL, live)) {  // (no early return: every warp takes part in closing the tick below)
   const long long t1 = prof ? clock64() : 0;
   const bool waiting = live && st == ST_WAIT_NN;
@@ -945,7 +1036,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   }
   G.cache_own = 0u;
   const long long t2 = prof ? clock64() : 0;
-  const uint32_t ns = run_games(D, L, G, live, st, epoch, waiting, x, vq, vn);
+  const uint32_t ns = run_games(D, L, G, live, st, epoch, spec_budget, waiting, x, vq, vn);
   const long long t3 = prof ? clock64() : 0;
   const unsigned nwait = __popc(__ballot_sync(FULL, live && L.l == 0 && ns == ST_WAIT_NN));
   if ((threadIdx.x & 31) == 0 && nwait) atomicAdd(&D.g->wait_acc, nwait);
@@ -972,6 +1063,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     }
   }
   }
+  if (D.spec_cap) spec_collect(D, epoch);
   // ---- the last CTA to finish closes the tick (or hands it to k_tail) ---------------------------
   __shared__ uint32_t sh_last;
   __syncthreads();
@@ -1068,8 +1160,7 @@ __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float*
     qn[row] = 0.0f;
     return;
   }
-  const Slot* S = D.slots + D.row_slot[row];
-  uint64_t mask = S->leaf_mask, value = S->leaf_value, model = leaf_model_of(*S);
+  uint64_t mask = D.row_mask[row], value = D.row_value[row], model = D.row_model[row];
   uint64_t h = splitmix64(mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(value ^ model));
   for (int k = 0; k < 7; k++) {
     uint64_t hk = splitmix64(h + (uint64_t)k);
@@ -1080,15 +1171,6 @@ __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float*
   const float qs = kind == C4A0_EVAL_HASH_FLAT ? 0.1f : 0.75f;
   qp[row] = ((float)(uint32_t)((hq >> 48) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * qs;
   qn[row] = ((float)(uint32_t)((hq >> 32) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * qs;
-}
-
-__global__ void k_gather_rows(Dev D, uint64_t* mask, uint64_t* value, uint64_t* model) {
-  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= D.g->n_rows) return;
-  const Slot* S = D.slots + D.row_slot[row];
-  mask[row] = S->leaf_mask;
-  value[row] = S->leaf_value;
-  model[row] = leaf_model_of(*S);
 }
 
 // Training tensors straight from the sample store (what src/c4a0/training.py:317-333 builds with a
@@ -1155,7 +1237,6 @@ struct c4a0_engine {
   uint32_t n_req = 0;
   uint64_t steps = 0;
   unsigned long long* scratch4 = nullptr;
-  uint64_t *row_mask = nullptr, *row_value = nullptr, *row_model = nullptr;
   Globals* h_globals = nullptr;   // pinned
   HostStatus* h_status = nullptr; // pinned + mapped
   float *b_logits = nullptr, *b_qp = nullptr, *b_qn = nullptr;  // writable aliases for eval_builtin
@@ -1232,6 +1313,8 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   if (cfg->arena_blocks && cfg->arena_blocks < cfg->n_mcts_iterations + 2)
     return fail(C4A0_E_INVALID, "arena_blocks must be 0 or >= n_mcts_iterations + 2");
   if (cfg->arena_blocks >= (1u << 29)) return fail(C4A0_E_INVALID, "arena_blocks too large");
+  if ((cfg->flags & C4A0_FLAG_SPECULATE) && !(cfg->flags & C4A0_FLAG_EVAL_CACHE))
+    return fail(C4A0_E_INVALID, "C4A0_FLAG_SPECULATE needs C4A0_FLAG_EVAL_CACHE");
   int r = c4host::no_gpu_error();
   if (r) return r;
   CK(cudaSetDevice(cfg->device));
@@ -1263,7 +1346,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   DA(D.n_samples, R); DA(D.s_mask, R * MAXS); DA(D.s_value, R * MAXS);
   DA(D.s_policy, R * MAXS * 7); DA(D.s_qp, R * MAXS); DA(D.s_qn, R * MAXS);
   DA(D.g, 1); DA(D.movers, S);
-  DA(e->scratch4, 4); DA(e->row_mask, S); DA(e->row_value, S); DA(e->row_model, S);
+  DA(e->scratch4, 4); DA(D.row_mask, S); DA(D.row_value, S);
   size_t CE = 0;
   if (use_cache) {
     // default: room for 8 entries per simulation of one move of every resident game (a job evaluates a
@@ -1290,6 +1373,12 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
     DA(tab, D.ln_n);
     k_ln_table<<<blocks_for(D.ln_n, 256), 256>>>(tab, D.ln_n);
     D.ln_tab = tab;
+  }
+  if (use_cache && (cfg->flags & C4A0_FLAG_SPECULATE)) {
+    D.spec_cap = cfg->spec_rows ? cfg->spec_rows : 2048u;
+    if (D.spec_cap > cfg->n_slots) D.spec_cap = cfg->n_slots;
+    D.max_inline_spec = 4 * D.max_inline;
+    DA(D.spec_list, 2 * (size_t)D.spec_cap);
   }
   cudaError_t err = cudaGetLastError();
   if (err == cudaSuccess) err = cudaMemset(D.slots, 0, S * sizeof(Slot));
@@ -1473,6 +1562,7 @@ int c4a0_engine_stats(c4a0_engine* e, c4a0_stats* out, void* stream) {
   out->compactions = g.compactions;
   out->cache_hits = g.cache_hits;
   out->cache_inserts = g.cache_inserts;
+  out->spec_rows = g.spec_total;
   return 0;
 }
 
@@ -1480,16 +1570,13 @@ int c4a0_engine_fetch_rows(c4a0_engine* e, uint32_t* n_rows, uint64_t* leaf_mask
                            uint64_t* model_id, void* stream) {
   if (!e || !n_rows) return fail(C4A0_E_INVALID, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  size_t S = e->D.n_slots;
-  k_gather_rows<<<blocks_for(S, 256), 256, 0, s>>>(e->D, e->row_mask, e->row_value, e->row_model);
-  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_globals, e->D.g, sizeof(Globals), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   uint32_t n = e->h_globals->n_rows;
   *n_rows = n;
-  if (n && leaf_mask) CK(cudaMemcpyAsync(leaf_mask, e->row_mask, n * 8, cudaMemcpyDeviceToHost, s));
-  if (n && leaf_value) CK(cudaMemcpyAsync(leaf_value, e->row_value, n * 8, cudaMemcpyDeviceToHost, s));
-  if (n && model_id) CK(cudaMemcpyAsync(model_id, e->row_model, n * 8, cudaMemcpyDeviceToHost, s));
+  if (n && leaf_mask) CK(cudaMemcpyAsync(leaf_mask, e->D.row_mask, n * 8, cudaMemcpyDeviceToHost, s));
+  if (n && leaf_value) CK(cudaMemcpyAsync(leaf_value, e->D.row_value, n * 8, cudaMemcpyDeviceToHost, s));
+  if (n && model_id) CK(cudaMemcpyAsync(model_id, e->D.row_model, n * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return 0;
 }

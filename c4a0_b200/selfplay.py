@@ -38,7 +38,9 @@ DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, 
             "max_inline_sims": 0, "arena_blocks": None,
             # evaluation cache (engine.cu, C4A0_FLAG_EVAL_CACHE) for device evaluators reached through
             # c4a0_rust.play_games; callbacks never get it (they need not be pure functions of the position)
-            "eval_cache": True, "eval_cache_entries": 0}
+            "eval_cache": True, "eval_cache_entries": 0,
+            # with the cache: top small batches up with the children of expanded leaves (C4A0_FLAG_SPECULATE)
+            "speculate": True, "spec_rows": 0}
 
 def _buckets():
     """Network batch sizes that get their own CUDA graph: fine steps (a tick launches the smallest
@@ -184,13 +186,13 @@ class _Lane:
     """One engine + its NN I/O tensors + its stream."""
 
     def __init__(self, n_slots, max_requests, n_iter, c_expl, c_pen, plane_dtype, device, max_inline, stride, flags,
-                 arena_blocks, offset=0, eval_cache_entries=0):
+                 arena_blocks, offset=0, eval_cache_entries=0, spec_rows=0):
         self.n_slots = n_slots
         self.offset = offset
         self.engine = Engine(
             n_slots, max(1, max_requests), n_iter, c_expl, c_pen,
             L.PLANES_BF16 if plane_dtype == torch.bfloat16 else L.PLANES_F32, max_inline, device.index, stride, flags,
-            arena_blocks, eval_cache_entries,
+            arena_blocks, eval_cache_entries, spec_rows,
         )
         self.planes = torch.zeros(n_slots, stride, dtype=plane_dtype, device=device)
         self.logits = torch.zeros(n_slots, 7, dtype=torch.float32, device=device)
@@ -257,6 +259,8 @@ class SelfPlaySession:
         arena_blocks: Optional[int] = None,
         eval_cache: bool = False,
         eval_cache_entries: int = 0,
+        speculate: bool = False,
+        spec_rows: int = 0,
     ):
         """`eval_cache=True` lets the engine answer repeated (position, model) leaves of one play() call from
         a device table instead of the network; only for evaluators that are pure functions of the position."""
@@ -275,8 +279,12 @@ class SelfPlaySession:
         self.plane_dtype = plane_dtype
         self.plane_stride = plane_stride
         self.plane_offset = plane_offset
-        flags = (0 if dedup else L.FLAG_NO_DEDUP) | (L.FLAG_EVAL_CACHE if eval_cache else 0)
+        if speculate and not eval_cache:
+            raise ValueError("speculate=True needs eval_cache=True")
+        flags = ((0 if dedup else L.FLAG_NO_DEDUP) | (L.FLAG_EVAL_CACHE if eval_cache else 0)
+                 | (L.FLAG_SPECULATE if speculate else 0))
         self.eval_cache = bool(eval_cache)
+        self.speculate = bool(speculate)
         if arena_blocks is None:
             arena_blocks = DEFAULTS["arena_blocks"]
         if arena_blocks is None:
@@ -289,7 +297,7 @@ class SelfPlaySession:
         per = [(n_slots + i) // n_lanes for i in range(n_lanes)][::-1]
         self.lanes = [
             _Lane(s, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, self.device,
-                  max_inline_sims, plane_stride, flags, arena_blocks, plane_offset, eval_cache_entries)
+                  max_inline_sims, plane_stride, flags, arena_blocks, plane_offset, eval_cache_entries, spec_rows)
             for s in per if s > 0
         ]
 

@@ -312,14 +312,15 @@ def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lan
     from c4a0_b200 import selfplay
     from c4a0_b200.selfplay import SelfPlaySession
 
-    knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks", "eval_cache_entries")))
+    knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks", "eval_cache_entries", "speculate", "spec_rows")))
     key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, offset, n_lanes, knobs, eval_cache)
     if _SESSION["key"] == key and _SESSION["sess"] is not None and _SESSION["cap"] >= n_req:
         return _SESSION["sess"]
     close_cached_session()
     sess = SelfPlaySession(n_slots, n_req, n_iter, c_expl, c_pen, plane_dtype=dtype, device=device,
                            plane_stride=stride, plane_offset=offset, n_lanes=n_lanes, eval_cache=eval_cache,
-                           eval_cache_entries=selfplay.DEFAULTS["eval_cache_entries"])
+                           eval_cache_entries=selfplay.DEFAULTS["eval_cache_entries"],
+                           speculate=bool(eval_cache and selfplay.DEFAULTS["speculate"]), spec_rows=selfplay.DEFAULTS["spec_rows"])
     _SESSION.update(key=key, sess=sess, cap=n_req)
     return sess
 

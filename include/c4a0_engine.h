@@ -76,6 +76,7 @@ typedef struct {
   uint32_t eval_cache_entries; /* with C4A0_FLAG_EVAL_CACHE: entries (96 B each) of the evaluation cache, rounded
                                   up to a power of two; 0 = sized from n_slots * n_mcts_iterations and the
                                   free device memory */
+  uint32_t spec_rows;          /* with C4A0_FLAG_SPECULATE: rows a small batch is topped up to (0 = 2048) */
 } c4a0_config;
 
 /* Evaluate every waiting leaf even when several games wait on the same (position, model); by default
@@ -89,6 +90,14 @@ typedef struct {
  * evaluator the games are identical with and without the cache; only n_rows per tick and the
  * number of ticks shrink.  The table is emptied by every set_requests(). */
 #define C4A0_FLAG_EVAL_CACHE 2u
+/* Needs C4A0_FLAG_EVAL_CACHE.  While a tick's batch is small (the first plies, when all games share a
+ * few positions, and the tail of a job, when few games are left) the network runs far below capacity
+ * and a tick costs the same whatever its rows.  With this flag such batches are topped up to
+ * spec_rows with the children of the leaves that are being expanded; the answers go into the
+ * evaluation cache, so that selection finds them answered when it gets there, and a game may then run
+ * several simulations per tick (4 x max_inline_sims).  Same assumption and same guarantee as the
+ * cache: game records do not change.  Rows of these evaluations have row_slot 0xffffffff. */
+#define C4A0_FLAG_SPECULATE 4u
 
 typedef struct {
   uint32_t n_requests;   /* games submitted */
@@ -116,6 +125,7 @@ typedef struct {
   uint64_t compactions;        /* number of such copies (re-roots that fit the arena copy nothing) */
   uint64_t cache_hits;         /* leaves answered from the evaluation cache (C4A0_FLAG_EVAL_CACHE) */
   uint64_t cache_inserts;      /* network answers stored in it */
+  uint64_t spec_rows;          /* rows evaluated ahead of time (C4A0_FLAG_SPECULATE); part of nn_evals */
 } c4a0_stats;
 
 const char *c4a0_last_error(void);
@@ -176,7 +186,7 @@ int c4a0_engine_fetch_rows(c4a0_engine *e, uint32_t *n_rows, uint64_t *leaf_mask
                            uint64_t *leaf_value, uint64_t *model_id, void *stream);
 
 /* Device views of the live rows, for evaluators that stay on the GPU: row_slot_dev[r] = the slot whose
- * leaf is row r, row_model_dev[r] = the model id that has to evaluate it (tournaments play several
+ * leaf is row r (0xffffffff: a speculative row, nobody waits for it), row_model_dev[r] = the model id that has to evaluate it (tournaments play several
  * models in one batch, rust/src/self_play.rs:203-220).  Valid for r < n_rows after every step(). */
 int c4a0_engine_rows_dev(c4a0_engine *e, uint32_t **row_slot_dev, uint64_t **row_model_dev);
 

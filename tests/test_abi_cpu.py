@@ -32,9 +32,9 @@ def test_header_symbols_are_exported_and_bound():
 def test_struct_sizes_match_the_header():
     from c4a0_b200 import _lib as L
 
-    assert C.sizeof(L.Config) == 12 * 4
+    assert C.sizeof(L.Config) == 13 * 4
     assert C.sizeof(L.Progress) == 7 * 4
-    assert C.sizeof(L.Stats) == 14 * 8
+    assert C.sizeof(L.Stats) == 15 * 8
     assert C.sizeof(L.RunReport) == 5 * 8 + 4 * 8 + 8 + 2 * 8 + 32 * 8
     assert C.sizeof(L.NNGraph) == 16
 

@@ -112,3 +112,48 @@ def test_play_games_fast_path_uses_the_cache_and_callbacks_do_not():
         b = res[other].to_arrays()
         for x, y in zip(a, b):
             assert np.array_equal(x, y), other
+
+
+def test_speculation_fills_spare_rows_and_saves_ticks():
+    """256 games in 1024 slots: every batch has spare rows; the children of expanded leaves are
+    evaluated in them, so later leaves are already answered.  Records stay those of the plain engine."""
+    _need_gpu()
+    from c4a0_b200 import _lib as L
+
+    n_games, n_slots, n_iter, c_expl, c_pen = 256, 1024, 80, 6.6, 0.01
+    ids = [11 * i + 3 for i in range(n_games)]
+    outs, stats, ticks = [], [], []
+    for flags in (0, L.FLAG_EVAL_CACHE, L.FLAG_EVAL_CACHE | L.FLAG_SPECULATE):
+        e, io = _make_engine(n_slots, n_games, n_iter, c_expl, c_pen, flags=flags, spec_rows=768)
+        e.set_requests(ids, [0] * n_games, [0] * n_games)
+        seen_max = 0
+        for t in range(200000):
+            e.eval_builtin(1)
+            e.step()
+            p = e.poll()
+            seen_max = max(seen_max, p.n_rows)
+            if p.n_finished == p.n_requests:
+                break
+        ticks.append(t + 1)
+        assert seen_max <= n_slots
+        outs.append(e.fetch_results())
+        stats.append(e.stats())
+        e.close()
+    for other in (1, 2):
+        for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
+            assert np.array_equal(getattr(outs[0], f), getattr(outs[other], f)), (other, f)
+    plain, cache, spec = stats
+    for k in ("sims", "terminal_leaf_sims", "moves", "samples", "expansions", "select_depth_sum"):
+        assert plain[k] == cache[k] == spec[k], k
+    assert plain["spec_rows"] == 0 and cache["spec_rows"] == 0 and spec["spec_rows"] > 0
+    assert spec["cache_hits"] > cache["cache_hits"]
+    assert spec["cache_hits"] + spec["leaf_requests"] == spec["expansions"]
+    assert ticks[2] < ticks[1] < ticks[0]
+
+
+def test_speculate_needs_the_cache():
+    _need_gpu()
+    from c4a0_b200 import _lib as L
+
+    with pytest.raises(L.EngineError):
+        _make_engine(8, 8, 10, 1.0, 0.01, flags=L.FLAG_SPECULATE)

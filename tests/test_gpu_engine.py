@@ -146,17 +146,21 @@ def _records(samples, i):
     ]
 
 
-@pytest.mark.parametrize("cache", [0, 1 << 20, 32], ids=["nocache", "cache", "cache32"])
+@pytest.mark.parametrize("cache", [0, 1 << 20, 32, -1], ids=["nocache", "cache", "cache32", "speculate"])
 @pytest.mark.parametrize("kind,name", [(0, "uniform"), (1, "hash")])
 def test_tree_state_matches_oracle_every_step(kind, name, cache):
     """Tree structure + every N / Qp / Qn / prior bit pattern after every lockstep tick; also with the
-    evaluation cache (several simulations per tick; 32 entries = constant replacement)."""
+    evaluation cache (several simulations per tick; 32 entries = constant replacement) and with
+    speculative evaluation of children in the spare rows (64 slots for 6 games)."""
     _need_gpu()
     from c4a0_b200 import _lib as L
 
     n_games, n_iter, c_expl, c_pen = 6, 40, 1.7, 0.01
-    e, io = _make_engine(n_games, n_games, n_iter, c_expl, c_pen, max_inline_sims=3, arena_blocks=70 if kind else 0,
-                         flags=L.FLAG_EVAL_CACHE if cache else 0, eval_cache_entries=cache)
+    spec = cache == -1
+    e, io = _make_engine(64 if spec else n_games, n_games, n_iter, c_expl, c_pen, max_inline_sims=3,
+                         arena_blocks=70 if kind else 0,
+                         flags=(L.FLAG_EVAL_CACHE if cache else 0) | (L.FLAG_SPECULATE if spec else 0),
+                         eval_cache_entries=(1 << 16) if spec else cache, spec_rows=48 if spec else 0)
     ids = [0, 1, 2, 77, 1234567, 2**40 + 5]
     e.set_requests(ids, [0] * n_games, [0] * n_games)
     games = [oracle.Game(game_id=g) for g in ids]
@@ -198,7 +202,7 @@ def test_tree_state_matches_oracle_every_step(kind, name, cache):
     e.close()
 
 
-@pytest.mark.parametrize("cache", [0, 0xFFFFFFFF, 256], ids=["nocache", "cache", "cache256"])
+@pytest.mark.parametrize("cache", [0, 0xFFFFFFFF, 256, -1, -256], ids=["nocache", "cache", "cache256", "speculate", "speculate256"])
 @pytest.mark.parametrize("kind,name", [(0, "uniform"), (1, "hash")])
 @pytest.mark.parametrize("n_slots,arena", [(64, 0), (17, 0), (64, 8 * 62), (33, 100)])
 def test_game_records_match_oracle(kind, name, n_slots, arena, cache):
@@ -210,8 +214,13 @@ def test_game_records_match_oracle(kind, name, n_slots, arena, cache):
 
     n_games, n_iter, c_expl, c_pen = 64, 60, 6.6, 0.01
     reqs = [(1000 + 37 * i, 0, 0) for i in range(n_games)]
+    spec = cache < 0
+    if spec:  # speculation uses rows no game can ask for: twice the slots the games need
+        cache = 0xFFFFFFFF if cache == -1 else -cache
+        n_slots = 2 * n_slots
     e, io = _make_engine(n_slots, n_games, n_iter, c_expl, c_pen, arena_blocks=arena,
-                         flags=L.FLAG_EVAL_CACHE if cache else 0, eval_cache_entries=0 if cache == 0xFFFFFFFF else cache)
+                         flags=(L.FLAG_EVAL_CACHE if cache else 0) | (L.FLAG_SPECULATE if spec else 0),
+                         eval_cache_entries=0 if cache == 0xFFFFFFFF else cache, spec_rows=40 if spec else 0)
     e.set_requests([r[0] for r in reqs], [0] * n_games, [0] * n_games)
     _run_builtin(e, kind)
     got = e.fetch_results()
@@ -221,6 +230,7 @@ def test_game_records_match_oracle(kind, name, n_slots, arena, cache):
     st = e.stats()
     assert st["samples"] == sum(len(r) for r in exp)
     assert (st["cache_hits"] > 0) == bool(cache) and (st["cache_inserts"] > 0) == bool(cache)
+    assert (st["spec_rows"] > 0) == spec
     if arena == 0:
         assert st["compactions"] > n_games and st["compacted_blocks"] > 0
     if arena == 8 * 62 and n_slots == n_games:
