@@ -106,7 +106,8 @@ def test_bf16_fused_network_runs_are_reproducible():
     b = R.play_games(reqs, 512, 40, 6.6, 0.01, ev)
     for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
         assert np.array_equal(getattr(a._soa, f), getattr(b._soa, f)), f
-    assert a._run_info.stats["nn_evals"] < a._run_info.stats["leaf_requests"]
+    st = a._run_info.stats  # equal leaves share rows (rows nobody asked for are speculative)
+    assert st["nn_evals"] - st["spec_rows"] < st["leaf_requests"]
 
 
 def test_training_loop_one_generation(tmp_path):
