@@ -1729,6 +1729,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     cudaStream_t s;
     uint32_t expect;     // status tick the host waits for next
     uint32_t spec_rows;  // rows covered by the network graph already enqueued behind that tick
+    uint32_t prev_rows;  // rows of the tick before the last closed one
     bool done;
     cudaEvent_t t0, t1;
   };
@@ -1744,7 +1745,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     }
     if (graphs[i][n_graphs[i] - 1].rows < e->D.n_slots)
       return fail(C4A0_E_INVALID, "the largest network graph must cover n_slots rows");
-    lanes[i] = Lane{e, (cudaStream_t)streams[i], e->h_status->tick, 0u, e->n_req == 0, nullptr, nullptr};
+    lanes[i] = Lane{e, (cudaStream_t)streams[i], e->h_status->tick, 0u, 0u, e->n_req == 0, nullptr, nullptr};
     CK(cudaEventCreate(&lanes[i].t0));
     CK(cudaEventCreate(&lanes[i].t1));
   }
@@ -1794,7 +1795,10 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     int r = launch_tick(L.e, L.s, nullptr, false);
     if (r) return r;
     if (ev) CK(cudaEventRecord(ev[1], L.s));
-    const uint32_t margin = (rows >> spec_shift) > 16 ? (rows >> spec_shift) : 16;
+    // ... or, while the batch is growing, by as much again as it grew last time
+    uint32_t margin = (rows >> spec_shift) > 16 ? (rows >> spec_shift) : 16;
+    if (rows > L.prev_rows && rows - L.prev_rows > margin) margin = rows - L.prev_rows;
+    L.prev_rows = rows;
     const uint32_t guess = rows + margin < L.e->D.n_slots ? rows + margin : L.e->D.n_slots;
     r = launch_nn(i, guess, &L.spec_rows);
     if (r) return r;

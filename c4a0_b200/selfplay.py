@@ -44,10 +44,11 @@ DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, 
 
 def _buckets():
     """Network batch sizes that get their own CUDA graph: fine steps (a tick launches the smallest
-    graph covering its live rows, so coarse steps waste GEMM rows), multiples of 256 above 1024."""
+    graph covering its live rows, so coarse steps waste GEMM rows), a few percent apart above 1024."""
     b = [128, 256, 384, 512, 768, 1024]
-    b += list(range(1536, 4096 + 1, 512))
-    b += list(range(5120, 32768 + 1, 1024))
+    b += list(range(1280, 4096 + 1, 256))
+    b += list(range(4608, 16384 + 1, 512))
+    b += list(range(17408, 32768 + 1, 1024))
     b += list(range(36864, 131072 + 1, 4096))
     return tuple(b)
 
