@@ -78,7 +78,9 @@ static_assert(sizeof(Block) == 160, "block must be ten 16-byte vectors");
 //   State changes go through one atomicCAS on the tag and never touch a payload that a reader of
 //   the same tick could accept:
 //     claim (stale, or dying since an earlier tick)  -> {job, 0, e + 1}; the claimer writes the key
-//          now and the payload when its answer arrives in tick e + 1; readable from tick e + 2
+//          now and the payload when its answer arrives in tick e + 1; readable from tick e + 2.
+//          During tick e + 1 itself a reader that finds `row` set takes the answer straight from
+//          the network's output row (those buffers do not change within a tick).
 //     kill  (readable, other key)                    -> {job, 1, e}; payload untouched; claimable
 //          from tick e + 1 (always-replace with one tick of delay)
 struct __align__(64) EvalEntry {
@@ -87,7 +89,9 @@ struct __align__(64) EvalEntry {
   uint64_t model;
   float qp, qn;
   float logit[7];
-  uint32_t pad;
+  uint32_t row;            // 1 + the network row that evaluates the position in the batch of the claiming tick
+                           // (0 = not known to the claimer): the answer can be read from the network's
+                           // output buffers one tick before the payload is readable
 };
 static_assert(sizeof(EvalEntry) == 64, "an entry is two sectors");
 
@@ -261,7 +265,7 @@ __device__ __forceinline__ void write_planes(const Dev& D, uint32_t row, Pos p) 
 // the leader.  (Which of several equal leaves leads, and hence the order of rows, depends on
 // arrival order; rows are independent in the network, so results do not.)
 __device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64_t km, uint64_t kv, uint64_t kmod,
-                                             uint32_t epoch) {
+                                             uint32_t epoch, uint32_t cache_own) {
   uint32_t leader = slot;
   if (D.dedup) {
     __threadfence();  // the slot line must be visible before the slot can be found in the table
@@ -294,6 +298,7 @@ __device__ __forceinline__ void publish_leaf(const Dev& D, uint32_t slot, uint64
     D.row_model[row] = kmod;
     D.row_mask[row] = km;
     D.row_value[row] = kv;
+    if (cache_own) D.cache[cache_own - 1u].row = row + 1u;
     write_planes(D, row, Pos{km, kv});
   }
 }
@@ -587,10 +592,18 @@ __device__ __forceinline__ bool cache_lookup(const Dev& D, const Lanes& L, Game&
     const bool old = (uint32_t)tag < epoch;  // the last state change happened in an earlier tick
     const bool same = ekey == key && emodel == model;
     hit = mine && !dying && old && same;
+    // claimed during the last tick with a known row: that row of the last batch holds the answer
+    const uint32_t frow = (mine && !dying && same && (uint32_t)tag == epoch) ? E->row : 0u;
     if (hit) {
       x = lg;
       vq = __uint_as_float(b.z);
       vn = __uint_as_float(b.w);
+      G.hits++;
+    } else if (frow) {
+      hit = true;
+      x = D.logits[(size_t)(frow - 1u) * 7 + (L.l < 7 ? L.l : 6)];
+      vq = D.qp[frow - 1u];
+      vn = D.qn[frow - 1u];
       G.hits++;
     } else if (L.l == 0) {
       const unsigned long long jb = (unsigned long long)D.job << 33;
@@ -598,6 +611,7 @@ __device__ __forceinline__ bool cache_lookup(const Dev& D, const Lanes& L, Game&
         if (atomicCAS(&E->tag, tag, jb | (unsigned long long)(epoch + 1u)) == tag) {
           E->key = key;
           E->model = model;
+          E->row = 0u;  // set by publish_leaf() if this game also leads the key
           G.cache_own = h + 1u;
           G.claims++;
         }
@@ -649,6 +663,7 @@ __device__ __forceinline__ void speculate_children(const Dev& D, const Lanes& L,
     E->model = model;
     const uint32_t row = atomicAdd(&g->rows_acc, 1u);
     atomicAdd(&g->spec_ok, 1u);
+    E->row = row + 1u;
     D.row_slot[row] = 0xffffffffu;
     D.row_model[row] = model;
     D.row_mask[row] = child.mask;
@@ -1049,7 +1064,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     store_game(D, G, ns);
     if (ns == ST_NEED_MOVE) push_mover(D, slot);
     if (ns == ST_WAIT_NN)
-      publish_leaf(D, slot, G.leaf.mask, G.leaf.value, stored_leaf_model(D, G), epoch);
+      publish_leaf(D, slot, G.leaf.mask, G.leaf.value, stored_leaf_model(D, G), epoch, G.cache_own);
     if (prof) {  // cycles of this game's warp per phase (c4a0_engine_debug_phases)
       uint32_t* o = D.dbg + (size_t)slot * 8;
       o[0] = (uint32_t)(t1 - t0);         // load slot state
@@ -1119,7 +1134,7 @@ __global__ void k_init(Dev D, uint32_t n_req) {
   D.slots[slot] = S;
   if (slot < n_req) {
     atomicAdd(&D.g->wait_acc, 1u);
-    publish_leaf(D, slot, 0ull, 0ull, S.model0, 1u);
+    publish_leaf(D, slot, 0ull, 0ull, S.model0, 1u, 0u);
   }
 }
 
