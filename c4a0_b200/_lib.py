@@ -132,6 +132,7 @@ SIGNATURES = {
     "c4a0_abi_version": (C.c_int, []),
     "c4a0_engine_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "c4a0_engine_destroy": (None, [_P]),
+    "c4a0_engine_io_rows": (C.c_uint32, [_P]),
     "c4a0_engine_device_bytes": (C.c_size_t, [_P]),
     "c4a0_engine_bind_io": (C.c_int, [_P, _P, _P, _P, _P]),
     "c4a0_engine_set_requests": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P]),

@@ -176,8 +176,8 @@ struct Dev {  // passed to kernels by value
   Slot* slots;
   uint32_t* path;   // [n_slots][PATH_STRIDE]: (block << 3 | column) per level of the selected path
   Block* blocks;    // [n_slots][2][cap]
-  uint32_t* row_slot;   // [n_slots] slot whose leaf is the row; 0xffffffff for a speculative row
-  uint64_t* row_model;  // [n_slots] model that has to evaluate the row (mcts.rs:70-76)
+  uint32_t* row_slot;   // [row_cap] slot whose leaf is the row; 0xffffffff for a speculative row
+  uint64_t* row_model;  // [row_cap] model that has to evaluate the row (mcts.rs:70-76)
   uint32_t* bucket;  // [n_slots] hash-table entry of the slot's waiting leaf
   unsigned long long* rowtag;  // [2][n_slots] epoch << 32 | row, written by the slot that leads a key; the half is
                                // the epoch's parity: a leader may publish its next leaf while followers of its last
@@ -197,9 +197,11 @@ struct Dev {  // passed to kernels by value
   const float* ln_tab;             // [ln_n] c4_logf((float)i): visit counts are small integers
   uint32_t ln_n;
   uint32_t spec_cap;               // rows a batch may be topped up to with speculative evaluations, 0 = off
+  uint32_t spec_thr;               // ... while the rows games ask for are at most this many
+  uint32_t row_cap;                // rows of the I/O buffers: n_slots (+ spec_cap with speculation)
   uint32_t max_inline_spec;        // in-kernel simulation budget while speculation is running
   uint2* spec_list;                // [2][spec_cap] (row, cache entry) of the speculative rows of a batch
-  uint64_t *row_mask, *row_value;  // [n_slots] position of every row of the batch being built
+  uint64_t *row_mask, *row_value;  // [row_cap] position of every row of the batch being built
   // NN io
   void* planes;
   const float *logits, *qp, *qn;
@@ -982,20 +984,15 @@ __device__ __forceinline__ void close_tick(const Dev& D, uint32_t epoch, uint32_
   G->rows_total += rows;
   G->leaves_total += waiting;
   if (D.spec_cap) {
-    // this tick's speculative rows, and how many the next tick may add: a batch whose rows asked for by
-    // games fill at most half of spec_cap is topped up to spec_cap (rows can never exceed n_slots: every
-    // live game may ask for one)
+    // this tick's speculative rows, and how many the next tick may add: while the games themselves ask
+    // for at most spec_thr rows the batch is topped up to spec_cap (the I/O buffers hold n_slots +
+    // spec_cap rows, so every live game can still ask for its own)
     const uint32_t budget = G->spec_budget;
     const uint32_t acc = atomicExch(&G->spec_acc, 0u), ok = atomicExch(&G->spec_ok, 0u);
     G->spec_count[epoch & 1u] = acc < budget ? acc : budget;
     G->spec_total += ok;
     const uint32_t asked = rows - ok;
-    uint32_t next = 0u;
-    if (asked * 2u <= D.spec_cap) {
-      next = D.spec_cap - asked;
-      const uint32_t room = D.n_slots - G->n_running;
-      next = next < room ? next : room;
-    }
+    const uint32_t next = asked <= D.spec_thr ? D.spec_cap - (asked < D.spec_cap ? asked : D.spec_cap) : 0u;
     G->spec_budget = next;
   }
   HostStatus* hs = D.status;
@@ -1352,7 +1349,17 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   size_t T = 1;
   while (T < 2 * S) T <<= 1;
   D.table_mask = (uint32_t)(T - 1);
-  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, S); DA(D.row_model, S); DA(D.bucket, S); DA(D.rowtag, 2 * S);
+  if (use_cache && (cfg->flags & C4A0_FLAG_SPECULATE)) {
+    D.spec_cap = cfg->spec_rows ? cfg->spec_rows : 8192u;
+    if (D.spec_cap > cfg->n_slots) D.spec_cap = cfg->n_slots;
+    // speculate while the games themselves ask for at most this many rows: beyond that the spare rows
+    // cover too small a part of what the live games will want next (measured on the bench job)
+    D.spec_thr = D.spec_cap / 2 < 1024u ? D.spec_cap / 2 : 1024u;
+    D.max_inline_spec = 4 * D.max_inline;
+  }
+  D.row_cap = cfg->n_slots + D.spec_cap;
+  const size_t RC = D.row_cap;
+  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, RC); DA(D.row_model, RC); DA(D.bucket, S); DA(D.rowtag, 2 * S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
   DA(D.table, T);
   uint64_t *gid, *p0, *p1;
@@ -1361,7 +1368,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   DA(D.n_samples, R); DA(D.s_mask, R * MAXS); DA(D.s_value, R * MAXS);
   DA(D.s_policy, R * MAXS * 7); DA(D.s_qp, R * MAXS); DA(D.s_qn, R * MAXS);
   DA(D.g, 1); DA(D.movers, S);
-  DA(e->scratch4, 4); DA(D.row_mask, S); DA(D.row_value, S);
+  DA(e->scratch4, 4); DA(D.row_mask, RC); DA(D.row_value, RC);
   size_t CE = 0;
   if (use_cache) {
     // default: room for 8 entries per simulation of one move of every resident game (a job evaluates a
@@ -1389,12 +1396,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
     k_ln_table<<<blocks_for(D.ln_n, 256), 256>>>(tab, D.ln_n);
     D.ln_tab = tab;
   }
-  if (use_cache && (cfg->flags & C4A0_FLAG_SPECULATE)) {
-    D.spec_cap = cfg->spec_rows ? cfg->spec_rows : 2048u;
-    if (D.spec_cap > cfg->n_slots) D.spec_cap = cfg->n_slots;
-    D.max_inline_spec = 4 * D.max_inline;
-    DA(D.spec_list, 2 * (size_t)D.spec_cap);
-  }
+  if (D.spec_cap) DA(D.spec_list, 2 * (size_t)D.spec_cap);
   cudaError_t err = cudaGetLastError();
   if (err == cudaSuccess) err = cudaMemset(D.slots, 0, S * sizeof(Slot));
   if (err == cudaSuccess && CE) err = cudaMemset(D.cache, 0, CE * sizeof(EvalEntry));
@@ -1428,6 +1430,7 @@ void c4a0_engine_destroy(c4a0_engine* e) {
 }
 
 size_t c4a0_engine_device_bytes(const c4a0_engine* e) { return e ? e->bytes : 0; }
+uint32_t c4a0_engine_io_rows(const c4a0_engine* e) { return e ? e->D.row_cap : 0; }
 
 int c4a0_engine_bind_io(c4a0_engine* e, void* planes, const float* logits, const float* qp,
                         const float* qn) {
@@ -1530,7 +1533,7 @@ int c4a0_engine_debug_phases(c4a0_engine* e, void* stream, uint32_t* out8_per_sl
 int c4a0_engine_eval_builtin(c4a0_engine* e, int kind, void* stream) {
   if (!e || !e->io_bound) return fail(C4A0_E_INVALID, "engine not bound");
   if (kind != C4A0_EVAL_UNIFORM && kind != C4A0_EVAL_HASH && kind != C4A0_EVAL_HASH_FLAT) return fail(C4A0_E_INVALID, "bad evaluator kind");
-  k_eval_builtin<<<blocks_for(e->D.n_slots, 256), 256, 0, (cudaStream_t)stream>>>(e->D, kind, e->b_logits, e->b_qp, e->b_qn);
+  k_eval_builtin<<<blocks_for(e->D.row_cap, 256), 256, 0, (cudaStream_t)stream>>>(e->D, kind, e->b_logits, e->b_qp, e->b_qn);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1758,8 +1761,8 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
       if (!graphs[i][k].graph_exec) return fail(C4A0_E_INVALID, "null graph_exec");
       if (k && graphs[i][k].rows <= graphs[i][k - 1].rows) return fail(C4A0_E_INVALID, "network graphs must be sorted by rows");
     }
-    if (graphs[i][n_graphs[i] - 1].rows < e->D.n_slots)
-      return fail(C4A0_E_INVALID, "the largest network graph must cover n_slots rows");
+    if (graphs[i][n_graphs[i] - 1].rows < e->D.row_cap)
+      return fail(C4A0_E_INVALID, "the largest network graph must cover c4a0_engine_io_rows() rows");
     lanes[i] = Lane{e, (cudaStream_t)streams[i], e->h_status->tick, 0u, 0u, e->n_req == 0, nullptr, nullptr};
     CK(cudaEventCreate(&lanes[i].t0));
     CK(cudaEventCreate(&lanes[i].t1));
@@ -1814,7 +1817,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     uint32_t margin = (rows >> spec_shift) > 16 ? (rows >> spec_shift) : 16;
     if (rows > L.prev_rows && rows - L.prev_rows > margin) margin = rows - L.prev_rows;
     L.prev_rows = rows;
-    const uint32_t guess = rows + margin < L.e->D.n_slots ? rows + margin : L.e->D.n_slots;
+    const uint32_t guess = rows + margin < L.e->D.row_cap ? rows + margin : L.e->D.row_cap;
     r = launch_nn(i, guess, &L.spec_rows);
     if (r) return r;
     if (ev) CK(cudaEventRecord(ev[2], L.s));

@@ -54,6 +54,7 @@ class Engine:
         )
         L.check(self._lib.c4a0_engine_create(C.byref(self.cfg), C.byref(self._h)))
         self.n_slots = n_slots
+        self.io_rows = int(self._lib.c4a0_engine_io_rows(self._h))  # rows the NN I/O buffers must have
         self.n_requests = 0
 
     def close(self) -> None:
@@ -119,7 +120,7 @@ class Engine:
 
     def fetch_rows(self, stream: int = 0):
         """(n_rows, leaf_mask[n_rows], leaf_value[n_rows], model_id[n_rows]) of the live rows."""
-        S = self.n_slots
+        S = self.io_rows
         n = C.c_uint32(0)
         mask = np.empty(S, np.uint64)
         value = np.empty(S, np.uint64)
@@ -162,7 +163,7 @@ class Engine:
                                                      policy_ptr, qp_ptr, qn_ptr, stream))
 
     def rows_dev(self) -> Tuple[int, int]:
-        """Device pointers (row_slot u32[n_slots], row_model u64[n_slots])."""
+        """Device pointers (row_slot u32[io_rows], row_model u64[io_rows])."""
         a, b = C.c_void_p(), C.c_void_p()
         L.check(self._lib.c4a0_engine_rows_dev(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)

@@ -195,14 +195,15 @@ class _Lane:
             L.PLANES_BF16 if plane_dtype == torch.bfloat16 else L.PLANES_F32, max_inline, device.index, stride, flags,
             arena_blocks, eval_cache_entries, spec_rows,
         )
-        self.planes = torch.zeros(n_slots, stride, dtype=plane_dtype, device=device)
-        self.logits = torch.zeros(n_slots, 7, dtype=torch.float32, device=device)
-        self.qp = torch.zeros(n_slots, dtype=torch.float32, device=device)
-        self.qn = torch.zeros(n_slots, dtype=torch.float32, device=device)
+        self.io_rows = R = self.engine.io_rows  # n_slots, plus the speculative rows if that is on
+        self.planes = torch.zeros(R, stride, dtype=plane_dtype, device=device)
+        self.logits = torch.zeros(R, 7, dtype=torch.float32, device=device)
+        self.qp = torch.zeros(R, dtype=torch.float32, device=device)
+        self.qn = torch.zeros(R, dtype=torch.float32, device=device)
         self.engine.bind_io(self.planes.data_ptr() + offset * self.planes.element_size(), self.logits.data_ptr(),
                             self.qp.data_ptr(), self.qn.data_ptr())
         self.stream = torch.cuda.Stream(device=device)
-        self.row_model = _wrap_i64(self.engine.rows_dev()[1], n_slots, device)  # engine-owned, no copy
+        self.row_model = _wrap_i64(self.engine.rows_dev()[1], R, device)  # engine-owned, no copy
         self.graphs = {}  # rows -> torch.cuda.CUDAGraph
         self.graph_key = None
         self.pool = None
@@ -224,7 +225,7 @@ class _Lane:
         if self.graph_key is not evaluator:  # identity, and a strong reference: ids can be recycled
             self.graphs, self.graph_key = {}, evaluator
             self.pool = torch.cuda.graph_pool_handle()
-            sizes = [b for b in BUCKETS if b < self.n_slots] + [self.n_slots]
+            sizes = [b for b in BUCKETS if b < self.io_rows] + [self.io_rows]
             with torch.cuda.stream(self.stream):
                 for rows in reversed(sizes):  # largest first: the shared pool is sized once
                     self.evaluate(evaluator, rows)  # eager warm-up (cuBLAS handles, heuristics)
@@ -392,7 +393,7 @@ class SelfPlaySession:
             ev0.record(self.lanes[0].stream)
             ks, km, kn, ticks = 0.0, 0.0, 0, 0
             live = [hi > lo for lo, hi in ranges]
-            sizes = {id(ln): [b for b in BUCKETS if b < ln.n_slots] + [ln.n_slots] for ln in self.lanes}
+            sizes = {id(ln): [b for b in BUCKETS if b < ln.io_rows] + [ln.io_rows] for ln in self.lanes}
             rows = {id(ln): ln.engine.poll(ln.stream.cuda_stream).n_rows for ln in self.lanes}
             while any(live):
                 for i, ln in enumerate(self.lanes):
@@ -482,7 +483,7 @@ class SelfPlaySession:
         n_req = len(game_id)
         self._last_ranges = [(0, n_req)]
         t0 = time.perf_counter()
-        S = ln.n_slots
+        S = ln.io_rows
         h_logits = torch.zeros(S, 7, dtype=torch.float32).pin_memory()
         h_qp = torch.zeros(S, dtype=torch.float32).pin_memory()
         h_qn = torch.zeros(S, dtype=torch.float32).pin_memory()

@@ -76,7 +76,7 @@ typedef struct {
   uint32_t eval_cache_entries; /* with C4A0_FLAG_EVAL_CACHE: entries (96 B each) of the evaluation cache, rounded
                                   up to a power of two; 0 = sized from n_slots * n_mcts_iterations and the
                                   free device memory */
-  uint32_t spec_rows;          /* with C4A0_FLAG_SPECULATE: rows a small batch is topped up to (0 = 2048) */
+  uint32_t spec_rows;          /* with C4A0_FLAG_SPECULATE: rows a small batch is topped up to (0 = 8192, at most n_slots) */
 } c4a0_config;
 
 /* Evaluate every waiting leaf even when several games wait on the same (position, model); by default
@@ -92,11 +92,12 @@ typedef struct {
 #define C4A0_FLAG_EVAL_CACHE 2u
 /* Needs C4A0_FLAG_EVAL_CACHE.  While a tick's batch is small (the first plies, when all games share a
  * few positions, and the tail of a job, when few games are left) the network runs far below capacity
- * and a tick costs the same whatever its rows.  With this flag such batches are topped up to
- * spec_rows with the children of the leaves that are being expanded; the answers go into the
+ * and a tick costs the same whatever its rows.  With this flag batches for which the games ask for
+ * at most min(spec_rows / 2, 1024) rows are topped up to spec_rows with the children of the leaves that are being expanded; the answers go into the
  * evaluation cache, so that selection finds them answered when it gets there, and a game may then run
  * several simulations per tick (4 x max_inline_sims).  Same assumption and same guarantee as the
- * cache: game records do not change.  Rows of these evaluations have row_slot 0xffffffff. */
+ * cache: game records do not change.  Rows of these evaluations have row_slot 0xffffffff.  The I/O
+ * buffers must hold c4a0_engine_io_rows() = n_slots + spec_rows rows. */
 #define C4A0_FLAG_SPECULATE 4u
 
 typedef struct {
@@ -136,14 +137,18 @@ int c4a0_engine_create(const c4a0_config *cfg, c4a0_engine **out);
 void c4a0_engine_destroy(c4a0_engine *e);
 /* bytes of device memory the engine holds (arenas + state + sample store) */
 size_t c4a0_engine_device_bytes(const c4a0_engine *e);
+/* rows the NN I/O buffers must have: n_slots, or n_slots + spec_rows with C4A0_FLAG_SPECULATE (every
+ * live game can ask for a row of its own on top of the speculative ones) */
+uint32_t c4a0_engine_io_rows(const c4a0_engine *e);
 
 /* NN I/O buffers, caller-owned device memory (DLPack / torch tensors):
- *   planes_dev : [n_slots][plane_stride] f32 or bf16 (cfg.plane_dtype); the first 84 elements of a
+ *   planes_dev : [io_rows][plane_stride] f32 or bf16 (cfg.plane_dtype); the first 84 elements of a
  *                row are the [2][6][7] planes                          <- pybridge.rs:202-221
- *   logits_dev : [n_slots][7] f32, q_penalty_dev / q_no_penalty_dev : [n_slots] f32
+ *   logits_dev : [io_rows][7] f32, q_penalty_dev / q_no_penalty_dev : [io_rows] f32   (io_rows =
+ *                c4a0_engine_io_rows(): n_slots unless speculation is on)
  *                                                                      <- pybridge.rs:175-196
  * Rows are dense: after set_requests()/step() rows [0, n_rows) hold the distinct leaf positions that
- * wait for an answer (n_rows <= n_slots, reported by poll()), in no particular order; the network
+ * wait for an answer (n_rows <= io_rows, reported by poll()), in no particular order; the network
  * must fill the same rows of the three output buffers before the next step().  Rows >= n_rows are
  * ignored. */
 int c4a0_engine_bind_io(c4a0_engine *e, void *planes_dev, const float *logits_dev,
@@ -181,7 +186,7 @@ int c4a0_engine_stats(c4a0_engine *e, c4a0_stats *out, void *stream);
 
 /* Per-row view for the numpy-callback compatibility path and for tests: *n_rows, and for each live
  * row the leaf position and the model that has to evaluate it (mcts.rs:70-76).  The arrays must hold
- * n_slots entries; any of them may be NULL. */
+ * c4a0_engine_io_rows() entries; any of them may be NULL. */
 int c4a0_engine_fetch_rows(c4a0_engine *e, uint32_t *n_rows, uint64_t *leaf_mask,
                            uint64_t *leaf_value, uint64_t *model_id, void *stream);
 
@@ -193,7 +198,7 @@ int c4a0_engine_rows_dev(c4a0_engine *e, uint32_t **row_slot_dev, uint64_t **row
 /* ---- the host loop ------------------------------------------------------------------------
  * A network evaluator as CUDA graphs: graph_exec (a cudaGraphExec_t) reads rows [0, rows) of the
  * engine's planes buffer and writes the same rows of its logits / q buffers.  Pass several sizes,
- * sorted ascending, the largest covering n_slots; every tick the smallest one that covers n_rows is
+ * sorted ascending, the largest covering c4a0_engine_io_rows(); every tick the smallest one that covers n_rows is
  * launched. */
 typedef struct {
   uint32_t rows;

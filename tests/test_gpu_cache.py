@@ -136,7 +136,7 @@ def test_speculation_fills_spare_rows_and_saves_ticks():
             if p.n_finished == p.n_requests:
                 break
         ticks.append(t + 1)
-        assert seen_max <= n_slots
+        assert seen_max <= e.io_rows
         outs.append(e.fetch_results())
         stats.append(e.stats())
         e.close()

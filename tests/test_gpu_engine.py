@@ -111,11 +111,12 @@ def _make_engine(n_slots, n_req, n_iter, c_expl, c_pen, **kw):
     from c4a0_b200.engine import Engine
 
     e = Engine(n_slots, n_req, n_iter, c_expl, c_pen, **kw)
+    R = e.io_rows  # n_slots (+ the speculative rows)
     io = dict(
-        planes=torch.zeros(n_slots, 2, 6, 7, device="cuda"),
-        logits=torch.zeros(n_slots, 7, device="cuda"),
-        qp=torch.zeros(n_slots, device="cuda"),
-        qn=torch.zeros(n_slots, device="cuda"),
+        planes=torch.zeros(R, 2, 6, 7, device="cuda"),
+        logits=torch.zeros(R, 7, device="cuda"),
+        qp=torch.zeros(R, device="cuda"),
+        qn=torch.zeros(R, device="cuda"),
     )
     e.bind_io(io["planes"].data_ptr(), io["logits"].data_ptr(), io["qp"].data_ptr(), io["qn"].data_ptr())
     return e, io

@@ -24,7 +24,7 @@ with torch.cuda.stream(ln.stream):
     s = ln.stream.cuda_stream
     ln.engine.set_requests(ids, z, z, s)
     for tick in range(1, 20001):
-        ln.evaluate(ev, n)
+        ln.evaluate(ev, ln.io_rows)
         if tick in (300, 700, 1500, 3000, 5000, 7000, 9000, 10500):
             d = ln.engine.debug_phases(s).astype(np.int64)
             act = d[:, 7] > 0
@@ -35,7 +35,7 @@ with torch.cuda.stream(ln.stream):
             print("   max :", {k: int(a[:, i].max()) for i, k in enumerate(names)})
             print("   slowest game: %.1f us at 1.9 GHz" % (a[:, 7].max() / 1900))
             x, y = ln.engine.step_timed(s)
-            ln.evaluate(ev, n)
+            ln.evaluate(ev, ln.io_rows)
             print("   step_timed: k_step %.1f us k_tail %.1f us" % (x * 1e3, y * 1e3))
         else:
             ln.engine.step(s)
