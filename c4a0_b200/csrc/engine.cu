@@ -3,7 +3,7 @@
 //
 // What the reference does per game with a heap tree of Rc<RefCell<Node>> (rust/src/mcts.rs:332-355)
 // and a thread pool (rust/src/self_play.rs), this file does for thousands of games at once with
-// struct-of-arrays trees in HBM:
+// block-structured trees in HBM:
 //
 //   * A tree is a bump-allocated array of 160-byte BLOCKS.  A block belongs to one expanded node
 //     and holds its 7 children: one 16-byte record {N, Qp, Qn, P} per child plus child[8] block
@@ -29,6 +29,12 @@
 //     inserts (position, model) into an epoch-tagged hash table; the first game to claim a key
 //     draws the next row number from an atomic counter and writes the input planes of that row,
 //     later games with the same key just remember who leads it.  Rows are dense, 0..n_rows-1.
+//   * Optionally (C4A0_FLAG_EVAL_CACHE) every answer of the network is kept, for the duration of a
+//     job, in a direct-mapped table keyed by (position, model): a leaf the job has evaluated before
+//     is answered inside the tick and the game goes on to its next simulation.  On top of that
+//     (C4A0_FLAG_SPECULATE) small batches are topped up with the children of the leaves being
+//     expanded, whose answers land in the same table before selection gets to them.  Both assume an
+//     evaluator that is a pure function of (model, position); game records do not change.
 //
 // One tick = k_step, then the network on rows [0, n_rows).  The last CTA of k_step to finish closes
 // the tick: it compacts the (few) arenas that filled up and publishes the tick's status (n_rows,
