@@ -343,12 +343,7 @@ class FusedNet(FoldedNet):
         w_in, b_in = w0[:, F:], b0[F:]
         w2 = torch.cat([wh, w_in @ wh], dim=0)           # [F + 96, 2F]
         b2 = bh + b_in @ wh
-        # both output layers as one block-diagonal GEMM over [policy hidden | value hidden]
-        wo = torch.zeros(2 * F, 16, dtype=torch.float64, device=w0.device)
-        wo[:F, :8] = self.wpf.double()
-        wo[F:, 8:] = self.wvf.double()
-        bo = torch.cat([self.bpf.double(), self.bvf.double()])
-        for name, t in (("f_w1", w1), ("f_b1", b1), ("f_w2", w2), ("f_b2", b2), ("f_wo", wo), ("f_bo", bo)):
+        for name, t in (("f_w1", w1), ("f_b1", b1), ("f_w2", w2), ("f_b2", b2)):
             t = t.to(self.dtype).contiguous()
             if hasattr(self, name):
                 getattr(self, name).copy_(t)
@@ -366,9 +361,6 @@ class FusedNet(FoldedNet):
         self.f_b1.copy_(b0[:F])
         self.f_w2.copy_(torch.cat([wh, w0[:, F:] @ wh], dim=0))
         self.f_b2.copy_(bh + b0[F:] @ wh)
-        self.f_wo[:F, :8].copy_(self.wpf)
-        self.f_wo[F:, 8:].copy_(self.wvf)
-        self.f_bo.copy_(torch.cat([self.bpf, self.bvf]))
         return self
 
     def forward(self, buf: torch.Tensor, out=None):
@@ -392,17 +384,6 @@ class FusedNet(FoldedNet):
             buf[:, :F] = torch.relu(torch.addmm(self.f_b1, x0, self.f_w1))
             y = torch.relu(torch.addmm(self.f_b2, buf, self.f_w2))
         hp, hv = y[:, :F], y[:, F:]
-        if buf.is_cuda and self._strided_out_ok and self.n_p != 1 and self.n_v != 1:
-            # the last hidden layer of each head writes back into its half of y, so that both output
-            # layers are one GEMM over y (a layer never writes the buffer it reads: n_p, n_v != 1)
-            for i in range(self.n_p):
-                w, b = getattr(self, f"wp{i}"), getattr(self, f"bp{i}")
-                hp = torch._addmm_activation(b, hp, w, out=y[:, :F]) if i == self.n_p - 1 else torch._addmm_activation(b, hp, w)
-            for i in range(self.n_v):
-                w, b = getattr(self, f"wv{i}"), getattr(self, f"bv{i}")
-                hv = torch._addmm_activation(b, hv, w, out=y[:, F:]) if i == self.n_v - 1 else torch._addmm_activation(b, hv, w)
-            o = torch.addmm(self.f_bo, y, self.f_wo)  # [B, 16]: policy in columns 0..7, values in 8..15
-            return _output_stage(o, o[:, 8:], out)
         for i in range(self.n_p):
             hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
         for i in range(self.n_v):
