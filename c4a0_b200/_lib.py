@@ -153,6 +153,7 @@ SIGNATURES = {
     "c4a0_rules_batch": (C.c_int, [C.c_int, _P, _P, C.c_size_t, C.c_float] + [_P] * 10),
     "c4a0_math_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_size_t]),
     "c4a0_softmax_batch": (C.c_int, [C.c_int, _P, _P, _P, C.c_size_t]),
+    "c4a0_heads": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, C.c_uint32, _P, _P, _P, _P]),
     "c4a0_head_epilogue": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "c4a0_sample_batch": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_size_t]),
     "c4a0_host_logf": (None, [_P, _P, C.c_size_t]),

@@ -131,9 +131,123 @@ __global__ void k_head_epilogue(const T* __restrict__ pol, const T* __restrict__
   qn[r] = tanhf(head_ld(val + (size_t)r * ldv + 1));
 }
 
+// nn.py:100-130 — both output layers and the output stage, one warp per row.  The 9 weight rows live in
+// shared memory as f32; a lane owns the 8-element chunks lane, lane + 32, ... of the row.
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+constexpr int HEADS_WARPS = 8;
+template <typename T>
+__global__ void __launch_bounds__(HEADS_WARPS * 32) k_heads(const T* __restrict__ hp, const T* __restrict__ hv, uint32_t ldp,
+                                                            uint32_t ldv, uint32_t F, const T* __restrict__ wp_t,
+                                                            const float* __restrict__ bp, const T* __restrict__ wv_t,
+                                                            const float* __restrict__ bv, uint32_t rows,
+                                                            float* __restrict__ logits, float* __restrict__ qp,
+                                                            float* __restrict__ qn) {
+  // [9][2][F/2]: 7 policy rows, then 2 value rows; elements 8c..8c+3 of a row sit at [0][4c..], elements
+  // 8c+4..8c+7 at [1][4c..], so that consecutive lanes read consecutive 16-byte vectors (no bank conflicts)
+  extern __shared__ float sh_w[];
+  const uint32_t H = F >> 1;
+  for (uint32_t i = threadIdx.x; i < 9u * F; i += blockDim.x) {
+    const uint32_t o = i / F, k = i - o * F;
+    const float w = o < 7 ? head_ld(wp_t + (size_t)o * F + k) : head_ld(wv_t + (size_t)(o - 7) * F + k);
+    sh_w[(size_t)o * F + ((k >> 2) & 1u) * H + ((k >> 3) << 2) + (k & 3u)] = w;
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t chunks = F >> 3;
+  for (uint32_t r = blockIdx.x * HEADS_WARPS + warp; r < rows; r += gridDim.x * HEADS_WARPS) {
+    float acc[9];
+#pragma unroll
+    for (int o = 0; o < 9; o++) acc[o] = 0.0f;
+    const T* rp = hp + (size_t)r * ldp;
+    const T* rv = hv + (size_t)r * ldv;
+    for (uint32_t c = lane; c < chunks; c += 32u) {
+      float a[8], b[8];
+      load8<T>(rp + 8u * c, a);
+      load8<T>(rv + 8u * c, b);
+#pragma unroll
+      for (int o = 0; o < 7; o++) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
+        const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
+        acc[o] += a[0] * w0.x + a[1] * w0.y + a[2] * w0.z + a[3] * w0.w + a[4] * w1.x + a[5] * w1.y + a[6] * w1.z + a[7] * w1.w;
+      }
+#pragma unroll
+      for (int o = 7; o < 9; o++) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
+        const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
+        acc[o] += b[0] * w0.x + b[1] * w0.y + b[2] * w0.z + b[3] * w0.w + b[4] * w1.x + b[5] * w1.y + b[6] * w1.z + b[7] * w1.w;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+    }
+    if (lane == 0) {
+      float x[7], mx = -c4::f32_inf();
+#pragma unroll
+      for (int k = 0; k < 7; k++) {
+        x[k] = acc[k] + bp[k];
+        mx = fmaxf(mx, x[k]);
+      }
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 7; k++) s += expf(x[k] - mx);
+      const float lse = mx + logf(s);
+#pragma unroll
+      for (int k = 0; k < 7; k++) logits[(size_t)r * 7 + k] = x[k] - lse;
+      qp[r] = tanhf(acc[7] + bv[0]);
+      qn[r] = tanhf(acc[8] + bv[1]);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int c4a0_heads(const void* hp, const void* hv, uint32_t dtype, uint32_t ld_hp, uint32_t ld_hv, uint32_t F, const void* wp_t,
+               const float* bp, const void* wv_t, const float* bv, uint32_t rows, float* logits, float* qp, float* qn,
+               void* stream) {
+  if (!hp || !hv || !wp_t || !bp || !wv_t || !bv || !logits || !qp || !qn) return fail(C4A0_E_INVALID, "null argument");
+  if (dtype > C4A0_PLANES_BF16 || F == 0 || (F & 7u) || ld_hp < F || ld_hv < F || (ld_hp & 7u) || (ld_hv & 7u))
+    return fail(C4A0_E_INVALID, "bad head layout: F and the row strides must be multiples of 8");
+  if ((((uintptr_t)hp | (uintptr_t)hv) & 15u) != 0) return fail(C4A0_E_INVALID, "activations must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const size_t smem = (size_t)9 * F * sizeof(float);
+  if (smem > 200 * 1024) return fail(C4A0_E_INVALID, "F too large for c4a0_heads");
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned grid = (rows + HEADS_WARPS - 1) / HEADS_WARPS;
+  if (grid > 148u * 2u) grid = 148u * 2u;  // persistent: each CTA fills the weights once and strides over the rows
+  if (dtype == C4A0_PLANES_BF16) {
+    auto k = k_heads<__nv_bfloat16>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, HEADS_WARPS * 32, smem, s>>>((const __nv_bfloat16*)hp, (const __nv_bfloat16*)hv, ld_hp, ld_hv, F,
+                                           (const __nv_bfloat16*)wp_t, bp, (const __nv_bfloat16*)wv_t, bv, rows, logits, qp, qn);
+  } else {
+    auto k = k_heads<float>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, HEADS_WARPS * 32, smem, s>>>((const float*)hp, (const float*)hv, ld_hp, ld_hv, F, (const float*)wp_t, bp,
+                                           (const float*)wv_t, bv, rows, logits, qp, qn);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
 
 int c4a0_head_epilogue(const void* policy_head, const void* value_head, uint32_t dtype, uint32_t ld_policy,
                        uint32_t ld_value, uint32_t rows, float* logits, float* qp, float* qn, void* stream) {

@@ -184,6 +184,9 @@ class FoldedNet(nn.Module):
         self.n_blocks, self.joint_first, self.n_p, self.n_v = meta
         for name, t in tensors.items():
             self.register_buffer(name, t.to(device=device, dtype=dtype).contiguous(), persistent=False)
+        # biases of the output layers in f32 for the fused output kernel
+        self.register_buffer("bpf32", tensors["bpf"].to(device=device, dtype=torch.float32).contiguous(), persistent=False)
+        self.register_buffer("bvf32", tensors["bvf"].to(device=device, dtype=torch.float32).contiguous(), persistent=False)
 
     @torch.no_grad()
     def refresh(self, model: ConnectFourNet) -> "FoldedNet":
@@ -194,6 +197,8 @@ class FoldedNet(nn.Module):
             raise ValueError("refresh() needs a model of the same architecture")
         for name, t in tensors.items():
             getattr(self, name).copy_(t)
+        self.bpf32.copy_(tensors["bpf"])
+        self.bvf32.copy_(tensors["bvf"])
         return self
 
     @classmethod
@@ -264,6 +269,9 @@ class FoldedNet(nn.Module):
         bvf = torch.zeros(8, dtype=torch.float64, device=dev0)
         bvf[:2] = vf[1]
         out.update(wpf=wpf, bpf=bpf, wvf=wvf, bvf=bvf)
+        # the same two layers transposed, for the fused output kernel (c4a0_heads): [7][F], [2][F]
+        out["wpf_t"] = pf[0].t().contiguous()
+        out["wvf_t"] = vf[0].t().contiguous()
         return out, (n_blocks, joint_first, len(ph), len(vh))
 
     @staticmethod
@@ -293,12 +301,35 @@ class FoldedNet(nn.Module):
             hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
         for i in range(self.n_v):
             hv = self._lin_relu(hv, getattr(self, f"wv{i}"), getattr(self, f"bv{i}"))
+        return self._heads(hp, hv, out)
+
+    def _heads(self, hp: torch.Tensor, hv: torch.Tensor, out=None):
+        """Output layers + output stage from the heads' last hidden activations.  With `out` (the engine's
+        logits / q buffers) on CUDA this is one kernel of the engine library (c4a0_heads); otherwise two
+        GEMMs and the PyTorch output stage."""
+        if out is not None and hp.is_cuda:
+            from . import _lib as L
+
+            logits, qp, qn = out
+            rows = hp.shape[0]
+            fits = (hp.dtype == hv.dtype == self.dtype and self.dtype in (torch.float32, torch.bfloat16)
+                    and hp.stride(1) == 1 and hv.stride(1) == 1 and self.F % 8 == 0
+                    and hp.stride(0) % 8 == 0 and hv.stride(0) % 8 == 0
+                    and hp.data_ptr() % 16 == 0 and hv.data_ptr() % 16 == 0
+                    and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == rows for t in out))
+            if fits:
+                L.check(L.lib().c4a0_heads(
+                    hp.data_ptr(), hv.data_ptr(), L.PLANES_BF16 if self.dtype == torch.bfloat16 else L.PLANES_F32,
+                    hp.stride(0), hv.stride(0), self.F, self.wpf_t.data_ptr(), self.bpf32.data_ptr(),
+                    self.wvf_t.data_ptr(), self.bvf32.data_ptr(), rows, logits.data_ptr(), qp.data_ptr(), qn.data_ptr(),
+                    torch.cuda.current_stream(hp.device).cuda_stream))
+                return out
         return _output_stage(torch.addmm(self.bpf, hp, self.wpf), torch.addmm(self.bvf, hv, self.wvf), out)
 
     def flops_per_position(self) -> int:
         total = 0
         for name, t in self.named_buffers():
-            if name.startswith("w"):
+            if name.startswith("w") and not name.endswith("_t"):
                 total += 2 * t.shape[0] * t.shape[1]
         return total
 
@@ -388,7 +419,7 @@ class FusedNet(FoldedNet):
             hp = self._lin_relu(hp, getattr(self, f"wp{i}"), getattr(self, f"bp{i}"))
         for i in range(self.n_v):
             hv = self._lin_relu(hv, getattr(self, f"wv{i}"), getattr(self, f"bv{i}"))
-        return _output_stage(torch.addmm(self.bpf, hp, self.wpf), torch.addmm(self.bvf, hv, self.wvf), out)
+        return self._heads(hp, hv, out)
 
     def _probe_strided_out(self, buf: torch.Tensor) -> bool:
         """Does the cuBLASLt epilogue path accept a row-strided `out`?  Checked once, numerically."""

@@ -298,6 +298,16 @@ int c4a0_head_epilogue(const void *policy_head, const void *value_head, uint32_t
                        uint32_t ld_policy, uint32_t ld_value, uint32_t rows, float *logits_dev,
                        float *q_penalty_dev, float *q_no_penalty_dev, void *stream);
 
+/* The two output layers AND the output stage in one kernel: policy = log_softmax(hp . Wp + bp) over 7
+ * columns, values = tanh(hv . Wv + bv) over 2 (src/c4a0/nn.py:100-130), from the heads' last hidden
+ * activations hp / hv [rows][ld] (F valid columns, F a multiple of 8; C4A0_PLANES_F32 or _BF16), with
+ * the weights given transposed, wp_t [7][F] and wv_t [2][F] in the activations' dtype, biases f32.
+ * One warp per row, f32 accumulation; replaces two 8-column GEMMs and the output stage.  All
+ * pointers are device pointers; the kernel is enqueued on `stream` (capturable). */
+int c4a0_heads(const void *hp, const void *hv, uint32_t dtype, uint32_t ld_hp, uint32_t ld_hv, uint32_t F,
+               const void *wp_t, const float *bp, const void *wv_t, const float *bv, uint32_t rows,
+               float *logits_dev, float *q_penalty_dev, float *q_no_penalty_dev, void *stream);
+
 /* The same math compiled for the host (no GPU needed); used to pin the restated logf/expf and the
  * sampler against libm / the oracle in the CPU test-suite. */
 void c4a0_host_logf(const float *in, float *out, size_t n);
