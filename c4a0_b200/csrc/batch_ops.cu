@@ -162,14 +162,16 @@ __global__ void __launch_bounds__(HEADS_WARPS * 32) k_heads(const T* __restrict_
   // 8c+4..8c+7 at [1][4c..], so that consecutive lanes read consecutive 16-byte vectors (no bank conflicts)
   extern __shared__ float sh_w[];
   const uint32_t H = F >> 1;
-  for (uint32_t i = threadIdx.x; i < 9u * F; i += blockDim.x) {
-    const uint32_t o = i / F, k = i - o * F;
-    const float w = o < 7 ? head_ld(wp_t + (size_t)o * F + k) : head_ld(wv_t + (size_t)(o - 7) * F + k);
-    sh_w[(size_t)o * F + ((k >> 2) & 1u) * H + ((k >> 3) << 2) + (k & 3u)] = w;
+  const uint32_t chunks = F >> 3;
+  for (uint32_t i = threadIdx.x; i < 9u * chunks; i += blockDim.x) {  // one 8-element chunk per step
+    const uint32_t o = i / chunks, c = i - o * chunks;
+    float w[8];
+    load8<T>((o < 7 ? wp_t + (size_t)o * F : wv_t + (size_t)(o - 7) * F) + 8u * c, w);
+    *reinterpret_cast<float4*>(sh_w + (size_t)o * F + 4u * c) = make_float4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<float4*>(sh_w + (size_t)o * F + H + 4u * c) = make_float4(w[4], w[5], w[6], w[7]);
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t chunks = F >> 3;
   for (uint32_t r = blockIdx.x * HEADS_WARPS + warp; r < rows; r += gridDim.x * HEADS_WARPS) {
     float acc[9];
 #pragma unroll
@@ -184,13 +186,13 @@ __global__ void __launch_bounds__(HEADS_WARPS * 32) k_heads(const T* __restrict_
       for (int o = 0; o < 7; o++) {
         const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
         const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
-        acc[o] += a[0] * w0.x + a[1] * w0.y + a[2] * w0.z + a[3] * w0.w + a[4] * w1.x + a[5] * w1.y + a[6] * w1.z + a[7] * w1.w;
+        acc[o] = fmaf(a[0], w0.x, fmaf(a[1], w0.y, fmaf(a[2], w0.z, fmaf(a[3], w0.w, fmaf(a[4], w1.x, fmaf(a[5], w1.y, fmaf(a[6], w1.z, fmaf(a[7], w1.w, acc[o]))))))));
       }
 #pragma unroll
       for (int o = 7; o < 9; o++) {
         const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
         const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
-        acc[o] += b[0] * w0.x + b[1] * w0.y + b[2] * w0.z + b[3] * w0.w + b[4] * w1.x + b[5] * w1.y + b[6] * w1.z + b[7] * w1.w;
+        acc[o] = fmaf(b[0], w0.x, fmaf(b[1], w0.y, fmaf(b[2], w0.z, fmaf(b[3], w0.w, fmaf(b[4], w1.x, fmaf(b[5], w1.y, fmaf(b[6], w1.z, fmaf(b[7], w1.w, acc[o]))))))));
       }
     }
 #pragma unroll
