@@ -178,21 +178,29 @@ __global__ void __launch_bounds__(HEADS_WARPS * 32) k_heads(const T* __restrict_
     for (int o = 0; o < 9; o++) acc[o] = 0.0f;
     const T* rp = hp + (size_t)r * ldp;
     const T* rv = hv + (size_t)r * ldv;
-    for (uint32_t c = lane; c < chunks; c += 32u) {
-      float a[8], b[8];
-      load8<T>(rp + 8u * c, a);
-      load8<T>(rv + 8u * c, b);
+    // four chunks per lane in flight: all eight loads are issued before the first is used
+    for (uint32_t c0 = lane; c0 < chunks; c0 += 128u) {
+      float a[4][8], b[4][8];
 #pragma unroll
-      for (int o = 0; o < 7; o++) {
-        const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
-        const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
-        acc[o] = fmaf(a[0], w0.x, fmaf(a[1], w0.y, fmaf(a[2], w0.z, fmaf(a[3], w0.w, fmaf(a[4], w1.x, fmaf(a[5], w1.y, fmaf(a[6], w1.z, fmaf(a[7], w1.w, acc[o]))))))));
+      for (int j = 0; j < 4; j++) {
+        const uint32_t c = c0 + 32u * j;
+        if (c < chunks) {
+          load8<T>(rp + 8u * c, a[j]);
+          load8<T>(rv + 8u * c, b[j]);
+        }
       }
 #pragma unroll
-      for (int o = 7; o < 9; o++) {
-        const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
-        const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
-        acc[o] = fmaf(b[0], w0.x, fmaf(b[1], w0.y, fmaf(b[2], w0.z, fmaf(b[3], w0.w, fmaf(b[4], w1.x, fmaf(b[5], w1.y, fmaf(b[6], w1.z, fmaf(b[7], w1.w, acc[o]))))))));
+      for (int j = 0; j < 4; j++) {
+        const uint32_t c = c0 + 32u * j;
+        if (c < chunks) {
+#pragma unroll
+          for (int o = 0; o < 9; o++) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
+            const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
+            const float(&v)[8] = o < 7 ? a[j] : b[j];
+            acc[o] = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, acc[o]))))))));
+          }
+        }
       }
     }
 #pragma unroll
@@ -200,22 +208,22 @@ __global__ void __launch_bounds__(HEADS_WARPS * 32) k_heads(const T* __restrict_
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
     }
-    if (lane == 0) {
-      float x[7], mx = -c4::f32_inf();
+    // output stage across the lanes: lane k < 7 owns policy column k, lanes 7 and 8 the two values
+    float v = acc[0];
 #pragma unroll
-      for (int k = 0; k < 7; k++) {
-        x[k] = acc[k] + bp[k];
-        mx = fmaxf(mx, x[k]);
-      }
-      float s = 0.0f;
+    for (int k = 1; k < 9; k++) v = lane == (uint32_t)k ? acc[k] : v;
+    const float x = lane < 7u ? v + bp[lane] : -c4::f32_inf();
+    float mx = x;
 #pragma unroll
-      for (int k = 0; k < 7; k++) s += expf(x[k] - mx);
-      const float lse = mx + logf(s);
+    for (int m = 4; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));  // lanes 0..7
+    mx = __shfl_sync(0xffffffffu, mx, 0);
+    float e = lane < 7u ? expf(x - mx) : 0.0f;
 #pragma unroll
-      for (int k = 0; k < 7; k++) logits[(size_t)r * 7 + k] = x[k] - lse;
-      qp[r] = tanhf(acc[7] + bv[0]);
-      qn[r] = tanhf(acc[8] + bv[1]);
-    }
+    for (int m = 4; m >= 1; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+    const float lse = mx + logf(__shfl_sync(0xffffffffu, e, 0));
+    if (lane < 7u) logits[(size_t)r * 7 + lane] = x - lse;
+    if (lane == 7u) qp[r] = tanhf(v + bv[0]);
+    if (lane == 8u) qn[r] = tanhf(v + bv[1]);
   }
 }
 
@@ -235,7 +243,7 @@ int c4a0_heads(const void* hp, const void* hv, uint32_t dtype, uint32_t ld_hp, u
   if (smem > 200 * 1024) return fail(C4A0_E_INVALID, "F too large for c4a0_heads");
   cudaStream_t s = (cudaStream_t)stream;
   unsigned grid = (rows + HEADS_WARPS - 1) / HEADS_WARPS;
-  if (grid > 148u * 2u) grid = 148u * 2u;  // persistent: each CTA fills the weights once and strides over the rows
+  if (grid > 148u * 4u) grid = 148u * 4u;  // persistent: each CTA stages the weights once and strides over the rows
   if (dtype == C4A0_PLANES_BF16) {
     auto k = k_heads<__nv_bfloat16>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
