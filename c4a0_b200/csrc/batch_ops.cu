@@ -151,7 +151,7 @@ __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, flo
   }
 }
 constexpr int HEADS_WARPS = 8;
-template <typename T>
+template <typename T, int HEADS_ROWS>
 __global__ void __launch_bounds__(HEADS_WARPS * 32) k_heads(const T* __restrict__ hp, const T* __restrict__ hv, uint32_t ldp,
                                                             uint32_t ldv, uint32_t F, const T* __restrict__ wp_t,
                                                             const float* __restrict__ bp, const T* __restrict__ wv_t,
@@ -172,58 +172,61 @@ __global__ void __launch_bounds__(HEADS_WARPS * 32) k_heads(const T* __restrict_
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t r = blockIdx.x * HEADS_WARPS + warp; r < rows; r += gridDim.x * HEADS_WARPS) {
-    float acc[9];
+  // A warp takes HEADS_ROWS rows at a time, so that a weight vector read from shared memory is used for
+  // all of them (shared-memory bandwidth, not HBM, bounds a one-row-per-warp version) and eight global
+  // loads per lane are in flight.
+  for (uint32_t r0 = (blockIdx.x * HEADS_WARPS + warp) * HEADS_ROWS; r0 < rows; r0 += gridDim.x * HEADS_WARPS * HEADS_ROWS) {
+    float acc[HEADS_ROWS][9];
 #pragma unroll
-    for (int o = 0; o < 9; o++) acc[o] = 0.0f;
-    const T* rp = hp + (size_t)r * ldp;
-    const T* rv = hv + (size_t)r * ldv;
-    // four chunks per lane in flight: all eight loads are issued before the first is used
-    for (uint32_t c0 = lane; c0 < chunks; c0 += 128u) {
-      float a[4][8], b[4][8];
+    for (int q = 0; q < HEADS_ROWS; q++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t c = c0 + 32u * j;
-        if (c < chunks) {
-          load8<T>(rp + 8u * c, a[j]);
-          load8<T>(rv + 8u * c, b[j]);
-        }
+      for (int o = 0; o < 9; o++) acc[q][o] = 0.0f;
+    for (uint32_t c = lane; c < chunks; c += 32u) {
+      float a[HEADS_ROWS][8], b[HEADS_ROWS][8];
+#pragma unroll
+      for (int q = 0; q < HEADS_ROWS; q++) {
+        const uint32_t r = r0 + q < rows ? r0 + q : rows - 1u;  // a clamped duplicate instead of a branch
+        load8<T>(hp + (size_t)r * ldp + 8u * c, a[q]);
+        load8<T>(hv + (size_t)r * ldv + 8u * c, b[q]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t c = c0 + 32u * j;
-        if (c < chunks) {
+      for (int o = 0; o < 9; o++) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
+        const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
 #pragma unroll
-          for (int o = 0; o < 9; o++) {
-            const float4 w0 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + 4u * c);
-            const float4 w1 = *reinterpret_cast<const float4*>(sh_w + (size_t)o * F + H + 4u * c);
-            const float(&v)[8] = o < 7 ? a[j] : b[j];
-            acc[o] = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, acc[o]))))))));
-          }
+        for (int q = 0; q < HEADS_ROWS; q++) {
+          const float(&v)[8] = o < 7 ? a[q] : b[q];
+          acc[q][o] = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, acc[q][o]))))))));
         }
       }
     }
 #pragma unroll
-    for (int o = 0; o < 9; o++) {
+    for (int q = 0; q < HEADS_ROWS; q++) {
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+      for (int o = 0; o < 9; o++) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) acc[q][o] += __shfl_xor_sync(0xffffffffu, acc[q][o], m);
+      }
+      // output stage across the lanes: lane k < 7 owns policy column k, lanes 7 and 8 the two values
+      float v = acc[q][0];
+#pragma unroll
+      for (int k = 1; k < 9; k++) v = lane == (uint32_t)k ? acc[q][k] : v;
+      const float x = lane < 7u ? v + bp[lane] : -c4::f32_inf();
+      float mx = x;
+#pragma unroll
+      for (int m = 4; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));  // lanes 0..7
+      mx = __shfl_sync(0xffffffffu, mx, 0);
+      float e = lane < 7u ? expf(x - mx) : 0.0f;
+#pragma unroll
+      for (int m = 4; m >= 1; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+      const float lse = mx + logf(__shfl_sync(0xffffffffu, e, 0));
+      const uint32_t r = r0 + q;
+      if (r < rows) {
+        if (lane < 7u) logits[(size_t)r * 7 + lane] = x - lse;
+        if (lane == 7u) qp[r] = tanhf(v + bv[0]);
+        if (lane == 8u) qn[r] = tanhf(v + bv[1]);
+      }
     }
-    // output stage across the lanes: lane k < 7 owns policy column k, lanes 7 and 8 the two values
-    float v = acc[0];
-#pragma unroll
-    for (int k = 1; k < 9; k++) v = lane == (uint32_t)k ? acc[k] : v;
-    const float x = lane < 7u ? v + bp[lane] : -c4::f32_inf();
-    float mx = x;
-#pragma unroll
-    for (int m = 4; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));  // lanes 0..7
-    mx = __shfl_sync(0xffffffffu, mx, 0);
-    float e = lane < 7u ? expf(x - mx) : 0.0f;
-#pragma unroll
-    for (int m = 4; m >= 1; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
-    const float lse = mx + logf(__shfl_sync(0xffffffffu, e, 0));
-    if (lane < 7u) logits[(size_t)r * 7 + lane] = x - lse;
-    if (lane == 7u) qp[r] = tanhf(v + bv[0]);
-    if (lane == 8u) qn[r] = tanhf(v + bv[1]);
   }
 }
 
@@ -242,19 +245,24 @@ int c4a0_heads(const void* hp, const void* hv, uint32_t dtype, uint32_t ld_hp, u
   const size_t smem = (size_t)9 * F * sizeof(float);
   if (smem > 200 * 1024) return fail(C4A0_E_INVALID, "F too large for c4a0_heads");
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned grid = (rows + HEADS_WARPS - 1) / HEADS_WARPS;
+  // small batches: one row per warp, spread over the SMs; large ones: four rows per warp (weight reuse)
+  const bool wide = rows > 148u * 2u * HEADS_WARPS;
+  const unsigned per_cta = HEADS_WARPS * (wide ? 4 : 1);
+  unsigned grid = (rows + per_cta - 1) / per_cta;
   if (grid > 148u * 4u) grid = 148u * 4u;  // persistent: each CTA stages the weights once and strides over the rows
+#define C4A0_LAUNCH_HEADS(T, R)                                                                                        \
+  do {                                                                                                                 \
+    auto k = k_heads<T, R>;                                                                                            \
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    k<<<grid, HEADS_WARPS * 32, smem, s>>>((const T*)hp, (const T*)hv, ld_hp, ld_hv, F, (const T*)wp_t, bp, (const T*)wv_t, \
+                                           bv, rows, logits, qp, qn);                                                  \
+  } while (0)
   if (dtype == C4A0_PLANES_BF16) {
-    auto k = k_heads<__nv_bfloat16>;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, HEADS_WARPS * 32, smem, s>>>((const __nv_bfloat16*)hp, (const __nv_bfloat16*)hv, ld_hp, ld_hv, F,
-                                           (const __nv_bfloat16*)wp_t, bp, (const __nv_bfloat16*)wv_t, bv, rows, logits, qp, qn);
+    if (wide) C4A0_LAUNCH_HEADS(__nv_bfloat16, 4); else C4A0_LAUNCH_HEADS(__nv_bfloat16, 1);
   } else {
-    auto k = k_heads<float>;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, HEADS_WARPS * 32, smem, s>>>((const float*)hp, (const float*)hv, ld_hp, ld_hv, F, (const float*)wp_t, bp,
-                                           (const float*)wv_t, bv, rows, logits, qp, qn);
+    if (wide) C4A0_LAUNCH_HEADS(float, 4); else C4A0_LAUNCH_HEADS(float, 1);
   }
+#undef C4A0_LAUNCH_HEADS
   CK(cudaGetLastError());
   return 0;
 }
