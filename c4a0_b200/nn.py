@@ -175,6 +175,7 @@ class FoldedNet(nn.Module):
     """
 
     IN_PAD = 96
+    FUSED_HEADS_MAX_ROWS = 4096
 
     def __init__(self, model: ConnectFourNet, dtype: torch.dtype = torch.bfloat16, device=None):
         super().__init__()
@@ -307,7 +308,9 @@ class FoldedNet(nn.Module):
         """Output layers + output stage from the heads' last hidden activations.  With `out` (the engine's
         logits / q buffers) on CUDA this is one kernel of the engine library (c4a0_heads); otherwise two
         GEMMs and the PyTorch output stage."""
-        if out is not None and hp.is_cuda:
+        # measured on B200 (tools/nn_curve.py): the CUDA-core kernel wins below ~4,096 rows (one launch
+        # instead of three: 28.7 vs 32.8 us at 64 rows, 43 vs 49 us at 1,024), the tensor-core GEMMs above
+        if out is not None and hp.is_cuda and hp.shape[0] <= self.FUSED_HEADS_MAX_ROWS:
             from . import _lib as L
 
             logits, qp, qn = out

@@ -302,7 +302,8 @@ int c4a0_head_epilogue(const void *policy_head, const void *value_head, uint32_t
  * columns, values = tanh(hv . Wv + bv) over 2 (src/c4a0/nn.py:100-130), from the heads' last hidden
  * activations hp / hv [rows][ld] (F valid columns, F a multiple of 8; C4A0_PLANES_F32 or _BF16), with
  * the weights given transposed, wp_t [7][F] and wv_t [2][F] in the activations' dtype, biases f32.
- * One warp per row, f32 accumulation; replaces two 8-column GEMMs and the output stage.  All
+ * f32 accumulation on the CUDA cores: one launch instead of two 8-column GEMMs and the output stage,
+ * which pays for batches up to a few thousand rows (above that the tensor-core GEMMs win).  All
  * pointers are device pointers; the kernel is enqueued on `stream` (capturable). */
 int c4a0_heads(const void *hp, const void *hv, uint32_t dtype, uint32_t ld_hp, uint32_t ld_hv, uint32_t F,
                const void *wp_t, const float *bp, const void *wv_t, const float *bv, uint32_t rows,

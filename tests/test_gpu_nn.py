@@ -15,7 +15,7 @@ def _need_gpu():
 
 
 @pytest.mark.parametrize("form,dtype", [("folded", "float32"), ("fused", "float32"), ("fused", "bfloat16")])
-@pytest.mark.parametrize("rows", [1, 127, 4096])
+@pytest.mark.parametrize("rows", [1, 127, 4096, 5000])
 def test_fused_output_stage_matches_torch(form, dtype, rows):
     _need_gpu()
     from c4a0_b200.nn import ConnectFourNet, FoldedNet, FusedNet, default_config

@@ -11,9 +11,16 @@ from c4a0_b200.nn import ConnectFourNet, FusedNet, default_config  # noqa: E402
 torch.manual_seed(1337)
 model = ConnectFourNet(default_config()).cuda().eval()
 net = FusedNet(model, dtype=torch.bfloat16)
+if "--gemm-heads" in sys.argv:  # the two output layers as cuBLASLt GEMMs + c4a0_head_epilogue instead of c4a0_heads
+    from c4a0_b200.nn import _output_stage
+
+    net._heads = lambda hp, hv, out=None: _output_stage(torch.addmm(net.bpf, hp, net.wpf), torch.addmm(net.bvf, hv, net.wvf), out)
+sizes = (64, 128, 256, 512, 1024, 1536, 2048, 3072, 4096, 5120, 6144, 7168, 8192, 10240, 12288, 14336, 16384)
+if "--few" in sys.argv:
+    sizes = (64, 1024, 4096, 8192, 16384)
 flops = model.flops_per_position()
 s = torch.cuda.Stream()
-for B in (64, 128, 256, 512, 1024, 1536, 2048, 3072, 4096, 5120, 6144, 7168, 8192, 10240, 12288, 14336, 16384):
+for B in sizes:
     buf = torch.zeros(B, net.plane_stride, device="cuda", dtype=torch.bfloat16)
     out = (torch.zeros(B, 7, device="cuda"), torch.zeros(B, device="cuda"), torch.zeros(B, device="cuda"))
     with torch.cuda.stream(s), torch.no_grad():
