@@ -8,6 +8,15 @@ import torch  # noqa: E402
 
 from c4a0_b200.nn import ConnectFourNet, FusedNet, default_config  # noqa: E402
 
+if "--tunable" in sys.argv:  # let PyTorch's TunableOp pick the GEMM algorithm per shape (tuned on first use)
+    import time
+    import torch.cuda.tunable as tunable
+
+    tunable.enable(True)
+    tunable.tuning_enable(True)
+    tunable.set_max_tuning_duration(30)
+    tunable.set_max_tuning_iterations(20)
+    tunable.set_filename("/tmp/tunable.csv")
 torch.manual_seed(1337)
 model = ConnectFourNet(default_config()).cuda().eval()
 net = FusedNet(model, dtype=torch.bfloat16)
@@ -23,9 +32,13 @@ s = torch.cuda.Stream()
 for B in sizes:
     buf = torch.zeros(B, net.plane_stride, device="cuda", dtype=torch.bfloat16)
     out = (torch.zeros(B, 7, device="cuda"), torch.zeros(B, device="cuda"), torch.zeros(B, device="cuda"))
+    import time as _t
+    t0 = _t.time()
     with torch.cuda.stream(s), torch.no_grad():
         for _ in range(3):
             net(buf, out=out)
+        s.synchronize()
+        warm = _t.time() - t0
         s.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
@@ -39,4 +52,4 @@ for B in sizes:
         b.record(s)
         s.synchronize()
     us = a.elapsed_time(b) / 200 * 1e3
-    print(f"B={B:6d} {us:8.1f} us  {us / B * 1e3:7.1f} ns/row  {B * flops / us / 1e6:7.1f} TFLOP/s (reference-form flops)", flush=True)
+    print(f"B={B:6d} {us:8.1f} us  {us / B * 1e3:7.1f} ns/row  {B * flops / us / 1e6:7.1f} TFLOP/s (reference-form flops)  warm-up {warm:.2f} s", flush=True)
