@@ -161,6 +161,7 @@ SIGNATURES = {
     "c4a0_host_sample": (C.c_int, [_P, C.c_float, C.c_uint64, _P]),
     "c4a0_host_terminal_state": (C.c_int, [C.c_uint64, C.c_uint64]),
     "c4a0_host_make_move": (None, [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "c4a0_host_pos_key": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "c4a0_host_flip_h": (None, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "c4a0_host_shuffle": (None, [C.c_uint64, _P, C.c_size_t]),
 }

@@ -411,6 +411,7 @@ void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t* om, uint64_t* ov)
   *om = r.mask;
   *ov = r.value;
 }
+uint64_t c4a0_host_pos_key(uint64_t mask, uint64_t value) { return c4::pos_key(Pos{mask, value}); }
 void c4a0_host_shuffle(uint64_t seed, uint32_t* idx, size_t n) { c4::shuffle_indices(seed, idx, n); }
 
 }  // extern "C"

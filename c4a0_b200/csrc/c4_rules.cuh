@@ -103,6 +103,15 @@ C4_HD uint64_t flip_rows(uint64_t x) {
   for (int c = 0; c < N_COLS; c++) r |= ((x >> c) & COL0) << (N_COLS - 1 - c);
   return r;
 }
+// 49 bits that identify a position (key of the evaluation cache, engine.cu): the side-to-move's
+// stones plus one marker bit on the first empty cell of every column (row 6 for a full column).
+// Stones obey gravity, so the marker is the highest set bit of its column and the key decodes
+// uniquely: below the marker, 1 = side to move, 0 = opponent.
+C4_HD uint64_t pos_key(Pos p) {
+  const uint64_t rows7 = (1ull << 49) - 1ull;
+  return p.value | ((((p.mask << 7) | 0x7full) & ~p.mask) & rows7);
+}
+
 C4_HD Pos flip_h(Pos p) {
   Pos r;
   r.mask = flip_rows(p.mask);

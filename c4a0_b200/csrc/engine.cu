@@ -570,13 +570,7 @@ __device__ __forceinline__ bool apply_answer(const Dev& D, const Lanes& L, Game&
 }
 
 // ---- evaluation cache ---------------------------------------------------------------------------
-// 49 bits that identify a position: the side-to-move's stones plus one marker bit on the first
-// empty cell of every column (row 6 for a full column).  Stones obey gravity, so the marker is the
-// highest set bit of its column and the key decodes uniquely.
-__device__ __forceinline__ uint64_t pos_key(Pos p) {
-  const uint64_t rows7 = (1ull << 49) - 1ull;
-  return p.value | ((((p.mask << 7) | 0x7full) & ~p.mask) & rows7);
-}
+using c4::pos_key;  // c4_rules.cuh: the 49-bit key of the evaluation cache
 constexpr unsigned long long TAG_DYING = 1ull << 32;
 
 // The game's freshly selected, non-terminal leaf: answered from the cache (-> true, values in

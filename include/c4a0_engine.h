@@ -318,6 +318,8 @@ int c4a0_host_terminal_state(uint64_t mask, uint64_t value);
 void c4a0_host_make_move(uint64_t mask, uint64_t value, int col, uint64_t *out_mask,
                          uint64_t *out_value);
 void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t *out_mask, uint64_t *out_value);
+/* the evaluation cache's 49-bit key of a position (injective on positions reachable by play) */
+uint64_t c4a0_host_pos_key(uint64_t mask, uint64_t value);
 /* idx[0..n) permuted like `results.shuffle(&mut StdRng::seed_from_u64(seed))` (pybridge.rs:110-113) */
 void c4a0_host_shuffle(uint64_t seed, uint32_t *idx, size_t n);
 
