@@ -184,7 +184,6 @@ struct Dev {  // passed to kernels by value
   Block* blocks;    // [n_slots][2][cap]
   uint32_t* row_slot;   // [row_cap] slot whose leaf is the row; 0xffffffff for a speculative row
   uint64_t* row_model;  // [row_cap] model that has to evaluate the row (mcts.rs:70-76)
-  uint32_t* bucket;  // [n_slots] hash-table entry of the slot's waiting leaf
   unsigned long long* rowtag;  // [2][n_slots] epoch << 32 | row, written by the slot that leads a key; the half is
                                // the epoch's parity: a leader may publish its next leaf while followers of its last
                                // one (warps that start later in the same tick) still look its row up
@@ -1359,7 +1358,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   }
   D.row_cap = cfg->n_slots + D.spec_cap;
   const size_t RC = D.row_cap;
-  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, RC); DA(D.row_model, RC); DA(D.bucket, S); DA(D.rowtag, 2 * S);
+  DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, RC); DA(D.row_model, RC); DA(D.rowtag, 2 * S);
   DA(D.blocks, S * 2 * (size_t)D.cap);
   DA(D.table, T);
   uint64_t *gid, *p0, *p1;
