@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--nn-dtype", choices=["bf16", "f32"], default="bf16")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-nn-device", choices=["auto", "cuda", "cpu"], default="auto",
+                    help="where the CPU reference evaluates its network: auto/cuda = through the numpy callback on "
+                         "cuda:0, the way the reference is deployed (SURVEY 8d placement i); cpu = host cores only (ii)")
     ap.add_argument("--sample-kernels-every", type=int, default=53)
     ap.add_argument("--lanes", type=int, default=1, help="engines per GPU (2 = tree ticks overlap the other half's network)")
     ap.add_argument("--no-dedup", action="store_true", help="evaluate duplicate leaf positions separately")
@@ -189,7 +192,7 @@ def cpu_baseline(args, budget_s: float) -> dict:
     reference's NN batch size).  Every move yields exactly one training position at game end
     (mcts.rs:198-203, 271-313) and every finished game one more, so positions/s of the sample =
     (moves + finished games) / seconds."""
-    nn_device = "cuda:0" if torch.cuda.is_available() else "cpu"
+    nn_device = "cuda:0" if torch.cuda.is_available() and getattr(args, "cpu_nn_device", "auto") != "cpu" else "cpu"
     probe = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=150_000)
     rate = probe["sims"] / probe["seconds"]
     budget = int(max(300_000, rate * budget_s))
