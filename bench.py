@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--no-speculate", action="store_true", help="do not top small batches up with children of expanded leaves")
     ap.add_argument("--spec-rows", type=int, default=0, help="rows a small batch is topped up to (0 = engine default)")
     ap.add_argument("--eval-cache-entries", type=int, default=0, help="entries of the evaluation cache (0 = engine default)")
+    ap.add_argument("--arena-mult", type=float, default=0.0,
+                    help="tree blocks per arena half per game as a multiple of the minimum (sims + 2); 0 = session default")
     ap.add_argument("--no-ablation", action="store_true", help="skip the extra step without the evaluation cache")
     ap.add_argument("--max-inline", type=int, default=0, help="terminal-leaf sims per game per tick (0 = engine default)")
     ap.add_argument("--no-fold", action="store_true", help="run the module form of the network instead of the GEMM-folded form")
@@ -270,6 +272,8 @@ def run_ours(args):
     selfplay.DEFAULTS["dedup"] = not args.no_dedup
     selfplay.DEFAULTS["max_inline_sims"] = args.max_inline
     selfplay.DEFAULTS["eval_cache"] = not args.no_eval_cache
+    if args.arena_mult > 0:
+        selfplay.DEFAULTS["arena_blocks"] = int(args.arena_mult * (args.sims + 2))
     selfplay.DEFAULTS["eval_cache_entries"] = args.eval_cache_entries
     selfplay.DEFAULTS["speculate"] = not args.no_speculate
     selfplay.DEFAULTS["spec_rows"] = args.spec_rows

@@ -290,12 +290,13 @@ class SelfPlaySession:
         if arena_blocks is None:
             arena_blocks = DEFAULTS["arena_blocks"]
         if arena_blocks is None:
-            # Roomy arena halves make re-rooting copy-free (see engine.cu): up to 16x the minimum
-            # (a whole average game), within a third of the free device memory.  2 halves x 160 B
-            # per block per game.
+            # Roomy arena halves make re-rooting copy-free (see engine.cu): up to 32x the minimum (a
+            # whole game of any length: no compaction at all; measured 1,441 -> 1,395 ms per bench
+            # step against 16x), within 60 % of the free device memory.  2 halves x 160 B per block
+            # per game.
             free_b, _ = torch.cuda.mem_get_info(self.device)
             minimum = n_mcts_iterations + 2
-            arena_blocks = max(minimum, min(16 * minimum, int(free_b / 3) // (n_slots * 320)))
+            arena_blocks = max(minimum, min(32 * minimum, int(free_b * 0.6) // (n_slots * 320)))
         per = [(n_slots + i) // n_lanes for i in range(n_lanes)][::-1]
         self.lanes = [
             _Lane(s, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, self.device,
