@@ -186,29 +186,59 @@ def cpu_reference_run(n_games: int, n_iter: int, width: int, nn_device: str, max
                 threads=threads + 1, nn_batches=int(nb.value))
 
 
+SPEC_ROOM = 8192  # rows of max_nn_batch_size above the resident games: used for speculative evaluations
 CPU_GAMES = 1000  # BASELINE.json configs[0]: the reference's own CPU-runnable case (1,000 games x 600 sims)
 
 
-def cpu_baseline(args, budget_s: float) -> dict:
+def _nn_device(args) -> str:
+    return "cuda:0" if torch.cuda.is_available() and getattr(args, "cpu_nn_device", "auto") != "cpu" else "cpu"
+
+
+def cpu_sample(args, budget_s: float, rate_hint: float = 0.0) -> dict:
     """Time-boxed sample of configs[0] at its full concurrency (1,000 games in flight, which sets the
-    reference's NN batch size).  Every move yields exactly one training position at game end
-    (mcts.rs:198-203, 271-313) and every finished game one more, so positions/s of the sample =
-    (moves + finished games) / seconds."""
-    nn_device = "cuda:0" if torch.cuda.is_available() and getattr(args, "cpu_nn_device", "auto") != "cpu" else "cpu"
-    probe = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=150_000)
-    rate = probe["sims"] / probe["seconds"]
-    budget = int(max(300_000, rate * budget_s))
-    run = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=budget)
-    positions = run["moves"] + run["finished"]
+    reference's NN batch size): the first `budget` simulations of the job.  Returns the raw run."""
+    nn_device = _nn_device(args)
+    if rate_hint <= 0.0:
+        probe = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=150_000)
+        rate_hint = probe["sims"] / probe["seconds"]
+    budget = int(max(300_000, rate_hint * budget_s))
+    return cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=budget)
+
+
+def cpu_whole_job(args) -> dict:
+    """configs[0] played to completion: every game from the empty board to its terminal position."""
+    run = cpu_reference_run(CPU_GAMES, args.sims, args.width, _nn_device(args), max_sims=0)
+    run["positions_per_s"] = run["positions"] / run["seconds"]
+    run["sims_per_s"] = run["sims"] / run["seconds"]
+    run["sims_per_position"] = run["sims"] / max(1, run["positions"])
+    return run
+
+
+def _cpu_sample_text(args, what: str) -> str:
+    return (f"{what} of {CPU_GAMES} concurrent games x {args.sims} sims/move (BASELINE configs[0]); threaded port of "
+            f"rust/src/self_play.rs on the host cores, fp32 network via the numpy callback on {_nn_device(args)}")
+
+
+def cpu_baseline(args, budget_s: float) -> dict:
+    """The `cpu_baseline` object of our own bench line: a time-boxed sample (the first simulations of
+    configs[0]).  Early moves cost more simulations per position than a whole game does (no subtree to
+    reuse yet), so positions/s is quoted as sims/s divided by the WHOLE-JOB simulations per position of
+    the GPU run of the same workload shape (passed in by the caller as args._sims_per_position) when
+    known; the raw early-game count is kept next to it."""
+    run = cpu_sample(args, budget_s)
+    sims_per_s = run["sims"] / run["seconds"]
+    early = (run["moves"] + run["finished"]) / run["seconds"]
+    spp = getattr(args, "_sims_per_position", None)
     return {
-        "value": positions / run["seconds"],
+        "value": sims_per_s / spp if spp else early,
         "unit": UNIT,
         "cores": run["threads"],
         "kind": "port",
-        "sample": f"first {run['sims']} simulations ({run['seconds']:.1f} s) of {CPU_GAMES} concurrent games x {args.sims} "
-                  f"sims/move (BASELINE configs[0]); threaded port of rust/src/self_play.rs on the host cores, fp32 "
-                  f"network via the numpy callback on {nn_device}; positions = moves made + games finished",
-        "sims_per_s": run["sims"] / run["seconds"],
+        "sample": _cpu_sample_text(args, f"first {run['sims']} simulations ({run['seconds']:.1f} s)")
+                  + ("; positions/s = sims/s / whole-job simulations per position of this workload "
+                     f"({spp:.1f}, from the GPU run: identical games)" if spp else "; positions = moves made + games finished"),
+        "sims_per_s": sims_per_s,
+        "early_game_positions_per_s": early,
         "seconds": run["seconds"],
         "host_cpus": os.cpu_count(),
         "mean_nn_batch": (run["sims"] / run["nn_batches"]) if run["nn_batches"] else None,
@@ -216,27 +246,59 @@ def cpu_baseline(args, budget_s: float) -> dict:
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU self-play architecture on the host cores.  Timed step 1 plays
+    configs[0] to completion (all 1,000 games, ~30 s), so positions/s covers whole games; the remaining
+    steps are time-boxed samples of the same job (its first simulations) whose sims/s is converted with the
+    complete job's simulations per position.  `value` = positions/s over the whole timed region."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = max(4.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    total_budget = 170.0
     for _ in range(args.warmup):
-        cpu_baseline(args, per_step / 4)
-    vals, last = [], None
+        cpu_sample(args, 1.0, rate_hint=300_000.0)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        last = cpu_baseline(args, per_step)
-        vals.append(last["value"])
+    full = cpu_whole_job(args)
+    rest = max(0, args.steps - 1)
+    per_step = max(2.0, min(20.0, (total_budget - full["seconds"]) / max(1, rest)))
+    sims, secs = full["sims"], full["seconds"]
+    rates = [full["sims_per_s"]]
+    for _ in range(rest):
+        r = cpu_sample(args, per_step, rate_hint=full["sims_per_s"])
+        sims += r["sims"]
+        secs += r["seconds"]
+        rates.append(r["sims"] / r["seconds"])
     dt = time.perf_counter() - t0
-    v = float(np.mean(vals))
-    last["value"] = v
+    sims_per_s = sims / secs
+    v = sims_per_s / full["sims_per_position"]
+    cfg = workload_config(args, 1)
+    cfg.update({
+        "workload": f"gen-0 self-play, {CPU_GAMES} concurrent games x {args.sims} MCTS sims/move (BASELINE configs[0], the "
+                    f"reference's CPU-runnable case), 7x6 board, random-init c4a0 ResNet (1 block x {args.width} filters, "
+                    f"4 policy / 2 value layers), c_exploration={C_EXPLORATION}, c_ply_penalty={C_PLY_PENALTY}",
+        "games_per_gpu": CPU_GAMES, "global_games": CPU_GAMES, "games": CPU_GAMES,
+        "time_boxed": f"step 1 of {args.steps} plays all {CPU_GAMES} games to completion; the others are the first "
+                      f"~{per_step:.0f} s of the same job",
+        "parallelism": f"{full['threads']} host threads (1 NN thread + workers), network on {_nn_device(args)}",
+        "l2": "n/a (CPU arm)",
+    })
+    base = {
+        "value": v, "unit": UNIT, "cores": full["threads"], "kind": "port",
+        "sample": _cpu_sample_text(args, f"one complete job ({full['sims']} simulations, {full['positions']} positions, "
+                                         f"{full['seconds']:.1f} s) + {rest} time-boxed samples"),
+        "sims_per_s": sims_per_s, "host_cpus": os.cpu_count(),
+        "whole_job": {"games": CPU_GAMES, "finished": full["finished"], "positions": full["positions"], "sims": full["sims"],
+                      "seconds": full["seconds"], "positions_per_s": full["positions_per_s"], "sims_per_s": full["sims_per_s"],
+                      "sims_per_position": full["sims_per_position"]},
+        "step_sims_per_s": rates,
+        "mean_nn_batch": (full["sims"] / full["nn_batches"]) if full["nn_batches"] else None,
+    }
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1), "cpu_baseline": last,
+        "config": cfg, "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "sims_per_s": last["sims_per_s"],
+        "sims_per_s": sims_per_s,
     }
     print(json.dumps(line), flush=True)
 
@@ -247,8 +309,11 @@ def workload_config(args, world):
                     f"random-init c4a0 ResNet (1 block x {args.width} filters, 4 policy / 2 value layers), "
                     f"c_exploration={C_EXPLORATION}, c_ply_penalty={C_PLY_PENALTY}",
         "games_per_gpu": args.games, "sims_per_move": args.sims, "global_games": args.games * world,
+        "max_nn_batch_size": args.games + SPEC_ROOM,
         "parallelism": f"games sharded over {world} GPU(s), no search-path collective",
-        "l2": "inputs larger than L2: live tree arenas ~1.5 GB per GPU vs 126 MB L2",
+        "l2": "inputs larger than L2: the games' live trees (arenas of tens of GB per GPU, ~1.5 GB of them touched "
+              "between two visits of a game) and the evaluation cache (8.6 GB) against 126 MB of L2; every step starts "
+              "with an empty evaluation cache",
     }
 
 
@@ -295,7 +360,9 @@ def run_ours(args):
         evaluator = DeviceEvaluator.from_model(model, dtype, fold=(False if args.no_fold else ("plain" if args.plain_fold else True)), reuse=state["ev"])
         state["ev"] = evaluator
         reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
-        res = c4a0_rust.play_games(reqs, G, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
+        # max_nn_batch_size: the resident games plus room for the speculative rows (play_games keeps
+        # n_slots + spec_rows within the caller's bound)
+        res = c4a0_rust.play_games(reqs, G + SPEC_ROOM, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
         n_pos = int(res._soa.n_samples.sum())
         checksum = float(res._soa.q_no_penalty.sum())  # touch the host result
         if world > 1:  # the trainer lives on rank 0: gather every rank's samples there (NCCL)
@@ -422,8 +489,27 @@ def run_ours(args):
         finally:
             selfplay.DEFAULTS["eval_cache"] = True
             c4a0_rust._native.close_cached_session()
+    if world == 1 and args.nn_dtype == "bf16" and not args.no_ablation:
+        # the same job with the network evaluated in f32 (the reference arm's precision)
+        try:
+            c4a0_rust._native.close_cached_session()
+            state["ev"], dtype = None, torch.float32
+            one_step()
+            torch.cuda.synchronize()
+            dt, info, n_pos, _ = one_step()
+            line["f32_network"] = {
+                "value": n_pos / info.device_s, "unit": UNIT, "ms_per_step": 1e3 * info.device_s, "steps": 1,
+                "e2e_value": n_pos / dt, "ticks_per_step": info.ticks, "sims_per_s": info.stats["sims"] / info.device_s,
+            }
+        except Exception as exc:
+            line["f32_network"] = {"value": None, "error": str(exc)}
+        finally:
+            dtype = torch.bfloat16
+            state["ev"] = None
+            c4a0_rust._native.close_cached_session()
     if world == 1 and not args.no_cpu_baseline:
         try:
+            args._sims_per_position = sims / max(1, positions)
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_seconds)
         except Exception as exc:  # the number is a report, never a reason to lose the bench line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}

@@ -113,6 +113,23 @@ class DeviceEvaluator:
         qn.copy_(b.reshape(rows))
 
 
+class BuiltinEvaluator:
+    """The engine's synthetic evaluators (k_eval_builtin: uniform E0, integer-hash E1, flat hash) as a device
+    evaluator, so that parity jobs run through the same native host loop, CUDA graphs, evaluation cache and
+    speculation as a real network.  A pure function of (model, position); float32 planes (unused)."""
+
+    KINDS = {"uniform": L.EVAL_UNIFORM, "hash": L.EVAL_HASH, "hash_flat": L.EVAL_HASH_FLAT}
+
+    def __init__(self, kind: str = "hash"):
+        self.kind = self.KINDS[kind]
+        self.dtype = torch.float32
+        self.plane_stride = 84
+        self.plane_offset = 0
+
+    def __call__(self, planes):  # only reachable through _Lane.evaluate, which launches the kernel itself
+        raise TypeError("BuiltinEvaluator is evaluated by the engine (c4a0_engine_eval_builtin)")
+
+
 class MultiModelEvaluator:
     """Several networks in one batch (tournaments: `GameMetadata.player0_id != player1_id`,
     src/c4a0/tournament.py:112-142).  The reference's NN thread serves one model per callback
@@ -210,6 +227,10 @@ class _Lane:
 
     def evaluate(self, evaluator, rows: int) -> None:
         with torch.no_grad():
+            if isinstance(evaluator, BuiltinEvaluator):
+                # covers every live row whatever `rows` is (the kernel reads the tick's row count)
+                self.engine.eval_builtin(evaluator.kind, torch.cuda.current_stream(self.planes.device).cuda_stream)
+                return
             if isinstance(evaluator, MultiModelEvaluator):
                 pol, a, b = evaluator(self.planes[:rows], self.row_model[:rows])
             elif isinstance(evaluator, DeviceEvaluator):
@@ -226,6 +247,8 @@ class _Lane:
             self.graphs, self.graph_key = {}, evaluator
             self.pool = torch.cuda.graph_pool_handle()
             sizes = [b for b in BUCKETS if b < self.io_rows] + [self.io_rows]
+            if isinstance(evaluator, BuiltinEvaluator):
+                sizes = [self.io_rows]  # one kernel whatever the batch: one graph
             with torch.cuda.stream(self.stream):
                 for rows in reversed(sizes):  # largest first: the shared pool is sized once
                     self.evaluate(evaluator, rows)  # eager warm-up (cuBLAS handles, heuristics)
@@ -290,13 +313,14 @@ class SelfPlaySession:
         if arena_blocks is None:
             arena_blocks = DEFAULTS["arena_blocks"]
         if arena_blocks is None:
-            # Roomy arena halves make re-rooting copy-free (see engine.cu): up to 32x the minimum (a
-            # whole game of any length: no compaction at all; measured 1,441 -> 1,395 ms per bench
-            # step against 16x), within 60 % of the free device memory.  2 halves x 160 B per block
-            # per game.
+            # Roomy arena halves make re-rooting copy-free (see engine.cu).  Default 8x the minimum: 34 GB
+            # for 16,384 games x 600 sims, which leaves the GPU to a trainer as well; a half then fills up
+            # a few thousand times per job and its compaction costs ~3 % of a bench step (32x = 110 GB has
+            # none: 1,410 vs 1,455 ms, profiles/r01_summary.md).  Never more than 35 % of the free memory.
+            # 2 halves x 160 B per block per game.
             free_b, _ = torch.cuda.mem_get_info(self.device)
             minimum = n_mcts_iterations + 2
-            arena_blocks = max(minimum, min(32 * minimum, int(free_b * 0.6) // (n_slots * 320)))
+            arena_blocks = max(minimum, min(8 * minimum, int(free_b * 0.35) // (n_slots * 320)))
         per = [(n_slots + i) // n_lanes for i in range(n_lanes)][::-1]
         self.lanes = [
             _Lane(s, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, self.device,

@@ -253,6 +253,7 @@ class PlayGamesResult:
     def __setstate__(self, state: bytes) -> None:
         other = PlayGamesResult.from_cbor(state)
         self._meta, self._soa, self._results = other._meta, other._soa, other._results
+        self._run_info = None  # pickle bypasses __init__
 
     def __add__(self, other: "PlayGamesResult") -> "PlayGamesResult":
         if not isinstance(other, PlayGamesResult):
@@ -306,21 +307,22 @@ for _cls in (GameMetadata, Sample, GameResult, PlayGamesResult):
 _SESSION = {"key": None, "sess": None}
 
 
-def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes, offset=0, eval_cache=False):
+def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lanes, offset=0, eval_cache=False,
+             spec_rows=0):
     """One engine (tree arenas, NN I/O tensors, captured graphs) is kept between calls with the same
     configuration — a training loop calls play_games once per generation with identical settings."""
     from c4a0_b200 import selfplay
     from c4a0_b200.selfplay import SelfPlaySession
 
     knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks", "eval_cache_entries", "speculate", "spec_rows")))
-    key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, offset, n_lanes, knobs, eval_cache)
+    key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, offset, n_lanes, knobs, eval_cache, spec_rows)
     if _SESSION["key"] == key and _SESSION["sess"] is not None and _SESSION["cap"] >= n_req:
         return _SESSION["sess"]
     close_cached_session()
     sess = SelfPlaySession(n_slots, n_req, n_iter, c_expl, c_pen, plane_dtype=dtype, device=device,
                            plane_stride=stride, plane_offset=offset, n_lanes=n_lanes, eval_cache=eval_cache,
                            eval_cache_entries=selfplay.DEFAULTS["eval_cache_entries"],
-                           speculate=bool(eval_cache and selfplay.DEFAULTS["speculate"]), spec_rows=selfplay.DEFAULTS["spec_rows"])
+                           speculate=bool(eval_cache and spec_rows > 0), spec_rows=spec_rows)
     _SESSION.update(key=key, sess=sess, cap=n_req)
     return sess
 
@@ -351,7 +353,7 @@ def play_games(
     import torch
 
     from c4a0_b200 import selfplay
-    from c4a0_b200.selfplay import DeviceEvaluator, MultiModelEvaluator
+    from c4a0_b200.selfplay import BuiltinEvaluator, DeviceEvaluator, MultiModelEvaluator
 
     reqs = list(reqs)
     for r in reqs:
@@ -365,7 +367,7 @@ def play_games(
         return PlayGamesResult()
     meta = np.array([(r.game_id, r.player0_id, r.player1_id) for r in reqs], dtype=np.uint64)
     n_slots = min(len(reqs), int(max_nn_batch_size))
-    fast = isinstance(py_eval_pos_cb, (DeviceEvaluator, MultiModelEvaluator, torch.nn.Module))
+    fast = isinstance(py_eval_pos_cb, (DeviceEvaluator, MultiModelEvaluator, BuiltinEvaluator, torch.nn.Module))
     if fast:
         if isinstance(py_eval_pos_cb, torch.nn.Module):
             p = next(py_eval_pos_cb.parameters(), None)
@@ -375,13 +377,22 @@ def play_games(
             missing = ids - set(py_eval_pos_cb.evaluators)
             if missing:
                 raise ValueError(f"no evaluator for model ids {sorted(missing)}")
-        elif len(ids) != 1:
+        elif len(ids) != 1 and not isinstance(py_eval_pos_cb, BuiltinEvaluator):
             raise ValueError("one device evaluator plays one model against itself; pass a MultiModelEvaluator "
                              "{model_id: evaluator} (or the numpy callback) for tournaments")
+        # max_nn_batch_size bounds every network batch (pybridge.rs:20-53, self_play.rs:216-220).  The
+        # speculative rows (children of expanded leaves evaluated in the spare rows of a small batch) only
+        # use what the caller's bound leaves above the resident games: n_slots + spec_rows <= max_nn_batch_size.
+        use_cache = bool(selfplay.DEFAULTS["eval_cache"])
+        spec_rows = 0
+        if use_cache and selfplay.DEFAULTS["speculate"]:
+            spec_rows = min(selfplay.DEFAULTS["spec_rows"] or 8192, n_slots, int(max_nn_batch_size) - n_slots)
+            if spec_rows < 32:
+                spec_rows = 0
         sess = _session(
             n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),
             py_eval_pos_cb.dtype, torch.cuda.current_device(), py_eval_pos_cb.plane_stride, None,
-            getattr(py_eval_pos_cb, "plane_offset", 0), bool(selfplay.DEFAULTS["eval_cache"]),
+            getattr(py_eval_pos_cb, "plane_offset", 0), use_cache, spec_rows,
         )
         try:
             soa, info = sess.play(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb)

@@ -156,7 +156,7 @@ def lib() -> C.CDLL:
     L.c4o_self_play_threaded_budget.restype = C.c_int
     L.c4o_player0_score.argtypes = [C.POINTER(Sample), C.c_int]
     L.c4o_player0_score.restype = C.c_float
-    for ev in (L.c4o_eval_uniform, L.c4o_eval_hash):
+    for ev in (L.c4o_eval_uniform, L.c4o_eval_hash, L.c4o_eval_hash_flat):
         ev.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Pos), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         ev.restype = None
     L.c4o_logf_array.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -321,7 +321,7 @@ class Game:
 
 def builtin_eval(name: str, pos: Pos, model_id: int = 0):
     """One position through the 'uniform' (E0) or 'hash' (E1) synthetic evaluator."""
-    fn = lib().c4o_eval_uniform if name == "uniform" else lib().c4o_eval_hash
+    fn = {"uniform": lib().c4o_eval_uniform, "hash": lib().c4o_eval_hash, "hash_flat": lib().c4o_eval_hash_flat}[name]
     pol = (C.c_float * 7)()
     qp, qn = C.c_float(), C.c_float()
     fn(None, model_id, 1, C.byref(pos), pol, C.byref(qp), C.byref(qn))
@@ -373,6 +373,8 @@ def _wrap_eval(evaluator) -> Tuple[object, object]:
         return C.cast(L.c4o_eval_uniform, C.c_void_p), None
     if evaluator == "hash":
         return C.cast(L.c4o_eval_hash, C.c_void_p), None
+    if evaluator == "hash_flat":
+        return C.cast(L.c4o_eval_hash_flat, C.c_void_p), None
 
     def cb(_user, model_id, n, pos, policy, qp, qn):
         keys = [(int(pos[i].mask), int(pos[i].value)) for i in range(n)]
@@ -418,6 +420,27 @@ def self_play(
         raise RuntimeError(f"oracle self-play failed rc={rc}")
     samples = [[out[i * MAX_SAMPLES + k] for k in range(out_n[i])] for i in range(n)]
     return SelfPlayOutput(samples=samples, stats=st.as_dict(), nn_batches=int(nb.value))
+
+
+def self_play_parallel(reqs, n_mcts_iterations, c_exploration, c_ply_penalty, evaluator="hash", chunk=16, workers=0):
+    """Records (SelfPlayOutput.records() form) of many independent games, played by the serial state machine
+    on a pool of host threads (ctypes releases the GIL; the built-in evaluators never call back into
+    Python).  Per-game results do not depend on scheduling, so chunks can run anywhere."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    assert evaluator in ("uniform", "hash", "hash_flat")
+    reqs = list(reqs)
+    parts = [reqs[i : i + chunk] for i in range(0, len(reqs), chunk)]
+    workers = workers or max(1, (os.cpu_count() or 2))
+
+    def run(part):
+        return self_play(part, len(part), n_mcts_iterations, c_exploration, c_ply_penalty, evaluator=evaluator).records()
+
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        out = []
+        for r in ex.map(run, parts):
+            out.extend(r)
+    return out
 
 
 def player0_score(samples: Sequence[Sample]) -> float:

@@ -777,6 +777,25 @@ void c4o_eval_hash(void *user, uint64_t model_id, int n, const c4o_pos *pos, flo
   }
 }
 
+/* The same pseudo network with nearly flat outputs (logits / 16, q scaled by 0.1 instead of 0.75): the
+ * shape of a random-init network, so games run as long as gen-0 self-play (~9.5 k simulations per game
+ * at 600 per move).  Matches k_eval_builtin(C4A0_EVAL_HASH_FLAT) bit for bit (one f32 multiply each). */
+void c4o_eval_hash_flat(void *user, uint64_t model_id, int n, const c4o_pos *pos, float *policy,
+                        float *qp, float *qn) {
+  (void)user;
+  for (int i = 0; i < n; i++) {
+    uint64_t h = splitmix64(pos[i].mask * 0x9E3779B97F4A7C15ULL ^ splitmix64(pos[i].value ^ model_id));
+    for (int k = 0; k < 7; k++) {
+      uint64_t hk = splitmix64(h + (uint64_t)k);
+      float lg = (float)(uint32_t)(hk >> 48) * (1.0f / 8192.0f) - 4.0f;
+      policy[i * 7 + k] = lg * 0.0625f;
+    }
+    uint64_t hq = splitmix64(h + 7);
+    qp[i] = ((float)(uint32_t)((hq >> 48) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * 0.1f;
+    qn[i] = ((float)(uint32_t)((hq >> 32) & 0xffff) * (1.0f / 32768.0f) - 1.0f) * 0.1f;
+  }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Self-play state machine — rust/src/self_play.rs:268-323 (MctsThread::loop_once) applied to all
  * games in lockstep rounds on one thread.  F8: per-game records do not depend on how

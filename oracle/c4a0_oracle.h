@@ -111,6 +111,9 @@ void c4o_eval_uniform(void *user, uint64_t model_id, int n, const c4o_pos *pos, 
 void c4o_eval_hash(void *user, uint64_t model_id, int n, const c4o_pos *pos, float *policy,
                    float *qp, float *qn);
 
+void c4o_eval_hash_flat(void *user, uint64_t model_id, int n, const c4o_pos *pos, float *policy,
+                        float *qp, float *qn);
+
 /* ---- per-game state machine of MctsThread::loop_once (self_play.rs:268-323), run
  * game after game on one thread; per-game records do not depend on scheduling. ---- */
 typedef struct {

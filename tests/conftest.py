@@ -25,3 +25,8 @@ def _seed():
         torch.manual_seed(1337)
     except Exception:
         pass
+
+
+# tests/golden/ holds fixtures (and the reference's own pybridge_test.py, byte for byte); they are run by
+# the tests that name them, not collected on their own
+collect_ignore_glob = ["golden/*"]
