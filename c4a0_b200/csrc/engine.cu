@@ -1164,7 +1164,10 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(Dev D) {
 // ------------------------------------------------------------------------------------------------
 __global__ void k_eval_builtin(Dev D, int kind, float* logits, float* qp, float* qn) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= D.g->n_rows) return;
+  // rows of the batch: n_rows once the tick is closed; while a burst of compactions keeps it open for
+  // k_tail (the native loop has already enqueued the network behind k_step) the row counter itself
+  const uint32_t closed = D.g->n_rows, open = *reinterpret_cast<volatile uint32_t*>(&D.g->rows_acc);
+  if (row >= (closed > open ? closed : open)) return;
   if (kind == C4A0_EVAL_UNIFORM) {
     for (int k = 0; k < 7; k++) logits[(size_t)row * 7 + k] = 0.0f;
     qp[row] = 0.0f;
