@@ -119,6 +119,39 @@ class RunReport(C.Structure):
         return d
 
 
+NET_MAX_LAYERS, NET_MAX_BUFFERS = 12, 8
+NET_TILE_M, NET_TILE_N, NET_TILE_K, NET_HEAD_N = 128, 192, 64, 16
+NET_HIDDEN, NET_POLICY, NET_VALUE = 0, 1, 2
+
+
+class NetLayer(C.Structure):  # include/c4a0_net.h: c4a0_net_layer
+    _fields_ = [
+        ("weight_dev", C.c_void_p),
+        ("bias_dev", C.c_void_p),
+        ("n_pad", C.c_uint32),
+        ("k_pad", C.c_uint32),
+        ("in_buffer", C.c_uint32),
+        ("in_col0", C.c_uint32),
+        ("out_buffer", C.c_uint32),
+        ("out_col0", C.c_uint32),
+        ("dep", C.c_int32),
+        ("kind", C.c_uint32),
+    ]
+
+
+class NetSpec(C.Structure):  # c4a0_net_spec
+    _fields_ = [
+        ("device", C.c_int32),
+        ("max_rows", C.c_uint32),
+        ("n_buffers", C.c_uint32),
+        ("buffer_cols", C.c_uint32 * NET_MAX_BUFFERS),
+        ("planes_buffer", C.c_uint32),
+        ("planes_col0", C.c_uint32),
+        ("n_layers", C.c_uint32),
+        ("layers", NetLayer * NET_MAX_LAYERS),
+    ]
+
+
 class EngineError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"c4a0 engine error {code}: {msg}")
@@ -164,6 +197,15 @@ SIGNATURES = {
     "c4a0_host_pos_key": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "c4a0_host_flip_h": (None, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "c4a0_host_shuffle": (None, [C.c_uint64, _P, C.c_size_t]),
+    # include/c4a0_net.h
+    "c4a0_net_create": (C.c_int, [C.POINTER(NetSpec), C.POINTER(_P)]),
+    "c4a0_net_destroy": (None, [_P]),
+    "c4a0_net_device_bytes": (C.c_size_t, [_P]),
+    "c4a0_net_buffer": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "c4a0_net_bind_outputs": (C.c_int, [_P, _P, _P, _P]),
+    "c4a0_net_bind_row_count": (C.c_int, [_P, _P, _P]),
+    "c4a0_net_forward": (C.c_int, [_P, C.c_uint32, _P]),
+    "c4a0_net_forward_timed": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_float)]),
 }
 
 _lib = None

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libc4a0_engine.so")
 
-SOURCES = ["engine.cu", "batch_ops.cu"]
+SOURCES = ["engine.cu", "batch_ops.cu", "net.cu"]
 HEADERS = ["c4_rules.cuh", "c4_math.cuh", "c4_rng.cuh", "common.cuh"]
 
 NVCC_FLAGS = [
@@ -38,7 +38,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "c4a0_engine.h")]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", h) for h in ("c4a0_engine.h", "c4a0_net.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
