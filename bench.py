@@ -73,6 +73,9 @@ def parse_args():
     ap.add_argument("--host-loop", choices=["native", "python"], default="native",
                     help="python = eager network + per-tick polling (what ncu can follow; slower)")
     ap.add_argument("--plain-fold", action="store_true", help="GEMM-folded form without the epilogue-fused layout (FoldedNet)")
+    ap.add_argument("--nn", choices=["native", "cublas"], default="native",
+                    help="bf16 network: native = the library's tcgen05 kernel (csrc/net.cu), cublas = the same folded "
+                         "network as PyTorch/cuBLASLt GEMMs in bucketed CUDA graphs")
     return ap.parse_args()
 
 
@@ -357,7 +360,7 @@ def run_ours(args):
         D.broadcast_model(model)  # a generation's weights: rank 0 -> all (NCCL); no-op at N=1
         # weights -> inference form, loaded in place into the previous generation's evaluator so the
         # captured CUDA graphs and the engine of the previous call are reused
-        evaluator = DeviceEvaluator.from_model(model, dtype, fold=(False if args.no_fold else ("plain" if args.plain_fold else True)), reuse=state["ev"])
+        evaluator = DeviceEvaluator.from_model(model, dtype, fold=(False if args.no_fold else ("plain" if args.plain_fold else (True if args.nn == "native" else "cublas"))), reuse=state["ev"])
         state["ev"] = evaluator
         reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
         # max_nn_batch_size: the resident games plus room for the speculative rows (play_games keeps
@@ -433,6 +436,10 @@ def run_ours(args):
             except Exception:
                 pass
     flops = model.flops_per_position()
+    native = type(state["ev"]).__name__ == "NativeEvaluator"
+    nn_form = ("module" if args.no_fold else "GEMM-folded (FoldedNet)" if args.plain_fold else
+               "one persistent tcgen05/TMEM/TMA kernel over the GEMM-folded network (k_net2, csrc/net.cu)" if native else
+               "GEMM-folded, epilogue-fused (FusedNet), cuBLASLt")
     line = {
         "metric": METRIC, "value": positions_all / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / max(1, args.steps), "higher_is_better": True,
@@ -458,7 +465,7 @@ def run_ours(args):
                        "hit_rate_of_expansions": cache_hits / max(1, expansions),
                        "speculate": not (args.no_eval_cache or args.no_speculate), "speculative_rows": spec_rows},
         "compactions_per_step": compactions / max(1, args.steps), "engine_device_gb": engine_gb,
-        "lanes": args.lanes, "nn_form": "module" if args.no_fold else ("GEMM-folded (FoldedNet)" if args.plain_fold else "GEMM-folded, epilogue-fused (FusedNet)"),
+        "lanes": args.lanes, "nn_form": nn_form,
         "roofline": roofline,
         "nn_roofline": {
             "bound": "tensor", "unit": "TFLOP/s", "flops_per_eval": flops,

@@ -120,7 +120,7 @@ class RunReport(C.Structure):
 
 
 NET_MAX_LAYERS, NET_MAX_BUFFERS = 12, 8
-NET_TILE_M, NET_TILE_N, NET_TILE_K, NET_HEAD_N = 128, 192, 64, 16
+NET_TILE_M, NET_TILE_N, NET_TILE_K, NET_HEAD_N, NET_PAD_N = 128, 192, 64, 16, 1344
 NET_HIDDEN, NET_POLICY, NET_VALUE = 0, 1, 2
 
 
@@ -177,6 +177,7 @@ SIGNATURES = {
     "c4a0_engine_stats": (C.c_int, [_P, C.POINTER(Stats), _P]),
     "c4a0_engine_fetch_rows": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "c4a0_engine_rows_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "c4a0_engine_rows_count_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "c4a0_engine_run": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(RunReport)]),
     "c4a0_engine_fetch_results": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "c4a0_engine_export_samples": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_int, _P, _P, _P, _P, _P]),
@@ -205,6 +206,7 @@ SIGNATURES = {
     "c4a0_net_bind_outputs": (C.c_int, [_P, _P, _P, _P]),
     "c4a0_net_bind_row_count": (C.c_int, [_P, _P, _P]),
     "c4a0_net_forward": (C.c_int, [_P, C.c_uint32, _P]),
+    "c4a0_net_debug_trace": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, C.c_size_t]),
     "c4a0_net_forward_timed": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_float)]),
 }
 

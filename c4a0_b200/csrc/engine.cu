@@ -1651,6 +1651,13 @@ int c4a0_engine_rows_dev(c4a0_engine* e, uint32_t** row_slot_dev, uint64_t** row
   return 0;
 }
 
+int c4a0_engine_rows_count_dev(c4a0_engine* e, const uint32_t** closed_dev, const uint32_t** open_dev) {
+  if (!e) return fail(C4A0_E_INVALID, "null engine");
+  if (closed_dev) *closed_dev = &e->D.g->n_rows;
+  if (open_dev) *open_dev = &e->D.g->rows_acc;
+  return 0;
+}
+
 int c4a0_engine_slot_info(c4a0_engine* e, uint32_t slot, c4a0_slot_info* out, void* stream) {
   if (!e || !out) return fail(C4A0_E_INVALID, "null argument");
   if (slot >= e->D.n_slots) return fail(C4A0_E_INVALID, "slot out of range");

@@ -168,6 +168,12 @@ class Engine:
         L.check(self._lib.c4a0_engine_rows_dev(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def rows_count_dev(self) -> Tuple[int, int]:
+        """Device addresses (closed, open) of the batch's row count; see c4a0_engine_rows_count_dev."""
+        a, b = C.c_void_p(), C.c_void_p()
+        L.check(self._lib.c4a0_engine_rows_count_dev(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def slot_info(self, slot: int, stream: int = 0) -> L.SlotInfo:
         info = L.SlotInfo()
         L.check(self._lib.c4a0_engine_slot_info(self._h, slot, C.byref(info), stream))

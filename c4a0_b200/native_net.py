@@ -10,7 +10,7 @@ src/c4a0/nn.py:59-117 in eval mode) into the dense-layer program the kernel runs
     output layers (16 wide)                  log_softmax(7) -> logits, tanh(2) -> q_penalty, q_no_penalty
 
 (the algebra is FusedNet's, c4a0_b200/nn.py).  Fp is F = 42 * conv_filter_size rounded up to a multiple
-of 192 (the kernel's column tile); padding columns carry zero weights and zero biases.  Weights live in
+of 1344 (a common multiple of the kernel's column tiles); padding columns carry zero weights and zero biases.  Weights live in
 torch tensors owned by this object; `refresh(model)` overwrites them in place for a new generation.
 Torch is used for the folding arithmetic (float64, once per generation) and for device memory only.
 """
@@ -39,7 +39,7 @@ def fold_program(model: ConnectFourNet):
     t, (n_blocks, joint_first, n_p, n_v) = FoldedNet._fold(model)
     assert n_blocks == 1 and joint_first
     F = model.fc_size
-    Fp = _round_up(F, L.NET_TILE_N)
+    Fp = _round_up(F, L.NET_PAD_N)
     dev = t["w0"].device
     z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)  # noqa: E731
     w0, b0, wh, bh = t["w0"], t["b0"], t["wh0"], t["bh0"]  # [96,2F] (pre|inp), [F,2F] (policy|value)
@@ -153,7 +153,7 @@ class NativeEvaluator:
         if self.device.type != "cuda":
             raise RuntimeError("NativeEvaluator needs a CUDA device: there is no CPU fallback")
         self.F = model.fc_size
-        self.Fp = _round_up(self.F, L.NET_TILE_N)
+        self.Fp = _round_up(self.F, L.NET_PAD_N)
         self.plane_stride = self.Fp + XP
         self.plane_offset = self.Fp
         self._layers: List[dict] = []
@@ -278,6 +278,15 @@ class NativeNet:
         ms = C.c_float()
         L.check(self._lib.c4a0_net_forward_timed(self._h, rows, s, C.byref(ms)))
         return ms.value
+
+    def debug_trace(self, rows: int, cta: int = 0):
+        """Per-role event log of one CTA: three lists of (tag, SM cycle) (see c4a0_net_debug_trace)."""
+        import numpy as np
+
+        out = np.zeros((3, 4096), np.uint64)
+        s = torch.cuda.current_stream(self.ev.device).cuda_stream
+        L.check(self._lib.c4a0_net_debug_trace(self._h, rows, cta, s, L.ptr(out), out.size))
+        return [[(int(v) & 0xFF, int(v) >> 8) for v in role if v] for role in out]
 
     def __call__(self, planes: torch.Tensor):
         """planes [B,2,6,7] or [B,84] (any float dtype) -> (logits [B,7], q_penalty [B], q_no_penalty [B]) f32.

@@ -23,6 +23,7 @@ Two evaluator contracts are supported:
 
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Sequence, Tuple
@@ -77,10 +78,22 @@ class DeviceEvaluator:
         """ConnectFourNet -> evaluator.  fold=True uses the GEMM-folded inference form (nn.FoldedNet).
         Pass the previous generation's evaluator as `reuse` to load the new weights into it in place:
         the CUDA graphs captured over it (and the cached session) stay valid."""
+        from .native_net import NativeEvaluator
         from .nn import ConnectFourNet, FoldedNet, FusedNet
 
+        if (fold is True and dtype == torch.bfloat16 and NativeEvaluator.supports(model)
+                and os.environ.get("C4A0_NATIVE_NET", "1") != "0"):
+            # the library's own tcgen05 kernel (csrc/net.cu) evaluates the folded network in one launch
+            if isinstance(reuse, NativeEvaluator):
+                try:
+                    return reuse.refresh(model)
+                except ValueError:
+                    pass
+            return NativeEvaluator(model)
+        if fold == "cublas":  # the same folded network through PyTorch / cuBLASLt (comparison, multi-model)
+            fold = True
         if fold and isinstance(model, ConnectFourNet):
-            if reuse is not None and isinstance(reuse.fn, FoldedNet) and reuse.dtype == dtype:
+            if isinstance(reuse, DeviceEvaluator) and isinstance(reuse.fn, FoldedNet) and reuse.dtype == dtype:
                 try:
                     reuse.fn.refresh(model)
                     return reuse
@@ -144,6 +157,9 @@ class MultiModelEvaluator:
         first = next(iter(self.evaluators.values()))
         self.dtype, self.plane_stride, self.plane_offset = first.dtype, first.plane_stride, getattr(first, "plane_offset", 0)
         for ev in self.evaluators.values():
+            if not isinstance(ev, DeviceEvaluator):
+                raise TypeError("a MultiModelEvaluator combines DeviceEvaluators (PyTorch networks); build them with "
+                                "DeviceEvaluator.from_model(model, dtype, fold='cublas')")
             if (ev.dtype, ev.plane_stride, getattr(ev, "plane_offset", 0)) != (self.dtype, self.plane_stride, self.plane_offset):
                 raise ValueError("all evaluators of a MultiModelEvaluator must share dtype and plane layout")
 
@@ -224,9 +240,28 @@ class _Lane:
         self.graphs = {}  # rows -> torch.cuda.CUDAGraph
         self.graph_key = None
         self.pool = None
+        self.net = None  # native_net.NativeNet when the evaluator is the library's own kernel
+
+    def attach_native(self, evaluator) -> None:
+        """Give this lane a c4a0_net over `evaluator`'s weights: the engine writes its planes straight into
+        the net's input buffer, the net writes the engine's logits / q buffers and reads the batch's row
+        count on the device."""
+        if self.net is not None and self.net.ev is evaluator:
+            return
+        if self.net is not None:
+            self.net.close()
+        self.net = evaluator.instantiate(self.io_rows)
+        self.net.bind_outputs(self.logits, self.qp, self.qn)
+        self.net.bind_row_count(*self.engine.rows_count_dev())
+        self.engine.bind_io(self.net.planes_ptr(), self.logits.data_ptr(), self.qp.data_ptr(), self.qn.data_ptr())
+        self.planes = self.net.buffer(0)
+        self.graphs, self.graph_key = {}, None
 
     def evaluate(self, evaluator, rows: int) -> None:
         with torch.no_grad():
+            if self.net is not None and self.net.ev is evaluator:
+                self.net.forward(rows, torch.cuda.current_stream(self.logits.device).cuda_stream)  # rows: read on the device
+                return
             if isinstance(evaluator, BuiltinEvaluator):
                 # covers every live row whatever `rows` is (the kernel reads the tick's row count)
                 self.engine.eval_builtin(evaluator.kind, torch.cuda.current_stream(self.planes.device).cuda_stream)
@@ -247,7 +282,7 @@ class _Lane:
             self.graphs, self.graph_key = {}, evaluator
             self.pool = torch.cuda.graph_pool_handle()
             sizes = [b for b in BUCKETS if b < self.io_rows] + [self.io_rows]
-            if isinstance(evaluator, BuiltinEvaluator):
+            if isinstance(evaluator, BuiltinEvaluator) or (self.net is not None and self.net.ev is evaluator):
                 sizes = [self.io_rows]  # one kernel whatever the batch: one graph
             with torch.cuda.stream(self.stream):
                 for rows in reversed(sizes):  # largest first: the shared pool is sized once
@@ -262,6 +297,9 @@ class _Lane:
     def close(self):
         self.graphs = {}
         self.engine.close()
+        if self.net is not None:
+            self.net.close()
+            self.net = None
 
 
 class SelfPlaySession:
@@ -398,6 +436,11 @@ class SelfPlaySession:
         t0 = time.perf_counter()
         ranges = self._split(n_req)
         self._last_ranges = ranges
+        from .native_net import NativeEvaluator
+
+        if isinstance(evaluator, NativeEvaluator):
+            for ln in self.lanes:
+                ln.attach_native(evaluator)  # before set_requests(): it packs the planes of the initial roots
         for ln, (lo, hi) in zip(self.lanes, ranges):
             ln.engine.set_requests(gid[lo:hi], p0[lo:hi], p1[lo:hi], ln.stream.cuda_stream)
         if host_loop == "native":

@@ -327,6 +327,33 @@ def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lan
     return sess
 
 
+_MODULE_EVALUATORS = {}  # id(module) -> (weakref to the module, its evaluator)
+
+
+def _module_evaluator(module):
+    """An nn.Module handed to play_games: evaluate it in its own precision (bf16 parameters -> the library's
+    tcgen05 kernel, float32 -> PyTorch in float32, the reference's precision).  The evaluator is kept per
+    module, so a loop that calls play_games with the same module re-loads its weights in place instead of
+    re-folding into new buffers and re-capturing CUDA graphs; the module's training flag is left as found."""
+    import weakref
+
+    from c4a0_b200.selfplay import DeviceEvaluator
+
+    key = id(module)
+    hit = _MODULE_EVALUATORS.get(key)
+    prev = hit[1] if hit is not None and hit[0]() is module else None
+    was_training = module.training
+    p = next(module.parameters(), None)
+    try:
+        ev = DeviceEvaluator.from_model(module, p.dtype if p is not None else __import__("torch").float32, reuse=prev)
+    finally:
+        module.train(was_training)
+    for k in [k for k, (ref, _) in _MODULE_EVALUATORS.items() if ref() is None]:
+        del _MODULE_EVALUATORS[k]
+    _MODULE_EVALUATORS[key] = (weakref.ref(module), ev)
+    return ev
+
+
 def close_cached_session() -> None:
     """Free the engine kept by the last play_games call (device memory is released)."""
     if _SESSION["sess"] is not None:
@@ -353,6 +380,7 @@ def play_games(
     import torch
 
     from c4a0_b200 import selfplay
+    from c4a0_b200.native_net import NativeEvaluator
     from c4a0_b200.selfplay import BuiltinEvaluator, DeviceEvaluator, MultiModelEvaluator
 
     reqs = list(reqs)
@@ -367,11 +395,10 @@ def play_games(
         return PlayGamesResult()
     meta = np.array([(r.game_id, r.player0_id, r.player1_id) for r in reqs], dtype=np.uint64)
     n_slots = min(len(reqs), int(max_nn_batch_size))
-    fast = isinstance(py_eval_pos_cb, (DeviceEvaluator, MultiModelEvaluator, BuiltinEvaluator, torch.nn.Module))
+    fast = isinstance(py_eval_pos_cb, (DeviceEvaluator, MultiModelEvaluator, BuiltinEvaluator, NativeEvaluator, torch.nn.Module))
     if fast:
         if isinstance(py_eval_pos_cb, torch.nn.Module):
-            p = next(py_eval_pos_cb.parameters(), None)
-            py_eval_pos_cb = DeviceEvaluator.from_model(py_eval_pos_cb, p.dtype if p is not None else torch.float32)
+            py_eval_pos_cb = _module_evaluator(py_eval_pos_cb)
         ids = set(np.unique(meta[:, 1:]).tolist())
         if isinstance(py_eval_pos_cb, MultiModelEvaluator):
             missing = ids - set(py_eval_pos_cb.evaluators)

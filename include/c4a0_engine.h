@@ -195,6 +195,12 @@ int c4a0_engine_fetch_rows(c4a0_engine *e, uint32_t *n_rows, uint64_t *leaf_mask
  * models in one batch, rust/src/self_play.rs:203-220).  Valid for r < n_rows after every step(). */
 int c4a0_engine_rows_dev(c4a0_engine *e, uint32_t **row_slot_dev, uint64_t **row_model_dev);
 
+/* Device addresses of the row count of the batch to evaluate, for an evaluator that sizes itself on the
+ * device (c4a0_net_bind_row_count): the batch has max(*closed_dev, *open_dev) rows.  *closed_dev is set
+ * when a tick closes (= c4a0_progress.n_rows); *open_dev is the running counter of a tick that a burst of
+ * arena compactions keeps open for k_tail while the evaluator is already enqueued behind k_step. */
+int c4a0_engine_rows_count_dev(c4a0_engine *e, const uint32_t **closed_dev, const uint32_t **open_dev);
+
 /* ---- the host loop ------------------------------------------------------------------------
  * A network evaluator as CUDA graphs: graph_exec (a cudaGraphExec_t) reads rows [0, rows) of the
  * engine's planes buffer and writes the same rows of its logits / q buffers.  Pass several sizes,

@@ -32,7 +32,9 @@ extern "C" {
 #define C4A0_NET_MAX_LAYERS 12
 #define C4A0_NET_MAX_BUFFERS 8
 #define C4A0_NET_TILE_M 128   /* rows per tile */
-#define C4A0_NET_TILE_N 192   /* output columns per tile of a hidden layer */
+#define C4A0_NET_TILE_N 192   /* output columns per tile of a hidden layer (one-CTA kernel) */
+#define C4A0_NET_PAD_N 1344   /* hidden widths are padded to a multiple of this: a common multiple of the CTA-pair
+                                 kernel's column tiles (224, 96, 32) and of the 64-wide K step */
 #define C4A0_NET_TILE_K 64    /* input columns per pipeline stage */
 #define C4A0_NET_HEAD_N 16    /* padded width of an output layer (7 logits / 2 values) */
 
@@ -45,7 +47,7 @@ enum {
 typedef struct {
   const void* weight_dev;  /* bf16 [n_pad][k_pad] row-major (k contiguous), zero padded */
   const float* bias_dev;   /* f32 [n_pad], zero padded */
-  uint32_t n_pad;          /* hidden: a multiple of C4A0_NET_TILE_N; output layers: C4A0_NET_HEAD_N */
+  uint32_t n_pad;          /* hidden: a multiple of C4A0_NET_PAD_N; output layers: C4A0_NET_HEAD_N */
   uint32_t k_pad;          /* a multiple of C4A0_NET_TILE_K */
   uint32_t in_buffer;      /* activation buffer read ... */
   uint32_t in_col0;        /* ... from this column on (a multiple of 64), k_pad columns */
@@ -87,6 +89,12 @@ int c4a0_net_bind_row_count(c4a0_net* net, const uint32_t* a_dev, const uint32_t
 /* Enqueue one forward pass over rows [0, rows) (or the bound device-side count).  One kernel launch;
  * safe to capture into a CUDA graph. */
 int c4a0_net_forward(c4a0_net* net, uint32_t rows, void* stream);
+
+/* Diagnostics: one forward pass in which CTA `cta` logs (SM cycle counter << 8 | tag) events of its three
+ * roles into out[3][4096] (producer, MMA issuer, first epilogue thread; tags: 1 role start, 2 tile start,
+ * 3 dependency met, 4 barrier wait over, 5 K step issued, 6 accumulator ready, 7 accumulator released,
+ * 8 tile published; 0 = unused entry).  Synchronises the stream. */
+int c4a0_net_debug_trace(c4a0_net* net, uint32_t rows, uint32_t cta, void* stream, uint64_t* out, size_t n_out);
 
 /* forward() bracketed by CUDA events; synchronises the stream. */
 int c4a0_net_forward_timed(c4a0_net* net, uint32_t rows, void* stream, float* ms);

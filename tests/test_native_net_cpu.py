@@ -41,9 +41,9 @@ def test_program_shapes_obey_the_kernel_contract():
     Fp = 1344
     for i, (name, W, b, m) in enumerate(layers):
         assert W.shape[1] % L.NET_TILE_K == 0 and b.shape[0] == W.shape[0]
-        assert W.shape[0] == (L.NET_HEAD_N if m["kind"] != L.NET_HIDDEN else W.shape[0] // L.NET_TILE_N * L.NET_TILE_N)
+        assert W.shape[0] == (L.NET_HEAD_N if m["kind"] != L.NET_HIDDEN else W.shape[0] // L.NET_PAD_N * L.NET_PAD_N)
         assert -1 <= m["dep"] < i and m["inp"][1] % 64 == 0
     assert layers[1][1].shape == (2 * Fp, Fp + 128)
-    # width 8: F = 336 is padded to 384 columns
+    # width 8: F = 336 is padded to 1344 columns
     layers, _ = fold_program(_model(8, 2, 2))
-    assert layers[0][1].shape == (384, 128) and layers[1][1].shape == (768, 512)
+    assert layers[0][1].shape == (1344, 128) and layers[1][1].shape == (2688, 1472)

@@ -13,14 +13,23 @@ ap.add_argument("--rows", type=int, nargs="*", default=[1, 128, 300, 1024, 5120,
 ap.add_argument("--check-rows", type=int, default=300)
 ap.add_argument("--iters", type=int, default=30)
 ap.add_argument("--no-time", action="store_true")
+ap.add_argument("--configs", nargs="*", default=["pair", "pair:1", "pair:2", "pair:3", "one"],
+                help="pair = CTA-pair kernel with automatic column tile, pair:N = forced variant N (1: 224, 2: 96, 3: 32), one = one-CTA kernel")
 a = ap.parse_args()
 
 torch.manual_seed(1337)
 dev = torch.device("cuda", 0)
 model = ConnectFourNet(ModelConfig(n_residual_blocks=1, conv_filter_size=a.width, n_policy_layers=4, n_value_layers=2)).to(dev).eval()
 ev = NativeEvaluator(model)
+BODY = r"""
 cap = max(a.rows + [a.check_rows])
+os.environ.pop("C4A0_NET_ONE_CTA", None); os.environ.pop("C4A0_NET_VARIANT", None)
+if CONFIG == "one":
+    os.environ["C4A0_NET_ONE_CTA"] = "1"
+elif ":" in CONFIG:
+    os.environ["C4A0_NET_VARIANT"] = CONFIG.split(":")[1]
 net = ev.instantiate(cap)
+print(f"==== config {CONFIG}", flush=True)
 print(f"F={ev.F} Fp={ev.Fp} layers={[l['name'] for l in ev._layers]} buffers={ev.buffer_cols} net bytes={net.device_bytes/1e6:.1f} MB", flush=True)
 B = a.check_rows
 g = torch.Generator(device="cpu").manual_seed(5)
@@ -81,3 +90,11 @@ if not a.no_time:
         tt.sort()
         fl = ev.flops_per_row() * rows
         print(f"rows {rows:6d}: native {1e3*ts[len(ts)//2]:8.1f} us (min {1e3*ts[0]:.1f})  {fl/ts[len(ts)//2]/1e9:7.1f} TFLOP/s | cuBLASLt graph {1e3*tt[len(tt)//2]:8.1f} us (min {1e3*tt[0]:.1f})", flush=True)
+
+"""
+for CONFIG in a.configs:
+    try:
+        exec(BODY)
+    except Exception as exc:
+        print(f"config {CONFIG} FAILED: {exc!r}", flush=True)
+        break
