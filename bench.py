@@ -365,13 +365,20 @@ def run_ours(args):
         reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
         # max_nn_batch_size: the resident games plus room for the speculative rows (play_games keeps
         # n_slots + spec_rows within the caller's bound)
+        # the trainer lives on rank 0: at N > 1 the other ranks keep their samples on the device and send the
+        # valid ones, packed, straight from the engine's sample store to rank 0 (NCCL send/recv), which
+        # copies everything to the host; rank 0's own games come back through play_games as usual
+        selfplay.DEFAULTS["fetch"] = world == 1 or rank == 0
         res = c4a0_rust.play_games(reqs, G + SPEC_ROOM, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
-        n_pos = int(res._soa.n_samples.sum())
+        n_pos = int(res._run_info.stats["samples"])
         checksum = float(res._soa.q_no_penalty.sum())  # touch the host result
-        if world > 1:  # the trainer lives on rank 0: gather every rank's samples there (NCCL)
-            gm, gs = D.gather_samples(res._meta, res._soa, device=device)
+        if world > 1:
+            meta = np.array([(i, 0, 0) for i in ids], dtype=np.uint64)
+            gm, gs = D.gather_session_samples(c4a0_rust._native._SESSION["sess"], meta)
             if rank == 0:
-                assert int(gs.n_samples.sum()) >= n_pos
+                state["gathered"] = int(gs.n_samples.sum())
+                assert state["gathered"] >= n_pos and len(gm) == G * world
+                checksum += float(gs.q_no_penalty.sum())
         return time.perf_counter() - t0, res._run_info, n_pos, checksum
 
     for _ in range(args.warmup):
@@ -448,7 +455,9 @@ def run_ours(args):
         "sims_per_s": sims_all / dev_s_max, "nn_evals_per_s": evals_all / dev_s_max,
         "e2e": {
             "value": positions_all / e2e_s_max, "unit": UNIT,
-            "h2d_bytes_per_step": 3 * 8 * G, "d2h_bytes_per_step": G * (4 + 43 * (8 + 8 + 28 + 4 + 4)),
+            "h2d_bytes_per_step": 3 * 8 * G,
+            # rank 0: its own games as padded arrays, plus (N > 1) every rank's valid samples packed at 52 B each
+            "d2h_bytes_per_step": G * (4 + 43 * (8 + 8 + 28 + 4 + 4)) + (0 if world == 1 else int(52 * positions_all / max(1, args.steps)) + 28 * G * world),
             "sims_per_s": sims_all / e2e_s_max, "api": "c4a0_rust.play_games(list[GameMetadata], ...) -> PlayGamesResult",
             "wall_ms_per_step": 1e3 * wall_max / max(1, args.steps),
         },

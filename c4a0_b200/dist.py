@@ -45,68 +45,152 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def broadcast_model(model: torch.nn.Module, src: int = 0) -> int:
-    """Broadcast parameters and buffers (BatchNorm statistics) from `src`; returns bytes sent."""
+    """Broadcast parameters and buffers (BatchNorm statistics) from `src` as ONE flat tensor per dtype
+    (a c4a0 network is ~30 tensors; one NCCL call instead of thirty); returns bytes sent."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
     n = 0
     with torch.no_grad():
+        groups = {}
         for t in list(model.parameters()) + list(model.buffers()):
-            dist.broadcast(t.data, src=src)
-            n += t.numel() * t.element_size()
+            groups.setdefault((t.dtype, t.device), []).append(t.data)
+        for tensors in groups.values():
+            flat = torch.cat([t.reshape(-1) for t in tensors])
+            dist.broadcast(flat, src=src)
+            o = 0
+            for t in tensors:
+                t.copy_(flat[o : o + t.numel()].view_as(t))
+                o += t.numel()
+            n += flat.numel() * flat.element_size()
     return n
 
 
-def _gather_rows(x: torch.Tensor, counts: List[int], dst: int) -> Optional[torch.Tensor]:
-    """Gather variable-length leading-dim tensors to `dst` (padded all_gather, then trimmed)."""
-    world = dist.get_world_size()
-    mx = max(counts)
-    pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[: x.shape[0]] = x
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
-    if dist.get_rank() != dst:
+# ------------------------------------------------------------------------------------------------
+# Sample gather: only the valid samples travel, packed, rank -> dst point to point
+# ------------------------------------------------------------------------------------------------
+PACK_WORDS = 13  # int32 words per sample: mask (2), value (2), policy (7), q_penalty, q_no_penalty
+
+
+def pack_samples(n_samples: torch.Tensor, mask: torch.Tensor, value: torch.Tensor, policy: torch.Tensor,
+                 q_penalty: torch.Tensor, q_no_penalty: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[G] counts + padded [G,43,...] sample arrays (int64 bit patterns for the u64 fields) -> (counts int32 [G],
+    packed int32 [S, 13]) holding the S valid samples in game order.  Runs where the tensors live: on the
+    engine's device sample store (no host copy) or on CPU tensors (gloo tests)."""
+    G = n_samples.shape[0]
+    counts = n_samples.to(torch.int32)
+    valid = torch.arange(43, device=n_samples.device)[None, :] < counts[:, None]
+    words = torch.cat([
+        mask.reshape(G, 43, 1).view(torch.int32).reshape(G, 43, 2),
+        value.reshape(G, 43, 1).view(torch.int32).reshape(G, 43, 2),
+        policy.reshape(G, 43, 7).view(torch.int32),
+        q_penalty.reshape(G, 43, 1).view(torch.int32),
+        q_no_penalty.reshape(G, 43, 1).view(torch.int32),
+    ], dim=2)
+    return counts, words[valid].contiguous()
+
+
+def unpack_samples(counts: np.ndarray, packed: np.ndarray) -> GameSamples:
+    """Inverse of pack_samples on the host: padded [G,43,...] arrays (unused cells zero)."""
+    counts = np.asarray(counts, dtype=np.int64)
+    G = len(counts)
+    words = np.zeros((G, 43, PACK_WORDS), np.int32)
+    valid = np.arange(43)[None, :] < counts[:, None]
+    words[valid] = np.asarray(packed, dtype=np.int32).reshape(-1, PACK_WORDS)
+    return GameSamples(
+        counts.astype(np.uint32),
+        np.ascontiguousarray(words[:, :, 0:2]).view(np.uint64).reshape(G, 43),
+        np.ascontiguousarray(words[:, :, 2:4]).view(np.uint64).reshape(G, 43),
+        np.ascontiguousarray(words[:, :, 4:11]).view(np.float32),
+        np.ascontiguousarray(words[:, :, 11]).view(np.float32),
+        np.ascontiguousarray(words[:, :, 12]).view(np.float32),
+    )
+
+
+def gather_packed(meta: torch.Tensor, counts: torch.Tensor, packed: torch.Tensor, dst: int = 0):
+    """Send (meta int64 [G,3], counts int32 [G], packed int32 [S,13]) of every rank to `dst`: one small
+    all_gather of the sizes, then point-to-point transfers of exactly the valid bytes (NCCL send/recv over
+    NVLink, or gloo).  On `dst`: lists of the three tensors in rank order; elsewhere None."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = packed.device
+    sizes = torch.tensor([meta.shape[0], packed.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [tuple(int(v) for v in t.tolist()) for t in all_sizes]
+    if rank != dst:
+        ops = [dist.P2POp(dist.isend, t.contiguous(), dst) for t in (meta, counts, packed) if t.numel()]
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
         return None
-    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+    out, ops = [], []
+    for r, (g, s_) in enumerate(all_sizes):
+        if r == dst:
+            out.append((meta, counts, packed))
+            continue
+        bufs = (torch.empty(g, 3, dtype=torch.int64, device=dev), torch.empty(g, dtype=torch.int32, device=dev),
+                torch.empty(s_, PACK_WORDS, dtype=torch.int32, device=dev))
+        out.append(bufs)
+        ops += [dist.P2POp(dist.irecv, t, r) for t in bufs if t.numel()]
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    return out
+
+
+def _finish_gather(parts):
+    meta = torch.cat([p[0] for p in parts]).cpu().numpy().view(np.uint64)
+    counts = torch.cat([p[1] for p in parts]).cpu().numpy()
+    packed = torch.cat([p[2] for p in parts]).cpu().numpy()
+    return meta, unpack_samples(counts, packed)
 
 
 def gather_samples(meta: np.ndarray, soa: GameSamples, device: Optional[torch.device] = None, dst: int = 0):
-    """Concatenate every rank's finished games on `dst` in rank order.  Returns (meta, soa) on
-    `dst` and (None, None) elsewhere.  uint64 fields travel as int64 bit patterns."""
+    """Concatenate every rank's finished games on `dst` in rank order, from HOST arrays.  Returns (meta, soa)
+    on `dst` and (None, None) elsewhere.  (gather_session_samples() does the same from the engines' device
+    sample stores without the host round trip.)"""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return meta, soa
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    world = dist.get_world_size()
-    n_local = torch.tensor([len(soa.n_samples)], dtype=torch.int64, device=device)
-    all_n = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(all_n, n_local)
-    counts = [int(t.item()) for t in all_n]
 
     def up(a: np.ndarray, view=None) -> torch.Tensor:
         a = np.ascontiguousarray(a)
-        if view is not None:
-            a = a.view(view)
-        return torch.from_numpy(a).to(device)
+        return torch.from_numpy(a.view(view) if view is not None else a).to(device)
 
-    parts = dict(
-        meta=up(np.ascontiguousarray(meta, dtype=np.uint64).reshape(-1, 3), np.int64),
-        n_samples=up(soa.n_samples.astype(np.int64)),
-        mask=up(soa.mask, np.int64),
-        value=up(soa.value, np.int64),
-        policy=up(soa.policy),
-        q_penalty=up(soa.q_penalty),
-        q_no_penalty=up(soa.q_no_penalty),
-    )
-    got = {k: _gather_rows(v, counts, dst) for k, v in parts.items()}
-    if dist.get_rank() != dst:
+    counts, packed = pack_samples(up(soa.n_samples.astype(np.int32)), up(soa.mask, np.int64), up(soa.value, np.int64),
+                                  up(soa.policy), up(soa.q_penalty), up(soa.q_no_penalty))
+    parts = gather_packed(up(np.ascontiguousarray(meta, dtype=np.uint64).reshape(-1, 3), np.int64), counts, packed, dst)
+    if parts is None:
         return None, None
-    h = {k: v.cpu().numpy() for k, v in got.items()}
-    out = GameSamples(
-        h["n_samples"].astype(np.uint32),
-        h["mask"].view(np.uint64),
-        h["value"].view(np.uint64),
-        h["policy"],
-        h["q_penalty"],
-        h["q_no_penalty"],
-    )
-    return h["meta"].view(np.uint64), out
+    return _finish_gather(parts)
+
+
+def gather_session_samples(session, meta: np.ndarray, dst: int = 0):
+    """The samples of `session`'s last play() from every rank onto `dst`, packed on the device straight out of
+    the engines' sample stores (c4a0_engine_results_dev): no padded arrays, no host bounce on the senders.
+    Returns (meta u64 [G,3], GameSamples) on `dst`, (None, None) elsewhere."""
+    from .selfplay import _wrap_i64, _wrap_u32  # engine-owned device arrays as tensors, no copy
+
+    dev = session.device
+    cs, ps = [], []
+    for ln, (lo, hi) in zip(session.lanes, session._last_ranges):
+        n = hi - lo
+        if n == 0:
+            continue
+        with torch.cuda.stream(ln.stream):
+            p_n, p_mask, p_value, p_pol, p_qp, p_qn = ln.engine.results_dev()
+            c, p = pack_samples(
+                _wrap_u32(p_n, n, dev), _wrap_i64(p_mask, n * 43, dev).view(n, 43), _wrap_i64(p_value, n * 43, dev).view(n, 43),
+                _wrap_u32(p_pol, n * 43 * 7, dev).view(torch.float32).view(n, 43, 7),
+                _wrap_u32(p_qp, n * 43, dev).view(torch.float32).view(n, 43),
+                _wrap_u32(p_qn, n * 43, dev).view(torch.float32).view(n, 43))
+            ln.stream.synchronize()
+        cs.append(c)
+        ps.append(p)
+    counts = torch.cat(cs) if cs else torch.zeros(0, dtype=torch.int32, device=dev)
+    packed = torch.cat(ps) if ps else torch.zeros(0, PACK_WORDS, dtype=torch.int32, device=dev)
+    m = torch.from_numpy(np.ascontiguousarray(meta, dtype=np.uint64).reshape(-1, 3).view(np.int64)).to(dev)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return _finish_gather([(m, counts, packed)])
+    parts = gather_packed(m, counts, packed, dst)
+    if parts is None:
+        return None, None
+    return _finish_gather(parts)

@@ -203,6 +203,18 @@ class NativeEvaluator:
     def instantiate(self, max_rows: int) -> "NativeNet":
         return NativeNet(self, max_rows)
 
+    def __call__(self, planes: torch.Tensor):
+        """planes [B,2,6,7] / [B,84] -> (logits [B,7], q_penalty [B], q_no_penalty [B]) float32 CUDA tensors
+        (copies), through a private net sized for the largest batch seen.  The self-play engine does not go
+        through here: every lane owns a net whose input buffer the engine writes directly."""
+        B = int(planes.shape[0])
+        net = getattr(self, "_own_net", None)
+        if net is None or net.max_rows < B:
+            if net is not None:
+                net.close()
+            net = self._own_net = self.instantiate(max(B, 256))
+        return tuple(t.clone() for t in net(planes.to(self.device)))
+
 
 class NativeNet:
     """One c4a0_net: activation buffers for up to max_rows rows over an evaluator's weights."""

@@ -41,7 +41,10 @@ DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, 
             # c4a0_rust.play_games; callbacks never get it (they need not be pure functions of the position)
             "eval_cache": True, "eval_cache_entries": 0,
             # with the cache: top small batches up with the children of expanded leaves (C4A0_FLAG_SPECULATE)
-            "speculate": True, "spec_rows": 0}
+            "speculate": True, "spec_rows": 0,
+            # False: play_games leaves the samples in the engine's device store (multi-GPU ranks whose samples
+            # travel to rank 0 over NCCL, trainers that read export_tensors()) and returns an empty result
+            "fetch": True}
 
 def _buckets():
     """Network batch sizes that get their own CUDA graph: fine steps (a tick launches the smallest

@@ -422,10 +422,16 @@ def play_games(
             getattr(py_eval_pos_cb, "plane_offset", 0), use_cache, spec_rows,
         )
         try:
-            soa, info = sess.play(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb)
+            soa, info = sess.play(meta[:, 0], meta[:, 1], meta[:, 2], py_eval_pos_cb, fetch=bool(selfplay.DEFAULTS.get("fetch", True)))
         except Exception:
             close_cached_session()  # never keep an engine in an unknown state
             raise
+        if soa is None:
+            # selfplay.DEFAULTS["fetch"] = False (additive): the samples stay in the engine's device store for
+            # dist.gather_session_samples() / SelfPlaySession.export_tensors(); the result object is empty
+            out = PlayGamesResult()
+            out._run_info = info
+            return out
     else:
         sess = _session(
             n_slots, len(reqs), int(n_mcts_iterations), float(c_exploration), float(c_ply_penalty),

@@ -35,6 +35,10 @@ def _fake_samples(lo, hi):
         np.broadcast_to((ids[:, None] / 16).astype(np.float32), (n, 43)).copy(),
         np.broadcast_to((-ids[:, None] / 32).astype(np.float32), (n, 43)).copy(),
     )
+    # cells past a game's sample count are zero, as the engine leaves them (only valid samples travel)
+    dead = np.arange(43)[None, :] >= soa.n_samples[:, None]
+    for a in (soa.mask, soa.value, soa.policy, soa.q_penalty, soa.q_no_penalty):
+        a[dead] = 0
     meta = np.stack([ids, ids * 0, ids * 0 + 1], axis=1).astype(np.uint64)
     return meta, soa
 
