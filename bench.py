@@ -374,11 +374,11 @@ def run_ours(args):
         checksum = float(res._soa.q_no_penalty.sum())  # touch the host result
         if world > 1:
             meta = np.array([(i, 0, 0) for i in ids], dtype=np.uint64)
-            gm, gs = D.gather_session_samples(c4a0_rust._native._SESSION["sess"], meta)
-            if rank == 0:
-                state["gathered"] = int(gs.n_samples.sum())
-                assert state["gathered"] >= n_pos and len(gm) == G * world
-                checksum += float(gs.q_no_penalty.sum())
+            gm, gc, gp = D.gather_session_samples(c4a0_rust._native._SESSION["sess"], meta, packed_result=True)
+            if rank == 0:  # host arrays: per game its id and sample count, per valid sample 52 bytes
+                state["gathered"] = int(gc.sum())
+                assert state["gathered"] >= n_pos and len(gm) == G * world and gp.shape == (state["gathered"], D.PACK_WORDS)
+                checksum += float(gp[:, 12].view(np.float32).sum())
         return time.perf_counter() - t0, res._run_info, n_pos, checksum
 
     for _ in range(args.warmup):

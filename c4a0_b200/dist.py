@@ -135,11 +135,40 @@ def gather_packed(meta: torch.Tensor, counts: torch.Tensor, packed: torch.Tensor
     return out
 
 
-def _finish_gather(parts):
-    meta = torch.cat([p[0] for p in parts]).cpu().numpy().view(np.uint64)
-    counts = torch.cat([p[1] for p in parts]).cpu().numpy()
-    packed = torch.cat([p[2] for p in parts]).cpu().numpy()
-    return meta, unpack_samples(counts, packed)
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    if t.is_cuda:  # through pinned memory: a pageable destination halves the copy rate
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return h.numpy()
+    return t.numpy()
+
+
+def unpack_samples_device(counts: torch.Tensor, packed: torch.Tensor):
+    """pack_samples' inverse where the tensors live (rank 0's GPU): padded [G,43,...] tensors."""
+    G = counts.shape[0]
+    words = torch.zeros(G, 43, PACK_WORDS, dtype=torch.int32, device=packed.device)
+    valid = torch.arange(43, device=counts.device)[None, :] < counts[:, None]
+    words[valid] = packed
+    return (counts, words[:, :, 0:2].contiguous().view(torch.int64).reshape(G, 43), words[:, :, 2:4].contiguous().view(torch.int64).reshape(G, 43),
+            words[:, :, 4:11].contiguous().view(torch.float32), words[:, :, 11].contiguous().view(torch.float32),
+            words[:, :, 12].contiguous().view(torch.float32))
+
+
+def _finish_gather(parts, packed_result: bool = False):
+    """Rank-ordered parts on dst -> host.  packed_result: (meta u64 [G,3], counts i32 [G], packed i32 [S,13]) —
+    exactly the valid samples, 52 bytes each; otherwise (meta, GameSamples) with padded [G,43,...] arrays,
+    unpacked on the device when there is one."""
+    meta = torch.cat([p[0] for p in parts])
+    counts = torch.cat([p[1] for p in parts])
+    packed = torch.cat([p[2] for p in parts])
+    if packed_result:
+        return _to_host(meta).view(np.uint64), _to_host(counts), _to_host(packed)
+    if packed.is_cuda:
+        c, m, v, pol, qp, qn = unpack_samples_device(counts, packed)
+        return _to_host(meta).view(np.uint64), GameSamples(_to_host(c).astype(np.uint32), _to_host(m).view(np.uint64), _to_host(v).view(np.uint64),
+                                                           _to_host(pol), _to_host(qp), _to_host(qn))
+    return meta.numpy().view(np.uint64), unpack_samples(counts.numpy(), packed.numpy())
 
 
 def gather_samples(meta: np.ndarray, soa: GameSamples, device: Optional[torch.device] = None, dst: int = 0):
@@ -163,10 +192,11 @@ def gather_samples(meta: np.ndarray, soa: GameSamples, device: Optional[torch.de
     return _finish_gather(parts)
 
 
-def gather_session_samples(session, meta: np.ndarray, dst: int = 0):
+def gather_session_samples(session, meta: np.ndarray, dst: int = 0, packed_result: bool = False):
     """The samples of `session`'s last play() from every rank onto `dst`, packed on the device straight out of
     the engines' sample stores (c4a0_engine_results_dev): no padded arrays, no host bounce on the senders.
-    Returns (meta u64 [G,3], GameSamples) on `dst`, (None, None) elsewhere."""
+    Returns (meta u64 [G,3], GameSamples) on `dst` — or, with packed_result, (meta, counts, packed [S,13]) —
+    and a tuple of Nones elsewhere."""
     from .selfplay import _wrap_i64, _wrap_u32  # engine-owned device arrays as tensors, no copy
 
     dev = session.device
@@ -189,8 +219,8 @@ def gather_session_samples(session, meta: np.ndarray, dst: int = 0):
     packed = torch.cat(ps) if ps else torch.zeros(0, PACK_WORDS, dtype=torch.int32, device=dev)
     m = torch.from_numpy(np.ascontiguousarray(meta, dtype=np.uint64).reshape(-1, 3).view(np.int64)).to(dev)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return _finish_gather([(m, counts, packed)])
+        return _finish_gather([(m, counts, packed)], packed_result)
     parts = gather_packed(m, counts, packed, dst)
     if parts is None:
-        return None, None
-    return _finish_gather(parts)
+        return (None, None, None) if packed_result else (None, None)
+    return _finish_gather(parts, packed_result)

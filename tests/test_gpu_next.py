@@ -176,3 +176,27 @@ def test_multi_model_fast_path_equals_callback_path():
     assert {g.player0_score() for g in fast.results} <= {0.0, 0.5, 1.0}
     with pytest.raises(ValueError):
         R.play_games(reqs, 64, 16, 3.0, 0.01, MultiModelEvaluator({0: DeviceEvaluator(nets[0], torch.float32, 96)}))
+
+
+def test_gather_session_samples_equals_fetch_results():
+    """dist.gather_session_samples packs the valid samples on the device straight from the engine's store;
+    unpacked (on the device or on the host) they equal what fetch_results copies."""
+    from c4a0_b200 import dist as D
+    from c4a0_b200.selfplay import BuiltinEvaluator, SelfPlaySession
+
+    n = 300
+    sess = SelfPlaySession(256, n, 40, 6.6, 0.01, eval_cache=True)
+    ids = np.arange(n, dtype=np.uint64) * 5 + 2
+    z = np.zeros(n, np.uint64)
+    out, info = sess.play(ids, z, z, BuiltinEvaluator("hash"))
+    meta = np.stack([ids, z, z], axis=1)
+    gm, gs = D.gather_session_samples(sess, meta)
+    assert np.array_equal(gm, meta)
+    for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
+        assert np.array_equal(getattr(gs, f), getattr(out, f)), f
+    gm2, counts, packed = D.gather_session_samples(sess, meta, packed_result=True)
+    assert packed.shape == (int(out.n_samples.sum()), D.PACK_WORDS) and np.array_equal(counts, out.n_samples.astype(np.int32))
+    again = D.unpack_samples(counts, packed)
+    for f in ("mask", "value", "policy", "q_penalty", "q_no_penalty"):
+        assert np.array_equal(getattr(again, f), getattr(out, f)), f
+    sess.close()
