@@ -198,6 +198,10 @@ SIGNATURES = {
     "c4a0_host_pos_key": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "c4a0_host_flip_h": (None, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "c4a0_host_shuffle": (None, [C.c_uint64, _P, C.c_size_t]),
+    "c4a0_host_seed_to_key": (None, [C.c_uint64, _P]),
+    "c4a0_host_stdrng_words": (None, [_P, _P, C.c_size_t]),
+    "c4a0_results_to_cbor": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "c4a0_results_from_cbor": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_uint32), _P, _P, _P, _P, _P, _P, _P]),
     # include/c4a0_net.h
     "c4a0_net_create": (C.c_int, [C.POINTER(NetSpec), C.POINTER(_P)]),
     "c4a0_net_destroy": (None, [_P]),

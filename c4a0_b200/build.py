@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libc4a0_engine.so")
 
-SOURCES = ["engine.cu", "batch_ops.cu", "net.cu"]
+SOURCES = ["engine.cu", "batch_ops.cu", "net.cu", "cbor.cu"]
 HEADERS = ["c4_rules.cuh", "c4_math.cuh", "c4_rng.cuh", "common.cuh"]
 
 NVCC_FLAGS = [

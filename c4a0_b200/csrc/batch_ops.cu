@@ -413,5 +413,11 @@ void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t* om, uint64_t* ov)
 }
 uint64_t c4a0_host_pos_key(uint64_t mask, uint64_t value) { return c4::pos_key(Pos{mask, value}); }
 void c4a0_host_shuffle(uint64_t seed, uint32_t* idx, size_t n) { c4::shuffle_indices(seed, idx, n); }
+void c4a0_host_seed_to_key(uint64_t seed, uint32_t* key8) { c4::seed_to_key(seed, key8); }
+void c4a0_host_stdrng_words(const uint32_t* key8, uint32_t* out, size_t n) {
+  c4::StdRngStream rng(0);
+  for (int i = 0; i < 8; i++) rng.key[i] = key8[i];
+  for (size_t i = 0; i < n; i++) out[i] = rng.next_u32();
+}
 
 }  // extern "C"

@@ -9,7 +9,7 @@
 // restate exactly that data flow — same tables, same constants, the same five fused
 // multiply-adds — in double precision, which IEEE-754 makes reproducible on any hardware.
 // tests/test_math_host.py compares the host build against libm over tens of millions of inputs
-// (and DESIGN.md records the exhaustive 2^32 sweep); tests/test_gpu_math.py does the same on the
+// (and DESIGN.md records the exhaustive 2^32 sweep); tests/test_gpu_engine.py::test_device_logf_expf_match_libm does the same on the
 // device build.
 //
 // softmax          mcts.rs:416-434      (max; exp(x - max); left-fold sum; divide)

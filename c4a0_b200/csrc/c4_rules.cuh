@@ -6,7 +6,7 @@
 //   make_move / invert   c4r.rs:58-72, 125-129
 //   legal_moves          c4r.rs:266-269
 //   is_terminal_state    c4r.rs:165-249   (69 win masks == four shift-and tests, proved equal in
-//                                          tests/test_rules_*.py against the oracle's 69 masks)
+//                                          tests/test_oracle_rules.py, tests/test_math_host.py (host) and tests/test_gpu_engine.py (device) against the oracle's 69 masks)
 //   terminal value       c4r.rs:253-263
 //   NN planes            c4r.rs:378-392
 //   flip_h               c4r.rs:289-299

@@ -1357,6 +1357,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
     // speculate while the games themselves ask for at most this many rows: beyond that the spare rows
     // cover too small a part of what the live games will want next (measured on the bench job)
     D.spec_thr = D.spec_cap / 2 < 1024u ? D.spec_cap / 2 : 1024u;
+    if (const char* env = getenv("C4A0_SPEC_THR")) D.spec_thr = (uint32_t)atoi(env);  // tuning knob (results do not depend on it)
     D.max_inline_spec = 4 * D.max_inline;
   }
   D.row_cap = cfg->n_slots + D.spec_cap;

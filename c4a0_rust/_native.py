@@ -193,59 +193,62 @@ class PlayGamesResult:
     @property
     def results(self) -> List[GameResult]:
         if self._results is None:
+            # bulk conversions first (one C loop per array), then plain slot assignments per sample: the per-
+            # sample cost is object creation only (~1 us), not numpy scalar traffic
             soa, out = self._soa, []
-            for i in range(len(soa.n_samples)):
-                md = GameMetadata(int(self._meta[i, 0]), int(self._meta[i, 1]), int(self._meta[i, 2]))
-                samples = [
-                    Sample(int(soa.mask[i, k]), int(soa.value[i, k]), soa.policy[i, k], soa.q_penalty[i, k], soa.q_no_penalty[i, k])
-                    for k in range(int(soa.n_samples[i]))
-                ]
+            counts = soa.n_samples.tolist()
+            meta = self._meta.tolist()
+            valid = np.arange(43)[None, :] < soa.n_samples[:, None]
+            masks, values = soa.mask[valid].tolist(), soa.value[valid].tolist()
+            pol = np.ascontiguousarray(soa.policy[valid])
+            qps, qns = soa.q_penalty[valid], soa.q_no_penalty[valid]
+            new, j = Sample.__new__, 0
+            for i, n in enumerate(counts):
+                samples = []
+                for _ in range(n):
+                    s = new(Sample)
+                    s._mask, s._value, s._policy, s._q_penalty, s._q_no_penalty = masks[j], values[j], pol[j], qps[j], qns[j]
+                    samples.append(s)
+                    j += 1
+                md = new(GameMetadata)
+                md._game_id, md._player0_id, md._player1_id = meta[i]
                 out.append(GameResult(md, samples))
             self._results = out
         return list(self._results)
 
     def to_cbor(self) -> bytes:
-        F = _cbor.F32
+        """serde_cbor's encoding of the result (pybridge.rs:73-81), written by the library's bulk encoder
+        (csrc/cbor.cu); c4a0_rust/_cbor.py is the same codec in Python."""
+        import ctypes as C
+
         soa = self._soa
-        games = []
-        for i in range(len(soa.n_samples)):
-            samples = []
-            for k in range(int(soa.n_samples[i])):
-                samples.append(
-                    {
-                        "pos": {"mask": int(soa.mask[i, k]), "value": int(soa.value[i, k])},
-                        "policy": [F(x) for x in soa.policy[i, k].tolist()],
-                        "q_penalty": F(soa.q_penalty[i, k]),
-                        "q_no_penalty": F(soa.q_no_penalty[i, k]),
-                    }
-                )
-            games.append(
-                {
-                    "metadata": {
-                        "game_id": int(self._meta[i, 0]),
-                        "player0_id": int(self._meta[i, 1]),
-                        "player1_id": int(self._meta[i, 2]),
-                    },
-                    "samples": samples,
-                }
-            )
-        return _cbor.dumps({"results": games})
+        arrs = [np.ascontiguousarray(self._meta, dtype=np.uint64), np.ascontiguousarray(soa.n_samples, dtype=np.uint32),
+                np.ascontiguousarray(soa.mask, dtype=np.uint64), np.ascontiguousarray(soa.value, dtype=np.uint64),
+                np.ascontiguousarray(soa.policy, dtype=np.float32), np.ascontiguousarray(soa.q_penalty, dtype=np.float32),
+                np.ascontiguousarray(soa.q_no_penalty, dtype=np.float32)]
+        n, need = len(arrs[1]), C.c_size_t(0)
+        lib = L.lib()
+        L.check(lib.c4a0_results_to_cbor(*[L.ptr(a) for a in arrs], n, None, 0, C.byref(need)))
+        out = np.empty(need.value, np.uint8)
+        L.check(lib.c4a0_results_to_cbor(*[L.ptr(a) for a in arrs], n, L.ptr(out), out.size, C.byref(need)))
+        return out.tobytes()
 
     @staticmethod
     def from_cbor(cbor: bytes) -> "PlayGamesResult":
-        try:
-            doc = _cbor.loads(cbor)
-            results = []
-            for g in doc["results"]:
-                md = g["metadata"]
-                samples = [
-                    Sample(s["pos"]["mask"], s["pos"]["value"], s["policy"], s["q_penalty"], s["q_no_penalty"])
-                    for s in g["samples"]
-                ]
-                results.append(GameResult(GameMetadata(md["game_id"], md["player0_id"], md["player1_id"]), samples))
-            return PlayGamesResult._from_results(results)
-        except (KeyError, TypeError, IndexError) as exc:
-            raise ValueError(f"invalid PlayGamesResult CBOR: {exc!r}") from exc
+        import ctypes as C
+
+        buf = np.frombuffer(bytes(cbor), dtype=np.uint8)
+        lib, n = L.lib(), C.c_uint32(0)
+        if lib.c4a0_results_from_cbor(L.ptr(buf), buf.size, C.byref(n), None, None, None, None, None, None, None) != 0:
+            raise ValueError((lib.c4a0_last_error() or b"invalid PlayGamesResult CBOR").decode("utf-8", "replace"))
+        g = n.value
+        meta = np.zeros((g, 3), np.uint64)
+        soa = E.GameSamples(np.zeros(g, np.uint32), np.zeros((g, 43), np.uint64), np.zeros((g, 43), np.uint64),
+                            np.zeros((g, 43, 7), np.float32), np.zeros((g, 43), np.float32), np.zeros((g, 43), np.float32))
+        if lib.c4a0_results_from_cbor(L.ptr(buf), buf.size, C.byref(n), L.ptr(meta), L.ptr(soa.n_samples), L.ptr(soa.mask),
+                                      L.ptr(soa.value), L.ptr(soa.policy), L.ptr(soa.q_penalty), L.ptr(soa.q_no_penalty)) != 0:
+            raise ValueError((lib.c4a0_last_error() or b"invalid PlayGamesResult CBOR").decode("utf-8", "replace"))
+        return PlayGamesResult._from_soa(meta, soa)
 
     def __getstate__(self) -> bytes:
         return self.to_cbor()

@@ -69,11 +69,12 @@ typedef struct {
                                   run inside one step (0 = default: 2, or 4 with the evaluation cache) */
   int32_t device;              /* CUDA device ordinal */
   uint32_t plane_stride;       /* elements between consecutive rows of planes_dev (0 = 84; a multiple of
-                                  4, >= 84; elements 84.. of a row are never written) */
+                                  4, >= 84; elements 88.. of a row are never written; bf16 rows with a
+                                  16-byte-aligned stride get zeros in elements 84..87) */
   uint32_t flags;              /* C4A0_FLAG_* */
   uint32_t arena_blocks;       /* tree blocks (160 B) per arena half per game; 0 = n_mcts_iterations + 2,
                                   the minimum.  Larger halves make re-rooting copy-free until a half fills. */
-  uint32_t eval_cache_entries; /* with C4A0_FLAG_EVAL_CACHE: entries (96 B each) of the evaluation cache, rounded
+  uint32_t eval_cache_entries; /* with C4A0_FLAG_EVAL_CACHE: entries (64 B each) of the evaluation cache, rounded
                                   up to a power of two; 0 = sized from n_slots * n_mcts_iterations and the
                                   free device memory */
   uint32_t spec_rows;          /* with C4A0_FLAG_SPECULATE: rows a small batch is topped up to (0 = 8192, at most n_slots) */
@@ -328,6 +329,26 @@ void c4a0_host_flip_h(uint64_t mask, uint64_t value, uint64_t *out_mask, uint64_
 uint64_t c4a0_host_pos_key(uint64_t mask, uint64_t value);
 /* idx[0..n) permuted like `results.shuffle(&mut StdRng::seed_from_u64(seed))` (pybridge.rs:110-113) */
 void c4a0_host_shuffle(uint64_t seed, uint32_t *idx, size_t n);
+/* The pieces of rand 0.10.1's StdRng as restated here, for known-answer tests against public vectors:
+ * SeedableRng::seed_from_u64's PCG32 key expansion, and the ChaCha12 word stream of a 256-bit key
+ * (64-bit block counter from 0, stream 0): out[0..n) = next_u32() repeatedly. */
+void c4a0_host_seed_to_key(uint64_t seed, uint32_t *key8);
+void c4a0_host_stdrng_words(const uint32_t *key8, uint32_t *out, size_t n);
+
+/* ---- wire format of PlayGamesResult (host only) ------------------------------------------------------
+ * The reference pickles a PlayGamesResult as the CBOR bytes of `serde_cbor::to_vec` (rust/src/pybridge.rs:
+ * 73-92, 94-104).  to_cbor: meta [n_games][3] (game_id, player0_id, player1_id), n_samples [n_games] and the
+ * padded sample arrays [n_games][43] (policy [n_games][43][7]) -> out; *needed = bytes the encoding takes
+ * (call with out = NULL to size the buffer).  from_cbor: call with the arrays NULL to get *n_games, then again
+ * with arrays of that many games (cells past a game's sample count are left untouched: pass zeroed arrays).
+ * Unknown map keys are skipped; a missing field or malformed input is C4A0_E_INVALID (the reference raises
+ * ValueError, pybridge.rs:254-259). */
+int c4a0_results_to_cbor(const uint64_t *meta, const uint32_t *n_samples, const uint64_t *mask,
+                         const uint64_t *value, const float *policy, const float *q_penalty,
+                         const float *q_no_penalty, uint32_t n_games, uint8_t *out, size_t cap, size_t *needed);
+int c4a0_results_from_cbor(const uint8_t *buf, size_t len, uint32_t *n_games, uint64_t *meta,
+                           uint32_t *n_samples, uint64_t *mask, uint64_t *value, float *policy,
+                           float *q_penalty, float *q_no_penalty);
 
 #ifdef __cplusplus
 }

@@ -32,14 +32,35 @@ def test_header_symbols_are_exported_and_bound():
     assert lib.c4a0_abi_version() == 2
 
 
-def test_struct_sizes_match_the_header():
+def test_struct_layouts_match_the_compiled_headers(tmp_path):
+    """tests/abi_check.c includes include/c4a0_engine.h and include/c4a0_net.h, is compiled with gcc (C99, no
+    CUDA) and prints sizeof / offsetof of every struct field; the ctypes mirrors must agree field by field."""
+    import shutil
+    import subprocess
+
     from c4a0_b200 import _lib as L
 
-    assert C.sizeof(L.Config) == 13 * 4
-    assert C.sizeof(L.Progress) == 7 * 4
-    assert C.sizeof(L.Stats) == 15 * 8
-    assert C.sizeof(L.RunReport) == 5 * 8 + 4 * 8 + 8 + 2 * 8 + 32 * 8
-    assert C.sizeof(L.NNGraph) == 16
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    exe = tmp_path / "abi_check"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_check.c"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {ln.split()[0]: tuple(int(x) for x in ln.split()[1:]) for ln in out if ln.strip()}
+    mirrors = {"c4a0_config": L.Config, "c4a0_progress": L.Progress, "c4a0_stats": L.Stats, "c4a0_nn_graph": L.NNGraph,
+               "c4a0_run_report": L.RunReport, "c4a0_slot_info": L.SlotInfo, "c4a0_net_layer": L.NetLayer,
+               "c4a0_net_spec": L.NetSpec}
+    for cname, st in mirrors.items():
+        assert got[cname] == (C.sizeof(st),), cname
+        for fname, _ in st._fields_:
+            f = getattr(st, fname)
+            assert got[f"{cname}.{fname}"] == (f.offset, f.size), f"{cname}.{fname}"
+        # the header has no field the mirror lacks: the fields tile the struct up to alignment padding
+        assert sum(1 for k in got if k.startswith(cname + ".")) == len(st._fields_)
+    assert got["C4A0_ABI_VERSION"] == (L.lib().c4a0_abi_version(),)
+    assert got["C4A0_MAX_SAMPLES"] == (L.MAX_SAMPLES,) and got["C4A0_NET_MAX_LAYERS"] == (L.NET_MAX_LAYERS,)
+    assert got["C4A0_NET_PAD_N"] == (L.NET_PAD_N,)
 
 
 def test_no_cpu_fallback():

@@ -123,3 +123,50 @@ def test_unsupported_entry_points_say_so():
         R.run_tui(lambda m, p: None, 10, 1.0, 0.01)
     with pytest.raises(NotImplementedError):
         R.PlayGamesResult().score_policies("a", "b", "c")
+
+
+def _python_cbor(res):
+    """PlayGamesResult -> bytes with the Python codec (c4a0_rust/_cbor.py): the cross-check of csrc/cbor.cu."""
+    F = _cbor.F32
+    games = []
+    for g in res.results:
+        md = g.metadata
+        games.append({
+            "metadata": {"game_id": md.game_id, "player0_id": md.player0_id, "player1_id": md.player1_id},
+            "samples": [{"pos": {"mask": s._mask, "value": s._value}, "policy": [F(x) for x in s._policy.tolist()],
+                         "q_penalty": F(s._q_penalty), "q_no_penalty": F(s._q_no_penalty)} for s in g.samples],
+        })
+    return _cbor.dumps({"results": games})
+
+
+def test_bulk_cbor_codec_equals_the_python_codec_byte_for_byte():
+    res, _ = _result_from_oracle(n_games=9)
+    assert res.to_cbor() == _python_cbor(res)
+    # float edge cases: half normals / subnormals / limits, values that need a single, infinities, -0, NaN;
+    # integers at every head width
+    vals = [0.0, -0.0, 1.0, -1.0, 0.5, 65504.0, 65505.0, 65520.0, 2.0**-14, 2.0**-15, 2.0**-24, 2.0**-25, 3 * 2.0**-24,
+            1023 * 2.0**-24, 1025 * 2.0**-25, 1e-8, 1 / 7, 0.97, 1e30, float("inf"), float("-inf"), float("nan"), 6.1035156e-05]
+    ints = [0, 23, 24, 255, 256, 65535, 65536, 2**32 - 1, 2**32, 2**64 - 1]
+    samples = []
+    for i in range(0, len(vals) - 8, 3):
+        samples.append(R.Sample(ints[i % len(ints)], ints[(i + 3) % len(ints)], vals[i : i + 7], vals[i + 7], vals[(i + 8) % len(vals)]))
+    weird = R.PlayGamesResult._from_results([R.GameResult(R.GameMetadata(ints[k], ints[-1 - k], ints[(2 * k) % len(ints)]), samples)
+                                             for k in range(len(ints))])
+    blob = weird.to_cbor()
+    assert blob == _python_cbor(weird)
+    back = R.PlayGamesResult.from_cbor(blob)
+    assert np.array_equal(back._meta, weird._meta)
+    for f in ("n_samples", "mask", "value"):
+        assert np.array_equal(getattr(back._soa, f), getattr(weird._soa, f)), f
+    for f in ("policy", "q_penalty", "q_no_penalty"):  # bit patterns, NaN payload aside
+        a, b = getattr(back._soa, f), getattr(weird._soa, f)
+        same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), f
+    # another encoder's bytes for the same document decode too (cbor2 writes canonical floats, other key widths)
+    cbor2 = pytest.importorskip("cbor2")
+    doc = cbor2.loads(res.to_cbor())
+    doc["results"][0]["extra_field"] = [1, {"x": b"bytes"}]
+    again = R.PlayGamesResult.from_cbor(cbor2.dumps(doc))
+    assert again.to_cbor() == res.to_cbor()
+    empty = R.PlayGamesResult()
+    assert R.PlayGamesResult.from_cbor(empty.to_cbor()).to_cbor() == empty.to_cbor() == _cbor.dumps({"results": []})
