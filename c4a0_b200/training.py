@@ -61,8 +61,13 @@ class TrainingGen(BaseModel):
             f.write(self.model_dump_json(indent=2))
         with open(os.path.join(d, "games.pkl"), "wb") as f:
             pickle.dump(games, f)
+        cpu_model = copy.deepcopy(model).cpu()
         with open(os.path.join(d, "model.pkl"), "wb") as f:
-            pickle.dump(copy.deepcopy(model).cpu(), f)
+            pickle.dump(cpu_model, f)
+        # the same weights without a class path: what a reference checkout (c4a0.nn.ConnectFourNet, a
+        # LightningModule) can load with ConnectFourNet(ModelConfig(**config)).load_state_dict(state_dict)
+        torch.save({"config": cpu_model.config.model_dump(), "state_dict": cpu_model.state_dict()},
+                   os.path.join(d, "model_state.pt"))
 
     @staticmethod
     def load_all(base_dir: str) -> List["TrainingGen"]:
@@ -91,12 +96,103 @@ class TrainingGen(BaseModel):
         return gen
 
     def get_model(self, base_dir: str) -> ConnectFourNet:
-        with open(os.path.join(self.gen_folder(base_dir), "model.pkl"), "rb") as f:
-            return pickle.load(f)
+        """model.pkl of this generation.  A directory written by the reference holds a pickled
+        `c4a0.nn.ConnectFourNet` (a LightningModule with torchmetrics members, training.py:62-67); its
+        submodules `conv`, `fc_policy`, `fc_value` are plain torch and carry the same parameter names, so the
+        weights are moved into this package's class (see load_reference_model)."""
+        d = self.gen_folder(base_dir)
+        model = None
+        if os.path.exists(os.path.join(d, "model.pkl")):
+            with open(os.path.join(d, "model.pkl"), "rb") as f:
+                try:
+                    model = _ModelUnpickler(f).load()
+                except Exception:
+                    model = None
+        if isinstance(model, ConnectFourNet) and "_c4a0_foreign" not in model.__dict__:
+            return model
+        if model is not None:
+            return load_reference_model(model)
+        state = os.path.join(d, "model_state.pt")
+        if os.path.exists(state):
+            blob = torch.load(state, map_location="cpu", weights_only=False)
+            out = ConnectFourNet(ModelConfig(**blob["config"]))
+            out.load_state_dict(blob["state_dict"])
+            return out.eval()
+        raise RuntimeError(f"cannot load {os.path.join(d, 'model.pkl')}")
 
     def get_games(self, base_dir: str) -> Optional[PlayGamesResult]:
         with open(os.path.join(self.gen_folder(base_dir), "games.pkl"), "rb") as f:
             return pickle.load(f)
+
+
+class _Stub:
+    """Stands in for classes of packages this image lacks (pytorch_lightning, torchmetrics, ...) while
+    unpickling a model the reference wrote: accepts any constructor arguments and any state."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+
+    def __call__(self, *a, **k):
+        return _Stub()
+
+
+class _ModelUnpickler(pickle.Unpickler):
+    """Maps the reference's class paths onto this package's classes; unknown third-party classes become stubs."""
+
+    def find_class(self, module, name):
+        if module in ("c4a0.nn", "src.c4a0.nn"):
+            from . import nn as local
+
+            if name == "ConnectFourNet":
+                return _ForeignNet
+            if hasattr(local, name):
+                return getattr(local, name)
+            return _Stub
+        try:
+            return super().find_class(module, name)
+        except (ImportError, AttributeError):
+            return _Stub
+
+
+class _ForeignNet(torch.nn.Module):
+    """Receives the pickled state of the reference's ConnectFourNet (whatever its base classes stored)."""
+
+    def __setstate__(self, state):
+        torch.nn.Module.__init__(self)
+        self.__dict__.update(state)
+        self.__dict__["_c4a0_foreign"] = True
+
+
+def load_reference_model(obj) -> ConnectFourNet:
+    """A model unpickled from a reference-written model.pkl -> this package's ConnectFourNet with the same
+    weights.  The hyper-parameters come from the object's `config` (ModelConfig fields, nn.py:16-38) or are
+    read off the layer shapes."""
+    mods = obj.__dict__.get("_modules", {})
+    conv, fc_policy, fc_value = mods.get("conv"), mods.get("fc_policy"), mods.get("fc_value")
+    if conv is None or fc_policy is None or fc_value is None:
+        raise RuntimeError("the pickled model has no conv / fc_policy / fc_value submodules")
+    cfg = obj.__dict__.get("config")
+    if isinstance(cfg, dict):
+        cfg = ModelConfig(**cfg)
+    if not isinstance(cfg, ModelConfig):
+        fields = {k: getattr(cfg, k) for k in ("n_residual_blocks", "conv_filter_size", "n_policy_layers", "n_value_layers")
+                  if cfg is not None and hasattr(cfg, k)}
+        if len(fields) != 4:  # read the architecture off the modules
+            fields = dict(n_residual_blocks=len(list(conv.children())) - 1, conv_filter_size=list(conv.children())[0].out_channels,
+                          n_policy_layers=len(list(fc_policy.children())) - 1, n_value_layers=len(list(fc_value.children())) - 1)
+        extra = {k: getattr(cfg, k) for k in ("lr_schedule", "l2_reg") if cfg is not None and hasattr(cfg, k)}
+        cfg = ModelConfig(**fields, **extra)
+    out = ConnectFourNet(cfg)
+    sd = {}
+    for prefix, m in (("conv", conv), ("fc_policy", fc_policy), ("fc_value", fc_value)):
+        for k, v in m.state_dict().items():
+            sd[f"{prefix}.{k}"] = v
+    out.load_state_dict(sd)
+    return out.eval()
 
 
 def parse_lr_schedule(floats: List[float]) -> Dict[int, float]:
@@ -230,8 +326,18 @@ def self_play(model: ConnectFourNet, n_games: int, batch_size: int, n_mcts_itera
     evaluator = DeviceEvaluator.from_model(model, nn_dtype, reuse=evaluator)
     lo, hi = D.shard_range(n_games, rank, world)
     reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in range(lo, hi)]  # training.py:181
-    mine = c4a0_rust.play_games(reqs, batch_size, n_mcts_iterations, c_exploration, c_ply_penalty, evaluator)
-    meta, soa = D.gather_samples(mine._meta, mine._soa, device=device if world > 1 else None)
+    from . import selfplay
+
+    if world == 1:
+        return c4a0_rust.play_games(reqs, batch_size, n_mcts_iterations, c_exploration, c_ply_penalty, evaluator), evaluator
+    # every rank keeps its samples on the device; the valid ones travel packed to rank 0 (dist.py)
+    selfplay.DEFAULTS["fetch"] = False
+    try:
+        c4a0_rust.play_games(reqs, batch_size, n_mcts_iterations, c_exploration, c_ply_penalty, evaluator)
+    finally:
+        selfplay.DEFAULTS["fetch"] = True
+    meta = np.array([(i, 0, 0) for i in range(lo, hi)], dtype=np.uint64).reshape(-1, 3)
+    meta, soa = D.gather_session_samples(c4a0_rust._native._SESSION["sess"], meta)
     games = PlayGamesResult._from_soa(meta, soa) if rank == 0 else None
     return games, evaluator
 
@@ -288,12 +394,13 @@ def training_loop(base_dir: str, device: torch.device, n_self_play_games: int, n
         gen = box[0]
         torch.distributed.barrier()
     evaluator = None
-    while max_gens is None or gen.gen_n < max_gens:
+    while True:  # like the reference (training.py:278-294): at least one generation, then check max_gens
         gen, evaluator = train_single_gen(
             base_dir, device, gen, n_self_play_games, model_config=model_config, max_epochs=max_epochs,
             nn_dtype=nn_dtype, evaluator=evaluator, log=log if rank == 0 else None, **params,
         )
-    return gen
+        if max_gens is not None and gen.gen_n >= max_gens:
+            return gen
 
 
 def main(argv=None):

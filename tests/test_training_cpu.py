@@ -116,4 +116,97 @@ def test_generation_directory_round_trip(tmp_path):
     gens = T.TrainingGen.load_all(base)
     assert [g.gen_n for g in gens] == [1, 0] and gens[0].val_loss == 1.25
     assert len(gens[0].get_games(base).results) == 4
-    assert sorted(os.listdir(gens[0].gen_folder(base))) == ["games.pkl", "metadata.json", "model.pkl"]
+    assert sorted(os.listdir(gens[0].gen_folder(base))) == ["games.pkl", "metadata.json", "model.pkl", "model_state.pt"]
+
+
+def test_model_pkl_written_by_the_reference_can_be_resumed(tmp_path):
+    """model.pkl of a reference training directory names `c4a0.nn.ConnectFourNet`, a LightningModule
+    with torchmetrics members (src/c4a0/nn.py:41-57, training.py:62-67).  Emulated here with throw-away modules
+    `c4a0.nn`, `pytorch_lightning`, `torchmetrics` that exist only while the file is written."""
+    import pickle
+    import sys
+    import types
+
+    from c4a0_b200.nn import ConnectFourNet, ModelConfig
+    from c4a0_b200.training import TrainingGen
+
+    cfg = ModelConfig(n_residual_blocks=1, conv_filter_size=4, n_policy_layers=3, n_value_layers=2)
+    torch.manual_seed(3)
+    ours = ConnectFourNet(cfg)
+
+    pl = types.ModuleType("pytorch_lightning")
+    tm = types.ModuleType("torchmetrics")
+    ref_pkg, ref_nn = types.ModuleType("c4a0"), types.ModuleType("c4a0.nn")
+
+    class LightningModule(torch.nn.Module):
+        pass
+
+    class MeanMetric(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("mean_value", torch.zeros(()))
+
+    from typing import Dict
+
+    from pydantic import BaseModel
+
+    class RefModelConfig(BaseModel):  # the reference's ModelConfig is a pydantic model too (nn.py:16-38)
+        n_residual_blocks: int
+        conv_filter_size: int
+        n_policy_layers: int
+        n_value_layers: int
+        lr_schedule: Dict[int, float] = {0: 2e-3}
+        l2_reg: float = 4e-4
+
+    class RefNet(LightningModule):
+        def __init__(self, c):
+            super().__init__()
+            self.config = RefModelConfig(**c.model_dump())
+            self.conv, self.fc_policy, self.fc_value = ours.conv, ours.fc_policy, ours.fc_value
+            self.policy_kl_div, self.value_mse = MeanMetric(), MeanMetric()
+            self._trainer = None
+
+    for mod, cls, name in ((pl, LightningModule, "LightningModule"), (tm, MeanMetric, "MeanMetric"),
+                           (ref_nn, RefNet, "ConnectFourNet"), (ref_nn, RefModelConfig, "ModelConfig")):
+        cls.__module__, cls.__qualname__, cls.__name__ = mod.__name__, name, name
+        setattr(mod, name, cls)
+    ref_nn.ResidualBlock = type(list(ours.conv.children())[1])
+    saved = {k: sys.modules.get(k) for k in ("pytorch_lightning", "torchmetrics", "c4a0", "c4a0.nn")}
+    sys.modules.update({"pytorch_lightning": pl, "torchmetrics": tm, "c4a0": ref_pkg, "c4a0.nn": ref_nn})
+    try:
+        gen = TrainingGen(created_at=__import__("datetime").datetime(2024, 1, 2, 3, 4, 5), gen_n=3, n_mcts_iterations=4,
+                          c_exploration=1.0, c_ply_penalty=0.01, self_play_batch_size=4, training_batch_size=4)
+        d = gen.gen_folder(str(tmp_path))
+        os.makedirs(d)
+        with open(os.path.join(d, "model.pkl"), "wb") as f:
+            pickle.dump(RefNet(cfg), f)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert "pytorch_lightning" not in sys.modules and "c4a0.nn" not in sys.modules
+    loaded = gen.get_model(str(tmp_path))
+    assert type(loaded) is ConnectFourNet and loaded.config.n_policy_layers == 3 and loaded.config.conv_filter_size == 4
+    for (ka, a), (kb, b) in zip(sorted(ours.state_dict().items()), sorted(loaded.state_dict().items())):
+        assert ka == kb and torch.equal(a, b)
+    x = (torch.rand(5, 2, 6, 7) < 0.3).float()
+    for a, b in zip(ours.eval()(x), loaded(x)):
+        assert torch.equal(a, b)
+
+
+def test_generation_directory_also_holds_a_class_free_model_file(tmp_path):
+    from c4a0_b200.nn import ConnectFourNet, ModelConfig
+    from c4a0_b200.training import TrainingGen
+
+    cfg = ModelConfig(n_residual_blocks=1, conv_filter_size=2, n_policy_layers=2, n_value_layers=2)
+    gen = TrainingGen.load_latest_with_default(str(tmp_path), cfg, n_mcts_iterations=2, c_exploration=1.0, c_ply_penalty=0.01,
+                                               self_play_batch_size=4, training_batch_size=4)
+    blob = torch.load(os.path.join(gen.gen_folder(str(tmp_path)), "model_state.pt"), weights_only=False)
+    m = ConnectFourNet(ModelConfig(**blob["config"]))
+    m.load_state_dict(blob["state_dict"])
+    os.remove(os.path.join(gen.gen_folder(str(tmp_path)), "model.pkl"))
+    again = gen.get_model(str(tmp_path))  # falls back to the class-free file
+    for a, b in zip(m.state_dict().values(), again.state_dict().values()):
+        assert torch.equal(a, b)
