@@ -73,10 +73,18 @@ def parse_args():
     ap.add_argument("--host-loop", choices=["native", "python"], default="native",
                     help="python = eager network + per-tick polling (what ncu can follow; slower)")
     ap.add_argument("--plain-fold", action="store_true", help="GEMM-folded form without the epilogue-fused layout (FoldedNet)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: every GPU plays --games games; strong: --total-games games are divided over the GPUs")
+    ap.add_argument("--total-games", type=int, default=0, help="with --scaling strong: games of the whole job (default --games)")
+    ap.add_argument("--preset", choices=["config4"], default=None,
+                    help="config4 = BASELINE.json configs[3]: 131,072 concurrent games x 1,600 sims/move, 64-filter ResNet, bf16")
     ap.add_argument("--nn", choices=["native", "cublas"], default="native",
                     help="bf16 network: native = the library's tcgen05 kernel (csrc/net.cu), cublas = the same folded "
                          "network as PyTorch/cuBLASLt GEMMs in bucketed CUDA graphs")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.preset == "config4":
+        args.games, args.sims, args.width = 131072, 1600, 64
+    return args
 
 
 def make_model(width: int, dtype: torch.dtype, device):
@@ -306,18 +314,60 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def latest_counters():
+    """profiles/rNN_kernel_counters.json of the latest round (tools/ncu_counters.py over `ncu --set full` captures of
+    the benched job's own launches)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_kernel_counters.json")))
+    if not files:
+        return None, None
+    try:
+        return json.load(open(files[-1])), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
 def workload_config(args, world):
+    games = getattr(args, "_games_per_gpu", args.games)
     return {
-        "workload": f"gen-0 self-play, {args.games} lockstep games per GPU x {args.sims} MCTS sims/move, 7x6 board, "
+        "workload": f"gen-0 self-play, {games} lockstep games per GPU x {args.sims} MCTS sims/move, 7x6 board, "
                     f"random-init c4a0 ResNet (1 block x {args.width} filters, 4 policy / 2 value layers), "
                     f"c_exploration={C_EXPLORATION}, c_ply_penalty={C_PLY_PENALTY}",
-        "games_per_gpu": args.games, "sims_per_move": args.sims, "global_games": args.games * world,
-        "max_nn_batch_size": args.games + SPEC_ROOM,
+        "games_per_gpu": games, "sims_per_move": args.sims, "global_games": games * world,
+        "max_nn_batch_size": games + SPEC_ROOM,
         "parallelism": f"games sharded over {world} GPU(s), no search-path collective",
-        "l2": "inputs larger than L2: the games' live trees (arenas of tens of GB per GPU, ~1.5 GB of them touched "
-              "between two visits of a game) and the evaluation cache (8.6 GB) against 126 MB of L2; every step starts "
-              "with an empty evaluation cache",
+        "l2": "inputs larger than L2: the games' live trees (tens of GB of arenas per GPU, ~1.5 GB of them touched "
+              "between two visits of a game) and the evaluation cache (GBs; see engine_device_gb) against 126 MB of L2; "
+              "every step starts with an empty evaluation cache",
     }
+
+
+def nn_roofline(args, flops_per_row, rows_per_tick, nn_ms, native):
+    """The network kernel against the tensor roofline: reference-form FLOPs of the rows a tick really evaluates over
+    the kernel's sampled device time, against the measured dense bf16 peak; tensor-pipe utilisation by ncu counter
+    from the round's capture of the benched job."""
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        src = "measured burst (MEASURED_PEAKS.json)"
+    except Exception:
+        peak, src = 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
+    out = {"bound": "tensor", "unit": "TFLOP/s", "flops_per_eval": flops_per_row, "peak": peak, "peak_source": src,
+           "kernel": "k_net2 (csrc/net.cu: tcgen05.mma cta_group::2, TMEM accumulators, TMA operand ring)" if native
+                     else "cuBLASLt GEMM chain via PyTorch (library)",
+           "rows_per_launch": rows_per_tick, "avg_launch_ms": nn_ms}
+    if nn_ms:
+        out["achieved"] = flops_per_row * rows_per_tick / (nn_ms * 1e-3) / 1e12
+        out["frac"] = out["achieved"] / peak
+    counters, counters_file = latest_counters()
+    if native and counters and "k_net2" in counters:
+        kn = counters["k_net2"]
+        pct = kn.get("tensor_pipe_active_pct_of_elapsed") or []
+        if pct:
+            out["tensor_pipe_active_pct"] = sum(pct) / len(pct)  # sm__pipe_tensor_cycles_active, % of elapsed cycles
+            out["tensor_pipe_source"] = counters_file
+            out["l2_to_sm_bytes_per_launch"] = (sum(kn.get("l2_to_sm_read") or [0]) / max(1, len(kn.get("l2_to_sm_read") or [1])))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -345,8 +395,15 @@ def run_ours(args):
     selfplay.DEFAULTS["eval_cache_entries"] = args.eval_cache_entries
     selfplay.DEFAULTS["speculate"] = not args.no_speculate
     selfplay.DEFAULTS["spec_rows"] = args.spec_rows
-    G = args.games
-    ids = range(rank * G, (rank + 1) * G)  # weak scaling: every rank plays its own G games
+    if args.scaling == "strong":  # a fixed job divided over the GPUs (contiguous game-id ranges, like dist.shard_range)
+        total = args.total_games or args.games
+        lo, hi = D.shard_range(total, rank, world)
+        G = hi - lo
+        ids = range(lo, hi)
+        args._games_per_gpu = (total + world - 1) // world
+    else:  # weak scaling: every rank plays its own G games
+        G = args.games
+        ids = range(rank * G, (rank + 1) * G)
 
     def barrier():
         if world > 1:
@@ -369,7 +426,8 @@ def run_ours(args):
         # valid ones, packed, straight from the engine's sample store to rank 0 (NCCL send/recv), which
         # copies everything to the host; rank 0's own games come back through play_games as usual
         selfplay.DEFAULTS["fetch"] = world == 1 or rank == 0
-        res = c4a0_rust.play_games(reqs, G + SPEC_ROOM, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
+        with torch.cuda.nvtx.range("play_games"):
+            res = c4a0_rust.play_games(reqs, G + SPEC_ROOM, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
         n_pos = int(res._run_info.stats["samples"])
         checksum = float(res._soa.q_no_penalty.sum())  # touch the host result
         if world > 1:
@@ -436,12 +494,15 @@ def run_ours(args):
             avg_launch_ms=k_step_ms, nn_graph_avg_ms=float(np.mean([k.get("nn", 0.0) for k in kms])), launches_timed=int(sum(k["samples"] for k in kms)),
             select_depth=d, expand_frac=e,
         )
-        tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
-        if os.path.exists(tp):
-            try:
-                roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+        counters, counters_file = latest_counters()
+        if counters and "k_step" in counters:
+            # dram__bytes_read.sum + dram__bytes_write.sum of k_step launches of THIS job (a mid-job tick of the default
+            # bench configuration) under `ncu --set full`; cold-cache per-launch figure, see profiles/
+            ks = counters["k_step"]
+            roofline["traffic"] = ks.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = counters_file
+            if ks.get("sims_in_captured_launch"):
+                roofline["traffic_over_algorithmic"] = ks["dram_bytes_per_launch"] / (bytes_per_sim * ks["sims_in_captured_launch"])
     flops = model.flops_per_position()
     native = type(state["ev"]).__name__ == "NativeEvaluator"
     nn_form = ("module" if args.no_fold else "GEMM-folded (FoldedNet)" if args.plain_fold else
@@ -450,7 +511,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": positions_all / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.nn_dtype, "tree_dtype": "f32 (bit-exact with the reference), u64 bitboards",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": args.nn_dtype, "tree_dtype": "f32 (bit-exact with the reference), u64 bitboards",
         "data": "synthetic", "config": workload_config(args, world),
         "sims_per_s": sims_all / dev_s_max, "nn_evals_per_s": evals_all / dev_s_max,
         "e2e": {
@@ -476,11 +537,7 @@ def run_ours(args):
         "compactions_per_step": compactions / max(1, args.steps), "engine_device_gb": engine_gb,
         "lanes": args.lanes, "nn_form": nn_form,
         "roofline": roofline,
-        "nn_roofline": {
-            "bound": "tensor", "unit": "TFLOP/s", "flops_per_eval": flops,
-            "achieved_whole_tick": rows_launched_all / world * flops / dev_s_max / 1e12,
-            "note": "reference-form network FLOPs x rows launched / whole search time on one GPU (library kernels: cuBLASLt via PyTorch)",
-        },
+        "nn_roofline": nn_roofline(args, flops, evals / max(1, ticks), roofline.get("nn_graph_avg_ms"), native),
         "host_loop": {"wait_ms_per_step": sum(r[1].report.get("host_wait_ms", 0.0) for r in runs) / max(1, args.steps),
                       "launch_ms_per_step": sum(r[1].report.get("host_launch_ms", 0.0) for r in runs) / max(1, args.steps),
                       "tail_launches_per_step": sum(r[1].report.get("tail_launches", 0) for r in runs) / max(1, args.steps),

@@ -43,6 +43,7 @@
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost a pointer check unless a profiler is attached
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -638,26 +639,19 @@ __device__ __forceinline__ uint64_t model_to_play(const Dev& D, const Game& G, P
 // misses (tag tick = e + 1) and draws a row of the batch for it.  Nobody waits for these rows; the
 // answers are moved into the claimed entries during the next tick (spec_collect) and are readable
 // from tick e + 2, when selection may arrive at the child and finds it answered.
-__device__ __forceinline__ void speculate_children(const Dev& D, const Lanes& L, const Game& G, bool pred, uint32_t epoch,
-                                                   uint32_t budget) {
-  const unsigned legal = c4::legal_mask(G.leaf.mask);
-  const int c = L.l < 7 ? L.l : 0;
-  const Pos child = c4::make_move(G.leaf, c);
-  float tq0, tq1;
-  const bool want = pred && L.l < 7 && ((legal >> c) & 1u) && c4::terminal_value(child, D.c_pen, &tq0, &tq1) == c4::NONE;
-  if (!want) return;
-  const uint64_t model = model_to_play(D, G, child);
-  const uint64_t key = pos_key(child);
+__device__ __forceinline__ bool spec_request(const Dev& D, const Game& G, Pos pos, uint32_t epoch, uint32_t budget) {
+  const uint64_t model = model_to_play(D, G, pos);
+  const uint64_t key = pos_key(pos);
   const uint32_t h = (uint32_t)splitmix64(key ^ (model * 0x9E3779B97F4A7C15ULL)) & D.cache_mask;
   EvalEntry* E = D.cache + h;
   const unsigned long long tag = *reinterpret_cast<volatile unsigned long long*>(&E->tag);
   const bool mine = (uint32_t)(tag >> 33) == D.job;
   const bool dying = (tag & TAG_DYING) != 0ull;
   const bool old = (uint32_t)tag < epoch;
-  if (mine && !(dying && old)) return;  // cached, on its way, or another position lives here (never evicted for a guess)
+  if (mine && !(dying && old)) return true;  // cached, on its way, or another position lives here (never evicted for a guess)
   Globals* g = D.g;
   const uint32_t s = atomicAdd(&g->spec_acc, 1u);
-  if (s >= budget) return;
+  if (s >= budget) return false;
   uint2 item = make_uint2(0xffffffffu, 0u);
   if (atomicCAS(&E->tag, tag, ((unsigned long long)D.job << 33) | (unsigned long long)(epoch + 1u)) == tag) {
     E->key = key;
@@ -667,12 +661,24 @@ __device__ __forceinline__ void speculate_children(const Dev& D, const Lanes& L,
     E->row = row + 1u;
     D.row_slot[row] = 0xffffffffu;
     D.row_model[row] = model;
-    D.row_mask[row] = child.mask;
-    D.row_value[row] = child.value;
-    write_planes(D, row, child);
+    D.row_mask[row] = pos.mask;
+    D.row_value[row] = pos.value;
+    write_planes(D, row, pos);
     item = make_uint2(row, h);
   }
   D.spec_list[(size_t)(epoch & 1u) * D.spec_cap + s] = item;
+  return true;
+}
+__device__ __forceinline__ void speculate_children(const Dev& D, const Lanes& L, const Game& G, bool pred, uint32_t epoch,
+                                                   uint32_t budget) {
+  const unsigned legal = c4::legal_mask(G.leaf.mask);
+  const int c = L.l < 7 ? L.l : 0;
+  const Pos child = c4::make_move(G.leaf, c);
+  float tq0, tq1;
+  // (also asking for the position a game visits first below each child — its last legal successor, since a
+  // node with one visit scores all children equal — was measured and does not shorten the job)
+  if (pred && L.l < 7 && ((legal >> c) & 1u) && c4::terminal_value(child, D.c_pen, &tq0, &tq1) == c4::NONE)
+    spec_request(D, G, child, epoch, budget);
 }
 
 // The answers of last tick's speculative rows go into the cache entries claimed for them (any time
@@ -846,9 +852,9 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
 // hold an evaluation (x, vq, vn) of their leaf G.leaf that still has to be applied: the network's
 // answer on entry, an evaluation-cache hit later on.  Returns the new state.
 __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game& G, bool running, uint32_t state,
-                                              uint32_t epoch, uint32_t spec_budget, bool pend, float x, float vq, float vn) {
+                                              uint32_t epoch, uint32_t spec_budget, uint32_t max_inline, bool pend, float x,
+                                              float vq, float vn) {
   uint32_t inl = 0;
-  const uint32_t max_inline = spec_budget ? D.max_inline_spec : D.max_inline;
   for (;;) {
     if (__any_sync(FULL, pend)) {
       const bool ok = apply_answer(D, L, G, pend, x, vq, vn);
@@ -1027,6 +1033,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
   const uint32_t epoch = D.g->tick;
   const uint32_t spec_budget = D.spec_cap ? D.g->spec_budget : 0u;
+  // simulations a game may run in this tick without a network row (terminal leaves, evaluation-cache hits)
+  const uint32_t max_inline = spec_budget ? D.max_inline_spec : D.max_inline;
   if (__any_sync(FULL, live)) {  // (no early return: every warp takes part in closing the tick below)
   const long long t1 = prof ? clock64() : 0;
   const bool waiting = live && st == ST_WAIT_NN;
@@ -1047,7 +1055,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   }
   G.cache_own = 0u;
   const long long t2 = prof ? clock64() : 0;
-  const uint32_t ns = run_games(D, L, G, live, st, epoch, spec_budget, waiting, x, vq, vn);
+  const uint32_t ns = run_games(D, L, G, live, st, epoch, spec_budget, max_inline, waiting, x, vq, vn);
   const long long t3 = prof ? clock64() : 0;
   const unsigned nwait = __popc(__ballot_sync(FULL, live && L.l == 0 && ns == ST_WAIT_NN));
   if ((threadIdx.x & 31) == 0 && nwait) atomicAdd(&D.g->wait_acc, nwait);
@@ -1341,7 +1349,7 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   // index 0 is unused; a tree holds at most n_iter expanded nodes, so n_iter + 2 always suffices
   D.cap = cfg->arena_blocks ? cfg->arena_blocks : cfg->n_mcts_iterations + 2;
   const bool use_cache = (cfg->flags & C4A0_FLAG_EVAL_CACHE) != 0;
-  D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : (use_cache ? 4 : 2);
+  D.max_inline = cfg->max_inline_sims ? cfg->max_inline_sims : (use_cache ? 3 : 2);
   D.plane_bf16 = cfg->plane_dtype == C4A0_PLANES_BF16;
   D.plane_stride = cfg->plane_stride ? cfg->plane_stride : 84;
   D.dedup = (cfg->flags & C4A0_FLAG_NO_DEDUP) ? 0u : 1u;
@@ -1359,7 +1367,9 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
     D.spec_thr = D.spec_cap / 2 < 1024u ? D.spec_cap / 2 : 1024u;
     if (const char* env = getenv("C4A0_SPEC_THR")) D.spec_thr = (uint32_t)atoi(env);  // tuning knob (results do not depend on it)
     D.max_inline_spec = 4 * D.max_inline;
+    if (const char* env = getenv("C4A0_INLINE_SPEC_MULT")) D.max_inline_spec = (uint32_t)atoi(env) * D.max_inline;
   }
+
   D.row_cap = cfg->n_slots + D.spec_cap;
   const size_t RC = D.row_cap;
   DA(D.slots, S); DA(D.path, S * PATH_STRIDE); DA(D.row_slot, RC); DA(D.row_model, RC); DA(D.rowtag, 2 * S);
@@ -1374,10 +1384,11 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   DA(e->scratch4, 4); DA(D.row_mask, RC); DA(D.row_value, RC);
   size_t CE = 0;
   if (use_cache) {
-    // default: room for 8 entries per simulation of one move of every resident game (a job evaluates a
+    // default: room for 16 entries per simulation of one move of every resident game (a job evaluates a
     // few times that many distinct positions; later answers replace earlier ones), at most a quarter of
-    // the memory that is still free
-    size_t want = cfg->eval_cache_entries ? cfg->eval_cache_entries : S * (size_t)cfg->n_mcts_iterations * 8;
+    // the memory that is still free.  Bench job: 2^28 entries = 17 GB; 2^27 costs 4.5 % of the step (a
+    // fuller table drops more speculative claims and delays more replacements), 2^29 gains another 2 %
+    size_t want = cfg->eval_cache_entries ? cfg->eval_cache_entries : S * (size_t)cfg->n_mcts_iterations * 16;
     if (want < 1024) want = cfg->eval_cache_entries ? (want < 2 ? 2 : want) : 1024;
     CE = 1;
     while (CE < want && CE < ((size_t)1 << 31)) CE <<= 1;
@@ -1786,6 +1797,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   };
   auto wall0 = std::chrono::steady_clock::now();
   int rc = 0;
+  nvtxRangePushA("c4a0_engine_run");
   // guess for the next tick's rows = this tick's rows * (1 + 2^-spec_shift): rows drift slowly
   uint32_t spec_shift = 8;
   if (const char* env = getenv("C4A0_SPEC_SHIFT")) spec_shift = (uint32_t)atoi(env) & 31u;
@@ -1810,6 +1822,10 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   auto launch_round = [&](uint32_t i, uint32_t rows) -> int {
     Lane& L = lanes[i];
     cudaEvent_t* ev = nullptr;
+    struct Range {  // NVTX: the host-side enqueue of one tick (k_step + the network behind it)
+      Range() { nvtxRangePushA("tick: k_step + network"); }
+      ~Range() { nvtxRangePop(); }
+    } range;
     if (time_kernels_every && (L.e->steps % time_kernels_every) == 0 && kev.size() < 3 * 4096) {
       size_t b = kev.size();
       for (int q = 0; q < 3; q++) {
@@ -1941,6 +1957,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
     out->nn_ms_sum = sum[1];
   }
   out->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  nvtxRangePop();
   cleanup();
   return rc;
 }

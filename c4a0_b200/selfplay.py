@@ -444,14 +444,23 @@ class SelfPlaySession:
         if isinstance(evaluator, NativeEvaluator):
             for ln in self.lanes:
                 ln.attach_native(evaluator)  # before set_requests(): it packs the planes of the initial roots
+        nvtx = torch.cuda.nvtx  # ranges for nsys / ncu --nvtx timelines; no-ops without a profiler
+        nvtx.range_push("c4a0.set_requests")
         for ln, (lo, hi) in zip(self.lanes, ranges):
             ln.engine.set_requests(gid[lo:hi], p0[lo:hi], p1[lo:hi], ln.stream.cuda_stream)
+        nvtx.range_pop()
         if host_loop == "native":
+            nvtx.range_push("c4a0.capture_graphs")
             graphs = [ln.capture(evaluator) for ln in self.lanes]
-            rep = run_engines(
-                [ln.engine for ln in self.lanes], graphs, [ln.stream.cuda_stream for ln in self.lanes], 0,
-                sample_kernels_every,
-            )
+            nvtx.range_pop()
+            nvtx.range_push("c4a0.search")
+            try:
+                rep = run_engines(
+                    [ln.engine for ln in self.lanes], graphs, [ln.stream.cuda_stream for ln in self.lanes], 0,
+                    sample_kernels_every,
+                )
+            finally:
+                nvtx.range_pop()
             info.report = rep
             info.ticks = int(rep["ticks"])
             info.device_s = rep["device_ms"] / 1e3
@@ -495,7 +504,9 @@ class SelfPlaySession:
         info.stats = _sum_stats([ln.engine.stats(ln.stream.cuda_stream) for ln in self.lanes])
         out = None
         if fetch:
+            nvtx.range_push("c4a0.fetch_results")
             parts = [ln.engine.fetch_results(0, hi - lo, ln.stream.cuda_stream) for ln, (lo, hi) in zip(self.lanes, ranges)]
+            nvtx.range_pop()
             out = GameSamples(*[
                 np.concatenate([getattr(p, f) for p in parts])
                 for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty")

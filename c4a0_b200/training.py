@@ -345,16 +345,25 @@ def self_play(model: ConnectFourNet, n_games: int, batch_size: int, n_mcts_itera
 def train_single_gen(base_dir: str, device: torch.device, parent: TrainingGen, n_self_play_games: int,
                      n_mcts_iterations: int, c_exploration: float, c_ply_penalty: float, self_play_batch_size: int,
                      training_batch_size: int, model_config: Optional[ModelConfig] = None, max_epochs: int = 100,
-                     nn_dtype: torch.dtype = torch.bfloat16, evaluator=None, log=print):
-    """One generation: self-play with the parent's model, train a copy on the samples, save."""
+                     nn_dtype: torch.dtype = torch.bfloat16, evaluator=None, log=print, report: Optional[list] = None):
+    """One generation: self-play with the parent's model, train a copy on the samples, save.  `report` (rank 0)
+    collects one dict per generation: wall seconds of self-play (all ranks, gather included), training and saving."""
+    import time
+
     rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+    world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
     gen_n = parent.gen_n + 1
     model = parent.get_model(base_dir)
     cfg = model_config or model.config
+    t0 = time.perf_counter()
+    torch.cuda.nvtx.range_push(f"c4a0.gen{gen_n}.self_play")
     games, evaluator = self_play(model, n_self_play_games, self_play_batch_size, n_mcts_iterations, c_exploration,
                                  c_ply_penalty, device, nn_dtype, evaluator)
+    torch.cuda.nvtx.range_pop()
+    t1 = time.perf_counter()
     gen = None
     if rank == 0:
+        torch.cuda.nvtx.range_push(f"c4a0.gen{gen_n}.train")
         train, val = split_arrays(games, 0.8, 1337, augment=True)
         lr = lr_for_generation(cfg.lr_schedule, gen_n)
         if log:
@@ -365,9 +374,18 @@ def train_single_gen(base_dir: str, device: torch.device, parent: TrainingGen, n
             c_ply_penalty=c_ply_penalty, self_play_batch_size=self_play_batch_size, training_batch_size=training_batch_size,
             parent=parent.created_at, val_loss=val_loss,
         )
+        t2 = time.perf_counter()
         gen.save_all(base_dir, games, best)
+        t3 = time.perf_counter()
+        torch.cuda.nvtx.range_pop()
+        n_pos = int(games._soa.n_samples.sum())
         if log:
-            log(f"gen {gen_n}: val_loss {val_loss:.5f} after {epochs} epochs")
+            log(f"gen {gen_n}: val_loss {val_loss:.5f} after {epochs} epochs | self-play {t1 - t0:.2f} s "
+                f"({n_pos / (t1 - t0):.0f} positions/s on {world} GPU(s)), training {t2 - t1:.2f} s, save {t3 - t2:.2f} s")
+        if report is not None:
+            report.append(dict(gen=gen_n, games=n_self_play_games, sims_per_move=n_mcts_iterations, gpus=world, positions=n_pos,
+                               self_play_s=t1 - t0, positions_per_s=n_pos / (t1 - t0), train_s=t2 - t1, epochs=epochs,
+                               save_s=t3 - t2, val_loss=val_loss))
     if torch.distributed.is_initialized():
         box = [gen]
         torch.distributed.broadcast_object_list(box, src=0)
@@ -379,7 +397,7 @@ def train_single_gen(base_dir: str, device: torch.device, parent: TrainingGen, n
 def training_loop(base_dir: str, device: torch.device, n_self_play_games: int, n_mcts_iterations: int,
                   c_exploration: float, c_ply_penalty: float, self_play_batch_size: int, training_batch_size: int,
                   model_config: ModelConfig, max_gens: Optional[int] = None, max_epochs: int = 100,
-                  nn_dtype: torch.dtype = torch.bfloat16, log=print) -> TrainingGen:
+                  nn_dtype: torch.dtype = torch.bfloat16, log=print, report: Optional[list] = None) -> TrainingGen:
     """training.py:242-294: generation after generation until max_gens."""
     rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
     params = dict(n_mcts_iterations=n_mcts_iterations, c_exploration=c_exploration, c_ply_penalty=c_ply_penalty,
@@ -397,7 +415,7 @@ def training_loop(base_dir: str, device: torch.device, n_self_play_games: int, n
     while True:  # like the reference (training.py:278-294): at least one generation, then check max_gens
         gen, evaluator = train_single_gen(
             base_dir, device, gen, n_self_play_games, model_config=model_config, max_epochs=max_epochs,
-            nn_dtype=nn_dtype, evaluator=evaluator, log=log if rank == 0 else None, **params,
+            nn_dtype=nn_dtype, evaluator=evaluator, log=log if rank == 0 else None, report=report, **params,
         )
         if max_gens is not None and gen.gen_n >= max_gens:
             return gen
@@ -423,6 +441,7 @@ def main(argv=None):
     ap.add_argument("--max-gens", type=int, default=None)
     ap.add_argument("--max-epochs", type=int, default=100)
     ap.add_argument("--nn-dtype", choices=["bf16", "f32"], default="bf16")
+    ap.add_argument("--report", default=None, help="write one JSON line per generation (timings) to this file")
     a = ap.parse_args(argv)
     rank, world, local_rank = D.init_from_env()
     device = torch.device("cuda", local_rank)
@@ -430,11 +449,22 @@ def main(argv=None):
     cfg = ModelConfig(n_residual_blocks=a.n_residual_blocks, conv_filter_size=a.conv_filter_size,
                       n_policy_layers=a.n_policy_layers, n_value_layers=a.n_value_layers,
                       lr_schedule=parse_lr_schedule(a.lr_schedule), l2_reg=a.l2_reg)
+    import time
+
+    report: list = []
+    t0 = time.perf_counter()
     gen = training_loop(a.base_dir, device, a.n_self_play_games, a.n_mcts_iterations, a.c_exploration, a.c_ply_penalty,
                         a.self_play_batch_size, a.training_batch_size, cfg, a.max_gens, a.max_epochs,
-                        torch.bfloat16 if a.nn_dtype == "bf16" else torch.float32)
+                        torch.bfloat16 if a.nn_dtype == "bf16" else torch.float32, report=report)
     if rank == 0:
-        print(f"finished at generation {gen.gen_n}, val_loss {gen.val_loss}")
+        print(f"finished at generation {gen.gen_n}, val_loss {gen.val_loss}, {time.perf_counter() - t0:.1f} s wall for "
+              f"{len(report)} generation(s) on {world} GPU(s)")
+        if a.report:
+            import json
+
+            with open(a.report, "w") as f:
+                for r in report:
+                    f.write(json.dumps(r) + "\n")
     if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 

@@ -66,7 +66,7 @@ typedef struct {
   float c_ply_penalty;
   uint32_t plane_dtype;        /* C4A0_PLANES_F32 | C4A0_PLANES_BF16 */
   uint32_t max_inline_sims;    /* simulations that need no network row (terminal leaf, evaluation-cache hit) a game may
-                                  run inside one step (0 = default: 2, or 4 with the evaluation cache) */
+                                  run inside one step (0 = default: 2, or 3 with the evaluation cache) */
   int32_t device;              /* CUDA device ordinal */
   uint32_t plane_stride;       /* elements between consecutive rows of planes_dev (0 = 84; a multiple of
                                   4, >= 84; elements 88.. of a row are never written; bf16 rows with a
