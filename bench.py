@@ -457,7 +457,10 @@ def run_ours(args):
     sims = sum(r[1].stats["sims"] for r in runs)
     evals = sum(r[1].stats["nn_evals"] for r in runs)
     expansions = sum(r[1].stats["expansions"] for r in runs)
-    nn_rows_launched = sum(r[1].report.get("nn_rows_launched", 0) for r in runs)
+    # rows the network kernels were launched on: bucket sizes for PyTorch graphs; the library's kernel reads the
+    # tick's own row count on the device, so it runs on exactly the rows evaluated
+    nn_rows_launched = (sum(r[1].stats["nn_evals"] for r in runs) if type(state["ev"]).__name__ == "NativeEvaluator"
+                        else sum(r[1].report.get("nn_rows_launched", 0) for r in runs))
     compactions = sum(r[1].stats.get("compactions", 0) for r in runs)
     cache_hits = sum(r[1].stats.get("cache_hits", 0) for r in runs)
     cache_inserts = sum(r[1].stats.get("cache_inserts", 0) for r in runs)
