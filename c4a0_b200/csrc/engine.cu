@@ -149,7 +149,7 @@ struct Globals {  // one instance in device memory
   uint32_t step_done;   // k_step CTA ticket
   uint32_t tail_pending;  // k_step left compaction work (and the closing of the tick) to k_tail
   int32_t error;
-  uint32_t pad;
+  uint32_t mover_claim;   // entries of `movers` already taken by a CTA of k_step (compaction work stealing)
   unsigned long long skipped_root_sims;
   unsigned long long moves;
   unsigned long long samples;
@@ -196,7 +196,7 @@ struct Dev {  // passed to kernels by value
   // global
   Globals* g;
   HostStatus* status;  // device address of the mapped host struct
-  uint32_t* movers;
+  unsigned long long* movers;      // [n_slots] epoch << 32 | slot: games whose arena half is full, in arrival order
   unsigned long long* table;       // [table_mask+1]: epoch << 32 | leader slot
   EvalEntry* cache;                // [cache_mask+1] evaluation cache, nullptr = off
   uint32_t cache_mask, job;
@@ -912,9 +912,21 @@ __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game
   return state;
 }
 
-__device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot) {
-  uint32_t i = atomicAdd(&D.g->n_movers, 1u);
-  D.movers[i] = slot;
+// Called by lane 0 of a game whose slot line is stored and whose warp has finished with the tree (the caller
+// put a __syncwarp() behind the other lanes' writes): from here on any CTA may compact the arena.  The entry
+// carries the epoch, so the list never needs clearing and a reader can tell a written entry from a stale one.
+__device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot, uint32_t epoch) {
+  __threadfence();
+  const uint32_t i = atomicAdd(&D.g->n_movers, 1u);
+  atomicExch(D.movers + i, ((unsigned long long)epoch << 32) | slot);
+}
+__device__ __forceinline__ uint32_t mover_slot(const Dev& D, uint32_t m, uint32_t epoch) {
+  unsigned long long v;
+  do {  // the entry is written right after the counter was advanced
+    v = *reinterpret_cast<volatile unsigned long long*>(D.movers + m);
+  } while ((uint32_t)(v >> 32) != epoch);
+  __threadfence();
+  return (uint32_t)v;
 }
 
 constexpr uint32_t INLINE_COMPACTIONS = 4;  // up to this many, k_step's last CTA compacts by itself
@@ -1010,6 +1022,7 @@ __device__ __forceinline__ void close_tick(const Dev& D, uint32_t epoch, uint32_
   hs->tick = epoch;      // written last: the host spins on it
   G->tick = epoch + 1u;  // open the next tick
   G->n_movers = 0u;
+  G->mover_claim = 0u;
   G->tail_pending = 0u;
 }
 
@@ -1029,9 +1042,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     memset(&G, 0, sizeof(G));
   }
   const uint32_t st = G.state;
-  if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot);  // asked for compaction after a compaction (cannot happen, kept for safety)
   const bool live = st == ST_WAIT_NN || st == ST_CONTINUE;
   const uint32_t epoch = D.g->tick;
+  if (st == ST_NEED_MOVE && L.l == 0) push_mover(D, slot, epoch);  // asked for compaction after a compaction (cannot happen, kept for safety)
   const uint32_t spec_budget = D.spec_cap ? D.g->spec_budget : 0u;
   // simulations a game may run in this tick without a network row (terminal leaves, evaluation-cache hits)
   const uint32_t max_inline = spec_budget ? D.max_inline_spec : D.max_inline;
@@ -1064,9 +1077,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     if ((threadIdx.x & 31) == 0 && nh) atomicAdd(&D.g->cache_hits, (unsigned long long)nh);
     if ((threadIdx.x & 31) == 0 && nc) atomicAdd(&D.g->cache_inserts, (unsigned long long)nc);
   }
+  __syncwarp();  // every lane's tree writes precede lane 0's publication of the game (push_mover / publish_leaf)
   if (live && L.l == 0) {
     store_game(D, G, ns);
-    if (ns == ST_NEED_MOVE) push_mover(D, slot);
+    if (ns == ST_NEED_MOVE) push_mover(D, slot, epoch);
     if (ns == ST_WAIT_NN)
       publish_leaf(D, slot, G.leaf.mask, G.leaf.value, stored_leaf_model(D, G), epoch, G.cache_own);
     if (prof) {  // cycles of this game's warp per phase (c4a0_engine_debug_phases)
@@ -1083,9 +1097,30 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   }
   }
   if (D.spec_cap) spec_collect(D, epoch);
-  // ---- the last CTA to finish closes the tick (or hands it to k_tail) ---------------------------
-  __shared__ uint32_t sh_last;
+  // ---- compactions: a CTA that is done with its own games takes arenas off the list while slower CTAs are
+  // still running, so the copies overlap the tail of the tick instead of following it -------------------
+  __shared__ uint32_t sh_last, sh_take;
   __syncthreads();
+  for (;;) {
+    if (threadIdx.x == 0) {
+      uint32_t got = 0xffffffffu;
+      uint32_t c = *reinterpret_cast<volatile uint32_t*>(&D.g->mover_claim);
+      while (c < *reinterpret_cast<volatile uint32_t*>(&D.g->n_movers)) {
+        const uint32_t prev = atomicCAS(&D.g->mover_claim, c, c + 1u);
+        if (prev == c) {
+          got = mover_slot(D, c, epoch);
+          break;
+        }
+        c = prev;
+      }
+      sh_take = got;
+    }
+    __syncthreads();
+    const uint32_t take = sh_take;
+    if (take == 0xffffffffu) break;
+    compact_one(D, take);  // ends with a CTA barrier: sh_take can be rewritten
+  }
+  // ---- the last CTA to finish closes the tick (or hands it to k_tail) ---------------------------
   if (threadIdx.x == 0) {
     __threadfence();
     sh_last = atomicAdd(&D.g->step_done, 1u) == gridDim.x - 1 ? 1u : 0u;
@@ -1094,11 +1129,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   if (sh_last) {
     __threadfence();
     const uint32_t n_movers = *reinterpret_cast<volatile uint32_t*>(&D.g->n_movers);
+    const uint32_t taken = *reinterpret_cast<volatile uint32_t*>(&D.g->mover_claim);  // final: every CTA has left the loop above
     if (threadIdx.x == 0) D.g->step_done = 0u;
-    if (n_movers <= INLINE_COMPACTIONS) {
-      for (uint32_t m = 0; m < n_movers; m++) compact_one(D, *reinterpret_cast<volatile uint32_t*>(D.movers + m));
+    if (n_movers - taken <= INLINE_COMPACTIONS) {
+      for (uint32_t m = taken; m < n_movers; m++) compact_one(D, mover_slot(D, m, epoch));
       if (threadIdx.x == 0) close_tick(D, epoch, n_movers);
-    } else if (threadIdx.x == 0) {  // a burst of compactions: one CTA per arena in k_tail
+    } else if (threadIdx.x == 0) {  // a late burst of compactions: one CTA per arena in k_tail
       D.g->tail_pending = 1u;
       __threadfence_system();
       D.status->need_tail = epoch;
@@ -1153,8 +1189,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(Dev D) {
   __shared__ uint32_t sh_last;
   if (*reinterpret_cast<volatile uint32_t*>(&D.g->tail_pending) == 0u) return;  // grid-uniform
   const uint32_t epoch = D.g->tick;
-  const uint32_t n_movers = D.g->n_movers;
-  for (uint32_t m = blockIdx.x; m < n_movers; m += gridDim.x) compact_one(D, D.movers[m]);
+  const uint32_t n_movers = D.g->n_movers, taken = D.g->mover_claim;  // k_step's CTAs compacted entries [0, taken)
+  for (uint32_t m = taken + blockIdx.x; m < n_movers; m += gridDim.x) compact_one(D, mover_slot(D, m, epoch));
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1484,6 +1520,7 @@ int c4a0_engine_set_requests(c4a0_engine* e, const uint64_t* game_id, const uint
   }
   CK(cudaMemsetAsync(D.table, 0, ((size_t)D.table_mask + 1) * sizeof(unsigned long long), s));
   CK(cudaMemsetAsync(D.rowtag, 0, 2 * (size_t)D.n_slots * sizeof(unsigned long long), s));
+  CK(cudaMemsetAsync(D.movers, 0, (size_t)D.n_slots * sizeof(unsigned long long), s));  // epochs restart at 1
   D.job = (D.job + 1u) & 0x7fffffffu;  // entries of the evaluation cache written by earlier jobs become stale
   if (D.job == 0u) {                   // (after 2^31 jobs: start over with an empty table)
     D.job = 1u;
