@@ -179,6 +179,7 @@ SIGNATURES = {
     "c4a0_engine_rows_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "c4a0_engine_rows_count_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "c4a0_engine_run": (C.c_int, [_P, C.c_uint32, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(RunReport)]),
+    "c4a0_engine_run_net": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(RunReport)]),
     "c4a0_engine_fetch_results": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "c4a0_engine_export_samples": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_int, _P, _P, _P, _P, _P]),
     "c4a0_engine_results_dev": (C.c_int, [_P] + [C.POINTER(_P)] * 6),
@@ -210,6 +211,7 @@ SIGNATURES = {
     "c4a0_net_bind_outputs": (C.c_int, [_P, _P, _P, _P]),
     "c4a0_net_bind_row_count": (C.c_int, [_P, _P, _P]),
     "c4a0_net_forward": (C.c_int, [_P, C.c_uint32, _P]),
+    "c4a0_net_forward_ex": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32]),
     "c4a0_net_debug_trace": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, C.c_size_t]),
     "c4a0_net_forward_timed": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_float)]),
 }

@@ -56,6 +56,7 @@
 #include "c4_math.cuh"
 #include "c4_rng.cuh"
 #include "c4_rules.cuh"
+#include "../../include/c4a0_net.h"
 #include "common.cuh"
 
 namespace {
@@ -1030,6 +1031,11 @@ __device__ __forceinline__ void close_tick(const Dev& D, uint32_t epoch, uint32_
 // K_step: the tick of every game.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 registers: 16,384 games in one wave
+  // Launched programmatically dependent by the native loop (c4a0_engine_run_net): the CTAs may already be
+  // resident while the network kernel before them drains; nothing is read before that kernel has completed.
+  // (Both instructions are no-ops in an ordinary launch.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const Lanes L = make_lanes();
   const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const bool valid = slot < D.n_slots;
@@ -1334,10 +1340,23 @@ int launch_post(c4a0_engine* e, cudaStream_t s) {
 // closes the tick by itself unless a burst of arenas needs compaction; with_tail enqueues k_tail
 // unconditionally (it returns at once when there is nothing to do) so that callers that cannot look
 // at the status word in between (engine_step(), CUDA-graph capture) always get a closed tick.
-int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev, bool with_tail) {
+int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev, bool with_tail, bool pdl = false) {
   const Dev& D = e->D;
   if (ev) CK(cudaEventRecord(ev[0], s));
-  k_step<<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
+  if (pdl) {  // programmatic dependent launch behind the network kernel (see k_step)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks_for((size_t)D.n_slots * 8, STEP_THREADS));
+    cfg.blockDim = dim3(STEP_THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_step, D));
+  } else {
+    k_step<<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
+  }
   if (ev) CK(cudaEventRecord(ev[1], s));
   if (ev) CK(cudaEventRecord(ev[2], s));
   if (with_tail) {
@@ -1794,12 +1813,20 @@ int c4a0_engine_dump_tree(c4a0_engine* e, uint32_t slot, uint32_t* buf, size_t c
 // With two engines (two half-batches on two streams) one engine's tree tick and host round trip
 // hide under the other engine's network.
 // ------------------------------------------------------------------------------------------------
-int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_nn_graph* const* graphs,
-                    const uint32_t* n_graphs, void* const* streams, uint64_t max_ticks,
-                    uint32_t time_kernels_every, c4a0_run_report* out) {
-  if (!engines || !graphs || !n_graphs || !streams || !out || n_engines == 0 || n_engines > 8)
+}  // extern "C"
+
+namespace {
+// graphs != nullptr: the evaluator of engine i is graphs[i][0..n_graphs[i]) (CUDA graphs, one per batch-size bucket);
+// nets != nullptr: it is nets[i], the library's own network kernel, launched directly — programmatically dependent
+// on the tree tick before it, and the next tick on it — unless C4A0_PDL=0.
+int run_loop(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_nn_graph* const* graphs, const uint32_t* n_graphs,
+             c4a0_net* const* nets, void* const* streams, uint64_t max_ticks, uint32_t time_kernels_every,
+             c4a0_run_report* out) {
+  if (!engines || (!graphs && !nets) || (graphs && !n_graphs) || !streams || !out || n_engines == 0 || n_engines > 8)
     return fail(C4A0_E_INVALID, "bad argument");
   memset(out, 0, sizeof(*out));
+  bool pdl = nets != nullptr;
+  if (const char* env = getenv("C4A0_PDL")) pdl = pdl && env[0] != '0';
   struct Lane {
     c4a0_engine* e;
     cudaStream_t s;
@@ -1814,13 +1841,17 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   for (uint32_t i = 0; i < n_engines; i++) {
     c4a0_engine* e = engines[i];
     if (!e || !e->have_requests) return fail(C4A0_E_INVALID, "engine %u has no requests", i);
-    if (n_graphs[i] == 0 || !graphs[i]) return fail(C4A0_E_INVALID, "engine %u has no network graphs", i);
-    for (uint32_t k = 0; k < n_graphs[i]; k++) {
-      if (!graphs[i][k].graph_exec) return fail(C4A0_E_INVALID, "null graph_exec");
-      if (k && graphs[i][k].rows <= graphs[i][k - 1].rows) return fail(C4A0_E_INVALID, "network graphs must be sorted by rows");
+    if (nets) {
+      if (!nets[i]) return fail(C4A0_E_INVALID, "engine %u has no network", i);
+    } else {
+      if (n_graphs[i] == 0 || !graphs[i]) return fail(C4A0_E_INVALID, "engine %u has no network graphs", i);
+      for (uint32_t k = 0; k < n_graphs[i]; k++) {
+        if (!graphs[i][k].graph_exec) return fail(C4A0_E_INVALID, "null graph_exec");
+        if (k && graphs[i][k].rows <= graphs[i][k - 1].rows) return fail(C4A0_E_INVALID, "network graphs must be sorted by rows");
+      }
+      if (graphs[i][n_graphs[i] - 1].rows < e->D.row_cap)
+        return fail(C4A0_E_INVALID, "the largest network graph must cover c4a0_engine_io_rows() rows");
     }
-    if (graphs[i][n_graphs[i] - 1].rows < e->D.row_cap)
-      return fail(C4A0_E_INVALID, "the largest network graph must cover c4a0_engine_io_rows() rows");
     lanes[i] = Lane{e, (cudaStream_t)streams[i], e->h_status->tick, 0u, 0u, e->n_req == 0, nullptr, nullptr};
     CK(cudaEventCreate(&lanes[i].t0));
     CK(cudaEventCreate(&lanes[i].t1));
@@ -1841,6 +1872,15 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   // the network on rows [0, >= rows): the smallest captured graph that covers them
   auto launch_nn = [&](uint32_t i, uint32_t rows, uint32_t* covered) -> int {
     Lane& L = lanes[i];
+    if (nets) {  // one kernel whatever the batch: it reads the tick's row count on the device
+      int r = c4a0_net_forward_ex(nets[i], L.e->D.row_cap, L.s, pdl ? C4A0_NET_LAUNCH_PDL : 0u);
+      if (r) return r;
+      out->nn_launches++;
+      out->bucket_launches[0]++;
+      out->nn_rows_launched += L.e->D.row_cap;
+      if (covered) *covered = L.e->D.row_cap;
+      return 0;
+    }
     const c4a0_nn_graph* g = graphs[i];
     uint32_t k = 0;
     while (k + 1 < n_graphs[i] && g[k].rows < rows) k++;
@@ -1873,7 +1913,7 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
       ev = &kev[b];
       CK(cudaEventRecord(ev[0], L.s));
     }
-    int r = launch_tick(L.e, L.s, nullptr, false);
+    int r = launch_tick(L.e, L.s, nullptr, false, pdl && !ev);
     if (r) return r;
     if (ev) CK(cudaEventRecord(ev[1], L.s));
     // ... or, while the batch is growing, by as much again as it grew last time
@@ -1997,6 +2037,22 @@ int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_
   nvtxRangePop();
   cleanup();
   return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int c4a0_engine_run(c4a0_engine* const* engines, uint32_t n_engines, const c4a0_nn_graph* const* graphs,
+                    const uint32_t* n_graphs, void* const* streams, uint64_t max_ticks,
+                    uint32_t time_kernels_every, c4a0_run_report* out) {
+  if (!graphs) return fail(C4A0_E_INVALID, "bad argument");
+  return run_loop(engines, n_engines, graphs, n_graphs, nullptr, streams, max_ticks, time_kernels_every, out);
+}
+
+int c4a0_engine_run_net(c4a0_engine* const* engines, uint32_t n_engines, c4a0_net* const* nets, void* const* streams,
+                        uint64_t max_ticks, uint32_t time_kernels_every, c4a0_run_report* out) {
+  if (!nets) return fail(C4A0_E_INVALID, "bad argument");
+  return run_loop(engines, n_engines, nullptr, nullptr, nets, streams, max_ticks, time_kernels_every, out);
 }
 
 }  // extern "C"

@@ -317,15 +317,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NET2_THREADS, 1) k_n
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES2 * STAGE2_BYTES + 8u * (2 * STAGES2 + 4));
 
-  uint32_t rows = A.rows_fixed;
-  if (A.rows_a != nullptr) {
-    const uint32_t a = *reinterpret_cast<const volatile uint32_t*>(A.rows_a);
-    const uint32_t b = *reinterpret_cast<const volatile uint32_t*>(A.rows_b);
-    rows = a > b ? a : b;
-  }
-  if (rows > A.rows_cap) rows = A.rows_cap;
-  const uint32_t Mt2 = (rows + 2 * BM - 1) / (2 * BM);  // 256-row blocks: one per CTA pair and column tile
-
+  // ---- prologue that needs nothing from the kernel before this one in the stream: it runs under that
+  // kernel's tail when this launch is programmatically dependent (c4a0_net_forward_ex, C4A0_NET_LAUNCH_PDL)
   if (threadIdx.x < A.n_layers) {
     const NetLayer2* L = &A.prog.layer[threadIdx.x];
     sh_kb[threadIdx.x] = L->k_blocks;
@@ -346,7 +339,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NET2_THREADS, 1) k_n
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 1) {  // the MMA warp of each CTA allocates the pair's tensor memory
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
   __syncthreads();
+  cluster_sync();  // both CTAs' barriers are initialised before anything can arrive on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // ---- from here on the kernel reads what its predecessor wrote (the row count, the planes)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint32_t rows = A.rows_fixed;
+  if (A.rows_a != nullptr) {
+    const uint32_t a = *reinterpret_cast<const volatile uint32_t*>(A.rows_a);
+    const uint32_t b = *reinterpret_cast<const volatile uint32_t*>(A.rows_b);
+    rows = a > b ? a : b;
+  }
+  if (rows > A.rows_cap) rows = A.rows_cap;
+  const uint32_t Mt2 = (rows + 2 * BM - 1) / (2 * BM);  // 256-row blocks: one per CTA pair and column tile
   if (threadIdx.x == 0) {
     // column-tile width of this launch: the variant that moves the fewest bytes through the busiest SM
     uint32_t best = 0;
@@ -374,15 +387,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NET2_THREADS, 1) k_n
     sh_bn[threadIdx.x] = hidden ? variant_bn(variant) : HEAD_N;
     sh_nt[threadIdx.x] = hidden ? sh_np[threadIdx.x] / variant_bn(variant) : 1u;
   }
-  if (warp == 1) {  // the MMA warp of each CTA allocates the pair's tensor memory
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
   __syncthreads();
-  cluster_sync();  // both CTAs' barriers are initialised before anything can arrive on them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
 
   uint32_t total = 0;
   for (uint32_t l = 0; l < A.n_layers; l++) total += Mt2 * sh_nt[l];
@@ -1104,14 +1109,32 @@ int c4a0_net_bind_row_count(c4a0_net* n, const uint32_t* a, const uint32_t* b) {
   return 0;
 }
 
-int c4a0_net_forward(c4a0_net* n, uint32_t rows, void* stream) {
+int c4a0_net_forward(c4a0_net* n, uint32_t rows, void* stream) { return c4a0_net_forward_ex(n, rows, stream, 0u); }
+
+int c4a0_net_forward_ex(c4a0_net* n, uint32_t rows, void* stream, uint32_t flags) {
   if (!n) return fail(C4A0_E_INVALID, "null net");
   if (!n->args.logits) return fail(C4A0_E_INVALID, "bind_outputs() must precede forward()");
   if (rows > n->spec.max_rows) return fail(C4A0_E_INVALID, "%u rows exceed max_rows=%u", rows, n->spec.max_rows);
   if (*n->h_error) return fail(C4A0_E_ENGINE, "the network kernel reported a stuck wait (code %d)", *n->h_error);
   if (n->pair) {
     n->args2.rows_fixed = rows;
-    k_net2<<<n->grid, NET2_THREADS, SMEM2_BYTES, (cudaStream_t)stream>>>(n->args2);  // clusters of two (__cluster_dims__)
+    if (flags & C4A0_NET_LAUNCH_PDL) {
+      // programmatic dependent launch: the CTAs may become resident, and run their prologue, while the kernel
+      // before this one in the stream is still draining; griddepcontrol.wait in the kernel orders the rest
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(n->grid);
+      cfg.blockDim = dim3(NET2_THREADS);
+      cfg.dynamicSmemBytes = SMEM2_BYTES;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, k_net2, n->args2));
+    } else {
+      k_net2<<<n->grid, NET2_THREADS, SMEM2_BYTES, (cudaStream_t)stream>>>(n->args2);  // clusters of two (__cluster_dims__)
+    }
   } else {
     n->args.rows_fixed = rows;
     k_net<<<n->grid, NET_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(n->args);

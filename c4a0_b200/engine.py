@@ -201,6 +201,19 @@ def run_engines(engines: Sequence["Engine"], graphs: Sequence[Sequence[Tuple[int
     return rep.as_dict()
 
 
+def run_engines_net(engines: Sequence["Engine"], nets: Sequence[int], streams: Sequence[int], max_ticks: int = 0,
+                    time_kernels_every: int = 0) -> dict:
+    """c4a0_engine_run_net(): nets[i] = c4a0_net handle (as int) evaluating engine i; both kernels of a tick are
+    launched directly by the C++ loop, programmatically dependent on each other."""
+    n = len(engines)
+    handles = (C.c_void_p * n)(*[e._h for e in engines])
+    nh = (C.c_void_p * n)(*nets)
+    st = (C.c_void_p * n)(*streams)
+    rep = L.RunReport()
+    L.check(L.lib().c4a0_engine_run_net(handles, n, nh, st, max_ticks, time_kernels_every, C.byref(rep)))
+    return rep.as_dict()
+
+
 # ------------------------------------------------------------------------------------------------
 # stand-alone batch kernels (host arrays in, host arrays out)
 # ------------------------------------------------------------------------------------------------

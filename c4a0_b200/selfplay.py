@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import Engine, GameSamples, run_engines
+from .engine import Engine, GameSamples, run_engines, run_engines_net
 
 # process-wide defaults, overridable by tools (bench.py turns kernel sampling on)
 DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, "n_lanes": 1, "dedup": True,
@@ -450,15 +450,21 @@ class SelfPlaySession:
             ln.engine.set_requests(gid[lo:hi], p0[lo:hi], p1[lo:hi], ln.stream.cuda_stream)
         nvtx.range_pop()
         if host_loop == "native":
-            nvtx.range_push("c4a0.capture_graphs")
-            graphs = [ln.capture(evaluator) for ln in self.lanes]
-            nvtx.range_pop()
+            native = isinstance(evaluator, NativeEvaluator) and all(ln.net is not None and ln.net.ev is evaluator for ln in self.lanes)
+            if not native:
+                nvtx.range_push("c4a0.capture_graphs")
+                graphs = [ln.capture(evaluator) for ln in self.lanes]
+                nvtx.range_pop()
             nvtx.range_push("c4a0.search")
             try:
-                rep = run_engines(
-                    [ln.engine for ln in self.lanes], graphs, [ln.stream.cuda_stream for ln in self.lanes], 0,
-                    sample_kernels_every,
-                )
+                if native:  # the library's network kernel: launched by the C++ loop itself, no graphs
+                    rep = run_engines_net([ln.engine for ln in self.lanes], [ln.net._h.value for ln in self.lanes],
+                                          [ln.stream.cuda_stream for ln in self.lanes], 0, sample_kernels_every)
+                else:
+                    rep = run_engines(
+                        [ln.engine for ln in self.lanes], graphs, [ln.stream.cuda_stream for ln in self.lanes], 0,
+                        sample_kernels_every,
+                    )
             finally:
                 nvtx.range_pop()
             info.report = rep

@@ -240,6 +240,16 @@ int c4a0_engine_run(c4a0_engine *const *engines, uint32_t n_engines,
                     void *const *streams, uint64_t max_ticks, uint32_t time_kernels_every,
                     c4a0_run_report *out);
 
+/* The same loop with the library's own network kernel as the evaluator (include/c4a0_net.h): nets[i] must read
+ * engine i's planes (c4a0_engine_bind_io on c4a0_net_buffer 0), write its logits / q buffers (c4a0_net_bind_outputs)
+ * and be bound to its row counters (c4a0_net_bind_row_count(c4a0_engine_rows_count_dev)).  No buckets, no row
+ * guess; the two kernels of a tick are launched programmatically dependent on each other, so each one's CTAs are
+ * resident and set up while the other drains (set C4A0_PDL=0 in the environment for ordinary launches). */
+struct c4a0_net;
+int c4a0_engine_run_net(c4a0_engine *const *engines, uint32_t n_engines, struct c4a0_net *const *nets,
+                        void *const *streams, uint64_t max_ticks, uint32_t time_kernels_every,
+                        c4a0_run_report *out);
+
 /* Finished games [first, first+n) in request order: n_samples[i] (0 = not finished) and
  * [n][43] sample fields (types.rs:104-110).  Any output pointer may be NULL. */
 int c4a0_engine_fetch_results(c4a0_engine *e, uint32_t first, uint32_t n, uint32_t *n_samples,

@@ -89,6 +89,11 @@ int c4a0_net_bind_row_count(c4a0_net* net, const uint32_t* a_dev, const uint32_t
 /* Enqueue one forward pass over rows [0, rows) (or the bound device-side count).  One kernel launch;
  * safe to capture into a CUDA graph. */
 int c4a0_net_forward(c4a0_net* net, uint32_t rows, void* stream);
+/* forward() with launch flags.  C4A0_NET_LAUNCH_PDL: programmatic dependent launch — the kernel's CTAs may become
+ * resident and set up shared / tensor memory while the preceding kernel of `stream` is still draining; everything
+ * that reads memory waits (griddepcontrol.wait) until that kernel has completed.  Used by c4a0_engine_run_net. */
+#define C4A0_NET_LAUNCH_PDL 1u
+int c4a0_net_forward_ex(c4a0_net* net, uint32_t rows, void* stream, uint32_t flags);
 
 /* Diagnostics: one forward pass in which CTA `cta` logs (SM cycle counter << 8 | tag) events of its three
  * roles into out[3][4096] (producer, MMA issuer, first epilogue thread; tags: 1 role start, 2 tile start,
