@@ -38,6 +38,8 @@ class Config(C.Structure):
         ("arena_blocks", C.c_uint32),
         ("eval_cache_entries", C.c_uint32),
         ("spec_rows", C.c_uint32),
+        ("dirichlet_alpha", C.c_float),
+        ("dirichlet_epsilon", C.c_float),
     ]
 
 
@@ -235,7 +237,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)  # AttributeError here == the library does not export the header
         fn.restype = res
         fn.argtypes = args
-    if L.c4a0_abi_version() != 2:
+    if L.c4a0_abi_version() != 3:
         raise ImportError("libc4a0_engine.so ABI version mismatch; rebuild with c4a0_b200/build.py")
     _lib = L
     return L

@@ -181,6 +181,7 @@ struct HostStatus {  // mapped pinned host memory, written by k_tail at the end 
 struct Dev {  // passed to kernels by value
   uint32_t n_slots, n_iter, cap, max_inline, plane_bf16, plane_stride, dedup, table_mask;
   float c_expl, c_pen;
+  float dir_alpha, dir_eps;  // Dirichlet noise on root priors; dir_eps == 0: off (the reference's behaviour)
   Slot* slots;
   uint32_t* path;   // [n_slots][PATH_STRIDE]: (block << 3 | column) per level of the selected path
   Block* blocks;    // [n_slots][2][cap]
@@ -537,10 +538,61 @@ __device__ __forceinline__ Pos select_leaf(const Dev& D, const Lanes& L, Game& G
   return pos;
 }
 
+// ---- Dirichlet noise on the root's priors (c4a0_config.dirichlet_alpha / _epsilon) -----------------------
+// Not in the reference (mcts.rs:114-132 keeps the masked softmax as it is): off unless configured.  eta ~ Dir(alpha)
+// over the legal moves = normalised Gamma(alpha, 1) draws; lane c draws for column c from a counter-based stream
+// keyed by (game_id, moves played, column), so the noise of a game does not depend on scheduling, slots or batches.
+// Gamma: Marsaglia-Tsang squeeze (alpha < 1: Gamma(alpha + 1) * U^(1/alpha)), normals by the polar method; the
+// f32 arithmetic is the kernel's usual exact kind (no contraction, c4_logf / c4_expf), so it is reproducible.
+struct NoiseRng {
+  uint64_t s;
+  __device__ __forceinline__ uint32_t next() {
+    s += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return (uint32_t)((z ^ (z >> 31)) >> 32);
+  }
+  __device__ __forceinline__ float uniform() { return ((float)(next() >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // in (0, 1)
+};
+__device__ __noinline__ float gamma_draw(float alpha, uint64_t seed) {
+  NoiseRng r{seed};
+  const float a = alpha < 1.0f ? alpha + 1.0f : alpha;
+  const float d = a - 1.0f / 3.0f, c = 1.0f / sqrtf(9.0f * d);
+  float g = d;  // (the mean, should 64 proposals all be rejected: probability < 1e-30)
+  for (int it = 0; it < 64; it++) {
+    const float u = 2.0f * r.uniform() - 1.0f, v = 2.0f * r.uniform() - 1.0f;
+    const float s2 = u * u + v * v;
+    if (s2 >= 1.0f || s2 == 0.0f) continue;
+    const float x = u * sqrtf(-2.0f * c4::c4_logf(s2) / s2);
+    const float t = 1.0f + c * x;
+    if (t <= 0.0f) continue;
+    const float v3 = t * t * t;
+    if (c4::c4_logf(r.uniform()) < 0.5f * x * x + d - d * v3 + d * c4::c4_logf(v3)) {
+      g = d * v3;
+      break;
+    }
+  }
+  if (alpha < 1.0f) g = g * c4::c4_expf(c4::c4_logf(r.uniform()) / alpha);
+  return g;
+}
+// Called by the whole warp; `pred` marks the games whose root priors are being set, `p` is this lane's prior.
+// (scalars only: a reference to the kernel's parameter struct would force a local copy of it)
+__device__ __noinline__ float root_noise(float alpha, float eps, int l, bool pred, unsigned legal, uint64_t game_id,
+                                         uint32_t n_moves, float p) {
+  const bool act = pred && l < 7 && ((legal >> l) & 1u);
+  float g = 0.0f;
+  if (act) g = gamma_draw(alpha, splitmix64(game_id ^ 0xD1B54A32D192ED03ULL) ^ (((uint64_t)n_moves << 8 | (uint64_t)l) * 0xA24BAED4963EE407ULL));
+  __syncwarp();
+  const float sum = fold7(g);
+  return (act && sum > 0.0f) ? (1.0f - eps) * p + eps * (g / sum) : p;
+}
+
 // mask_policy + softmax + expand_leaf + backup for a leaf whose evaluation (x = this lane's logit,
 // vq, vn) has arrived from the network or from the evaluation cache (c4r.rs:272-286,
 // mcts.rs:416-434, 114-132, 137-155).  Returns false for a game whose arena overflowed (engine bug;
 // reported).
+template <bool NOISE>
 __device__ __forceinline__ bool apply_answer(const Dev& D, const Lanes& L, Game& G, bool pred, float xin, float vq,
                                              float vn) {
   const unsigned legal = c4::legal_mask(G.leaf.mask);
@@ -549,7 +601,9 @@ __device__ __forceinline__ bool apply_answer(const Dev& D, const Lanes& L, Game&
   const float mx = gmax8(x);
   const float e = ok ? c4::c4_expf(x - mx) : 0.0f;
   const float s = fold7(e);
-  const float p = ok ? div_exact(e, s) : 0.0f;
+  float p = ok ? div_exact(e, s) : 0.0f;
+  if (NOISE && __any_sync(FULL, pred && G.len == 0u))  // this leaf is the root of its game's search
+    p = root_noise(D.dir_alpha, D.dir_eps, L.l, pred && G.len == 0u, legal, (pred && G.len == 0u) ? D.game_id[G.req] : 0ull, G.n_moves, p);
   const uint32_t nb = G.n_alloc;
   const bool fits = nb < D.cap;
   if (pred && fits) {
@@ -716,6 +770,7 @@ enum MoveResult : int { MV_CONTINUE = 0, MV_IDLE = 1, MV_COMPACT = 2 };
 // The root reached n_iterations (self_play.rs:283-313): sample and play a move (mcts.rs:187-222) or,
 // when that ends the game, emit its samples (mcts.rs:271-313) and seat the next request.  Executed
 // by the whole warp; `pred` marks the games that actually move.
+template <bool NOISE>
 __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, bool pred) {
   Globals* g = D.g;
   const int l = L.l;
@@ -766,7 +821,8 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
   if (!bad)
     while (scale * max_rand + 0.0f >= total) scale = c4::bits_f32(c4::f32_bits(scale) - 1u);
   uint32_t key[8];
-  c4::seed_to_key(c4::move_seed(pred ? D.game_id[G.req] : 0ull, (int)G.n_moves), key);
+  const uint64_t gid = pred ? D.game_id[G.req] : 0ull;
+  c4::seed_to_key(c4::move_seed(gid, (int)G.n_moves), key);
   const uint32_t u32 = c4::chacha12_first_word(key);
   const float x = (c4::bits_f32((u32 >> 9) | 0x3f800000u) - 1.0f) * scale + 0.0f;
   const int col = __popc(gballot(L, l < 6 && cum <= x));  // partition_point(|c| c <= x) over 6 entries
@@ -844,6 +900,14 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
       if (G.n_alloc + need > D.cap) result = MV_COMPACT;
     }
   }
+  // a reused subtree becomes the root of the next search: its priors get their noise now (see root_noise)
+  const bool renoise = go && !fin && child != 0u;
+  if (NOISE && __any_sync(FULL, renoise)) {
+    ChildStat* R = &G.arena[renoise ? child : 0u].rec[l];
+    const float p0n = renoise ? R->P : 0.0f;
+    const float p1n = root_noise(D.dir_alpha, D.dir_eps, l, renoise, c4::legal_mask(np.mask), gid, G.n_moves, p0n);
+    if (renoise && l < 7) R->P = p1n;
+  }
   return result;
 }
 
@@ -852,13 +916,14 @@ __device__ __forceinline__ int play_move(const Dev& D, const Lanes& L, Game& G, 
 // (NEED_MOVE) or holds no game (IDLE).  `running` marks the lanes of live games, `pend` those that
 // hold an evaluation (x, vq, vn) of their leaf G.leaf that still has to be applied: the network's
 // answer on entry, an evaluation-cache hit later on.  Returns the new state.
+template <bool NOISE>
 __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game& G, bool running, uint32_t state,
                                               uint32_t epoch, uint32_t spec_budget, uint32_t max_inline, bool pend, float x,
                                               float vq, float vn) {
   uint32_t inl = 0;
   for (;;) {
     if (__any_sync(FULL, pend)) {
-      const bool ok = apply_answer(D, L, G, pend, x, vq, vn);
+      const bool ok = apply_answer<NOISE>(D, L, G, pend, x, vq, vn);
       if (!ok) {
         if (L.l == 0) D.g->error = C4A0_E_ENGINE;
         running = false;
@@ -868,7 +933,7 @@ __device__ __forceinline__ uint32_t run_games(const Dev& D, const Lanes& L, Game
     }
     const bool need_move = running && G.rootN >= D.n_iter;  // self_play.rs:283: after every simulation
     if (__any_sync(FULL, need_move)) {
-      const int r = play_move(D, L, G, need_move);
+      const int r = play_move<NOISE>(D, L, G, need_move);
       if (need_move && r == MV_IDLE) {
         running = false;
         state = ST_IDLE;
@@ -1030,6 +1095,9 @@ __device__ __forceinline__ void close_tick(const Dev& D, uint32_t epoch, uint32_
 // ------------------------------------------------------------------------------------------------
 // K_step: the tick of every game.
 // ------------------------------------------------------------------------------------------------
+// NOISE = Dirichlet noise on root priors (c4a0_config.dirichlet_*): its own instantiation, so that the default
+// kernel carries none of it (the extra live values cost 5 % of the tick through spills when merely compiled in)
+template <bool NOISE>
 __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 registers: 16,384 games in one wave
   // Launched programmatically dependent by the native loop (c4a0_engine_run_net): the CTAs may already be
   // resident while the network kernel before them drains; nothing is read before that kernel has completed.
@@ -1074,7 +1142,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
   }
   G.cache_own = 0u;
   const long long t2 = prof ? clock64() : 0;
-  const uint32_t ns = run_games(D, L, G, live, st, epoch, spec_budget, max_inline, waiting, x, vq, vn);
+  const uint32_t ns = run_games<NOISE>(D, L, G, live, st, epoch, spec_budget, max_inline, waiting, x, vq, vn);
   const long long t3 = prof ? clock64() : 0;
   const unsigned nwait = __popc(__ballot_sync(FULL, live && L.l == 0 && ns == ST_WAIT_NN));
   if ((threadIdx.x & 31) == 0 && nwait) atomicAdd(&D.g->wait_acc, nwait);
@@ -1353,9 +1421,11 @@ int launch_tick(c4a0_engine* e, cudaStream_t s, cudaEvent_t* ev, bool with_tail,
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, k_step, D));
+    CK(D.dir_eps > 0.0f ? cudaLaunchKernelEx(&cfg, k_step<true>, D) : cudaLaunchKernelEx(&cfg, k_step<false>, D));
+  } else if (D.dir_eps > 0.0f) {
+    k_step<true><<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
   } else {
-    k_step<<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
+    k_step<false><<<blocks_for((size_t)D.n_slots * 8, STEP_THREADS), STEP_THREADS, 0, s>>>(D);
   }
   if (ev) CK(cudaEventRecord(ev[1], s));
   if (ev) CK(cudaEventRecord(ev[2], s));
@@ -1392,6 +1462,8 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   if (cfg->arena_blocks >= (1u << 29)) return fail(C4A0_E_INVALID, "arena_blocks too large");
   if ((cfg->flags & C4A0_FLAG_SPECULATE) && !(cfg->flags & C4A0_FLAG_EVAL_CACHE))
     return fail(C4A0_E_INVALID, "C4A0_FLAG_SPECULATE needs C4A0_FLAG_EVAL_CACHE");
+  if (!(cfg->dirichlet_alpha >= 0.0f) || !(cfg->dirichlet_epsilon >= 0.0f) || cfg->dirichlet_epsilon > 1.0f)
+    return fail(C4A0_E_INVALID, "dirichlet_alpha must be >= 0 and dirichlet_epsilon in [0, 1]");
   int r = c4host::no_gpu_error();
   if (r) return r;
   CK(cudaSetDevice(cfg->device));
@@ -1410,6 +1482,8 @@ int c4a0_engine_create(const c4a0_config* cfg, c4a0_engine** out) {
   D.dedup = (cfg->flags & C4A0_FLAG_NO_DEDUP) ? 0u : 1u;
   D.c_expl = cfg->c_exploration;
   D.c_pen = cfg->c_ply_penalty;
+  D.dir_alpha = cfg->dirichlet_alpha;
+  D.dir_eps = cfg->dirichlet_alpha > 0.0f ? cfg->dirichlet_epsilon : 0.0f;
   size_t S = cfg->n_slots, R = cfg->max_requests;
   size_t T = 1;
   while (T < 2 * S) T <<= 1;

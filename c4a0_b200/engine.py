@@ -45,12 +45,14 @@ class Engine:
         arena_blocks: int = 0,
         eval_cache_entries: int = 0,
         spec_rows: int = 0,
+        dirichlet_alpha: float = 0.0,
+        dirichlet_epsilon: float = 0.0,
     ):
         self._lib = L.lib()
         self._h = C.c_void_p()
         self.cfg = L.Config(
             n_slots, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, max_inline_sims, device,
-            plane_stride, flags, arena_blocks, eval_cache_entries, spec_rows,
+            plane_stride, flags, arena_blocks, eval_cache_entries, spec_rows, dirichlet_alpha, dirichlet_epsilon,
         )
         L.check(self._lib.c4a0_engine_create(C.byref(self.cfg), C.byref(self._h)))
         self.n_slots = n_slots

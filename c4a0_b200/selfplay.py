@@ -44,7 +44,9 @@ DEFAULTS = {"host_loop": "native", "poll_every": 32, "sample_kernels_every": 0, 
             "speculate": True, "spec_rows": 0,
             # False: play_games leaves the samples in the engine's device store (multi-GPU ranks whose samples
             # travel to rank 0 over NCCL, trainers that read export_tensors()) and returns an empty result
-            "fetch": True}
+            "fetch": True,
+            # (alpha, epsilon) of Dirichlet noise on root priors, or None: off, like the reference (c4a0_config)
+            "dirichlet": None}
 
 def _buckets():
     """Network batch sizes that get their own CUDA graph: fine steps (a tick launches the smallest
@@ -223,13 +225,13 @@ class _Lane:
     """One engine + its NN I/O tensors + its stream."""
 
     def __init__(self, n_slots, max_requests, n_iter, c_expl, c_pen, plane_dtype, device, max_inline, stride, flags,
-                 arena_blocks, offset=0, eval_cache_entries=0, spec_rows=0):
+                 arena_blocks, offset=0, eval_cache_entries=0, spec_rows=0, dirichlet=None):
         self.n_slots = n_slots
         self.offset = offset
         self.engine = Engine(
             n_slots, max(1, max_requests), n_iter, c_expl, c_pen,
             L.PLANES_BF16 if plane_dtype == torch.bfloat16 else L.PLANES_F32, max_inline, device.index, stride, flags,
-            arena_blocks, eval_cache_entries, spec_rows,
+            arena_blocks, eval_cache_entries, spec_rows, *(dirichlet or (0.0, 0.0)),
         )
         self.io_rows = R = self.engine.io_rows  # n_slots, plus the speculative rows if that is on
         self.planes = torch.zeros(R, stride, dtype=plane_dtype, device=device)
@@ -327,6 +329,7 @@ class SelfPlaySession:
         eval_cache_entries: int = 0,
         speculate: bool = False,
         spec_rows: int = 0,
+        dirichlet: Optional[Tuple[float, float]] = None,
     ):
         """`eval_cache=True` lets the engine answer repeated (position, model) leaves of one play() call from
         a device table instead of the network; only for evaluators that are pure functions of the position."""
@@ -365,7 +368,8 @@ class SelfPlaySession:
         per = [(n_slots + i) // n_lanes for i in range(n_lanes)][::-1]
         self.lanes = [
             _Lane(s, max_requests, n_mcts_iterations, c_exploration, c_ply_penalty, plane_dtype, self.device,
-                  max_inline_sims, plane_stride, flags, arena_blocks, plane_offset, eval_cache_entries, spec_rows)
+                  max_inline_sims, plane_stride, flags, arena_blocks, plane_offset, eval_cache_entries, spec_rows,
+                  dirichlet if dirichlet is not None else DEFAULTS["dirichlet"])
             for s in per if s > 0
         ]
 

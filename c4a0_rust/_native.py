@@ -323,7 +323,7 @@ def _session(n_slots, n_req, n_iter, c_expl, c_pen, dtype, device, stride, n_lan
     from c4a0_b200 import selfplay
     from c4a0_b200.selfplay import SelfPlaySession
 
-    knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks", "eval_cache_entries", "speculate", "spec_rows")))
+    knobs = tuple(sorted((k, v) for k, v in selfplay.DEFAULTS.items() if k in ("n_lanes", "dedup", "max_inline_sims", "arena_blocks", "eval_cache_entries", "speculate", "spec_rows", "dirichlet")))
     key = (n_slots, n_iter, c_expl, c_pen, dtype, device, stride, offset, n_lanes, knobs, eval_cache, spec_rows)
     if _SESSION["key"] == key and _SESSION["sess"] is not None and _SESSION["cap"] >= n_req:
         return _SESSION["sess"]

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define C4A0_ABI_VERSION 2
+#define C4A0_ABI_VERSION 3
 #define C4A0_N_ROWS 6               /* lib.rs:29 */
 #define C4A0_N_COLS 7               /* lib.rs:28 */
 #define C4A0_BUF_N_CHANNELS 2       /* lib.rs:30 */
@@ -78,6 +78,14 @@ typedef struct {
                                   up to a power of two; 0 = sized from n_slots * n_mcts_iterations and the
                                   free device memory */
   uint32_t spec_rows;          /* with C4A0_FLAG_SPECULATE: rows a small batch is topped up to (0 = 8192, at most n_slots) */
+  /* Dirichlet noise on the root's priors (AlphaZero's exploration noise; the reference has none — mcts.rs:114-132
+   * stores the network's masked softmax unchanged — so both default to 0 = off, which is the parity path).
+   * With alpha > 0 and epsilon > 0 a node's priors become (1 - epsilon) P + epsilon eta, eta ~ Dir(alpha) over its
+   * legal moves, once, when the node becomes the root of a search (game start, every move): at its expansion if it
+   * is expanded as the root, at the re-root (mcts.rs:187-206) if the subtree is reused.  The draw is a pure function
+   * of (game_id, moves played, column), so games are reproducible and independent of scheduling. */
+  float dirichlet_alpha;
+  float dirichlet_epsilon;
 } c4a0_config;
 
 /* Evaluate every waiting leaf even when several games wait on the same (position, model); by default

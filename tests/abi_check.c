@@ -26,6 +26,8 @@ int main(void) {
   F(c4a0_config, arena_blocks);
   F(c4a0_config, eval_cache_entries);
   F(c4a0_config, spec_rows);
+  F(c4a0_config, dirichlet_alpha);
+  F(c4a0_config, dirichlet_epsilon);
   S(c4a0_progress);
   F(c4a0_progress, n_requests);
   F(c4a0_progress, n_started);

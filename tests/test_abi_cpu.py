@@ -29,7 +29,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in L.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.c4a0_abi_version() == 2
+    assert lib.c4a0_abi_version() == 3
 
 
 def test_struct_layouts_match_the_compiled_headers(tmp_path):
