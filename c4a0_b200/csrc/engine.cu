@@ -995,6 +995,7 @@ __device__ __forceinline__ uint32_t mover_slot(const Dev& D, uint32_t m, uint32_
   return (uint32_t)v;
 }
 
+constexpr uint32_t STEAL_BACKLOG_MAX = 16;   // k_step's CTAs take compactions off the list while at most this many wait
 constexpr uint32_t INLINE_COMPACTIONS = 4;  // up to this many, k_step's last CTA compacts by itself
 
 // ------------------------------------------------------------------------------------------------
@@ -1179,7 +1180,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 7) k_step(Dev D) {  // <= 72 reg
     if (threadIdx.x == 0) {
       uint32_t got = 0xffffffffu;
       uint32_t c = *reinterpret_cast<volatile uint32_t*>(&D.g->mover_claim);
-      while (c < *reinterpret_cast<volatile uint32_t*>(&D.g->n_movers)) {
+      for (;;) {
+        const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&D.g->n_movers);
+        // a long backlog (minimal arenas: every re-root compacts) is left to k_tail, whose larger CTAs copy an
+        // arena faster and do not hold up the later waves of this kernel (config 4: 131,072 games, 8 waves)
+        if (c >= n || n - c > STEAL_BACKLOG_MAX) break;
         const uint32_t prev = atomicCAS(&D.g->mover_claim, c, c + 1u);
         if (prev == c) {
           got = mover_slot(D, c, epoch);

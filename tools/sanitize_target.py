@@ -47,3 +47,18 @@ for cls, dt in ((FusedNet, torch.bfloat16), (FoldedNet, torch.float32)):
             net(buf, out=out)
         torch.cuda.synchronize()
     print(cls.__name__, "ok", flush=True)
+
+# the shipped path: c4a0_rust.play_games -> c4a0_engine_run_net (k_step <-> k_net2 chained by programmatic dependent
+# launch), minimal arenas (every re-root compacts: the work-stealing path of k_step), cache + speculation
+if "--native" in sys.argv:
+    import c4a0_rust  # noqa: E402
+    from c4a0_b200 import selfplay  # noqa: E402
+
+    selfplay.DEFAULTS["arena_blocks"] = 26
+    m = ConnectFourNet(ModelConfig(n_residual_blocks=1, conv_filter_size=8, n_policy_layers=3, n_value_layers=2)).cuda().eval()
+    m = m.to(torch.bfloat16)
+    reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in range(96)]
+    res = c4a0_rust.play_games(reqs, 64 + 64, 24, 6.6, 0.01, m)
+    print("native path:", res._run_info.ticks, "ticks,", int(res._soa.n_samples.sum()), "samples,",
+          res._run_info.stats["compactions"], "compactions,", res._run_info.stats["spec_rows"], "speculative rows", flush=True)
+    c4a0_rust._native.close_cached_session()
