@@ -422,14 +422,13 @@ def run_ours(args):
         reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in ids]
         # max_nn_batch_size: the resident games plus room for the speculative rows (play_games keeps
         # n_slots + spec_rows within the caller's bound)
-        # the trainer lives on rank 0: at N > 1 the other ranks keep their samples on the device and send the
-        # valid ones, packed, straight from the engine's sample store to rank 0 (NCCL send/recv), which
-        # copies everything to the host; rank 0's own games come back through play_games as usual
-        selfplay.DEFAULTS["fetch"] = world == 1 or rank == 0
+        # the trainer lives on rank 0: at N > 1 every rank keeps its samples on the device; the valid ones travel
+        # packed, straight from the engines' sample stores, to rank 0 (NCCL send/recv), which copies them to the host
+        selfplay.DEFAULTS["fetch"] = world == 1  # at N > 1 the gather below delivers rank 0's own games as well
         with torch.cuda.nvtx.range("play_games"):
             res = c4a0_rust.play_games(reqs, G + SPEC_ROOM, args.sims, C_EXPLORATION, C_PLY_PENALTY, evaluator)
         n_pos = int(res._run_info.stats["samples"])
-        checksum = float(res._soa.q_no_penalty.sum())  # touch the host result
+        checksum = float(res._soa.q_no_penalty.sum()) if world == 1 else 0.0  # touch the host result
         if world > 1:
             meta = np.array([(i, 0, 0) for i in ids], dtype=np.uint64)
             gm, gc, gp = D.gather_session_samples(c4a0_rust._native._SESSION["sess"], meta, packed_result=True)
@@ -520,8 +519,9 @@ def run_ours(args):
         "e2e": {
             "value": positions_all / e2e_s_max, "unit": UNIT,
             "h2d_bytes_per_step": 3 * 8 * G,
-            # rank 0: its own games as padded arrays, plus (N > 1) every rank's valid samples packed at 52 B each
-            "d2h_bytes_per_step": G * (4 + 43 * (8 + 8 + 28 + 4 + 4)) + (0 if world == 1 else int(52 * positions_all / max(1, args.steps)) + 28 * G * world),
+            # N = 1: the games as padded arrays; N > 1 (rank 0): every rank's valid samples packed at 52 B each
+            "d2h_bytes_per_step": (G * (4 + 43 * (8 + 8 + 28 + 4 + 4)) if world == 1
+                                   else int(52 * positions_all / max(1, args.steps)) + 28 * G * world),
             "sims_per_s": sims_all / e2e_s_max, "api": "c4a0_rust.play_games(list[GameMetadata], ...) -> PlayGamesResult",
             "wall_ms_per_step": 1e3 * wall_max / max(1, args.steps),
         },

@@ -135,22 +135,24 @@ def gather_packed(meta: torch.Tensor, counts: torch.Tensor, packed: torch.Tensor
     return out
 
 
-_PINNED = {}  # dtype -> flat pinned staging tensor, grown on demand (cudaHostAlloc of ~100 MB costs tens of ms per call)
+_PINNED = {}  # (name, dtype) -> flat pinned staging tensor, grown on demand (cudaHostAlloc of ~100 MB costs tens of ms per call)
 
 
-def _to_host(t: torch.Tensor) -> np.ndarray:
-    """Device tensor -> a fresh numpy array, staged through a cached pinned buffer (a pageable destination
-    halves the copy rate; allocating the pinned buffer anew every generation costs more than the copy)."""
+def _to_host(t: torch.Tensor, name: str = "", copy: bool = True) -> np.ndarray:
+    """Device tensor -> numpy array, staged through a cached pinned buffer (a pageable destination halves the
+    copy rate; allocating the pinned buffer anew every generation costs more than the copy).  copy=False returns
+    a view of the staging buffer `name`: valid until the next call with the same name."""
     if not t.is_cuda:
         return t.numpy()
     n = t.numel()
-    buf = _PINNED.get(t.dtype)
+    key = (name, t.dtype)
+    buf = _PINNED.get(key)
     if buf is None or buf.numel() < n:
-        buf = _PINNED[t.dtype] = torch.empty(max(n, 1024), dtype=t.dtype, pin_memory=True)
+        buf = _PINNED[key] = torch.empty(max(n, 1024), dtype=t.dtype, pin_memory=True)
     h = buf[:n].view(t.shape)
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return h.numpy().copy()
+    return h.numpy().copy() if copy else h.numpy()
 
 
 def unpack_samples_device(counts: torch.Tensor, packed: torch.Tensor):
@@ -171,8 +173,9 @@ def _finish_gather(parts, packed_result: bool = False):
     meta = torch.cat([p[0] for p in parts])
     counts = torch.cat([p[1] for p in parts])
     packed = torch.cat([p[2] for p in parts])
-    if packed_result:
-        return _to_host(meta).view(np.uint64), _to_host(counts), _to_host(packed)
+    if packed_result:  # views of the pinned staging buffers: valid until the next gather (see gather_session_samples)
+        return (_to_host(meta, "meta", copy=False).view(np.uint64), _to_host(counts, "counts", copy=False),
+                _to_host(packed, "packed", copy=False))
     if packed.is_cuda:
         c, m, v, pol, qp, qn = unpack_samples_device(counts, packed)
         return _to_host(meta).view(np.uint64), GameSamples(_to_host(c).astype(np.uint32), _to_host(m).view(np.uint64), _to_host(v).view(np.uint64),
@@ -204,8 +207,9 @@ def gather_samples(meta: np.ndarray, soa: GameSamples, device: Optional[torch.de
 def gather_session_samples(session, meta: np.ndarray, dst: int = 0, packed_result: bool = False):
     """The samples of `session`'s last play() from every rank onto `dst`, packed on the device straight out of
     the engines' sample stores (c4a0_engine_results_dev): no padded arrays, no host bounce on the senders.
-    Returns (meta u64 [G,3], GameSamples) on `dst` — or, with packed_result, (meta, counts, packed [S,13]) —
-    and a tuple of Nones elsewhere."""
+    Returns (meta u64 [G,3], GameSamples) on `dst` — or, with packed_result, (meta, counts, packed [S,13]) as views
+    of pinned staging buffers that the next packed gather overwrites (copy what must outlive it) — and a tuple of
+    Nones elsewhere."""
     from .selfplay import _wrap_i64, _wrap_u32  # engine-owned device arrays as tensors, no copy
 
     dev = session.device
