@@ -226,3 +226,25 @@ def test_play_games_with_a_bf16_module_uses_the_native_kernel_and_keeps_the_trai
     assert np.array_equal(a._soa.mask, b._soa.mask) and np.array_equal(a._soa.policy, b._soa.policy)
     assert int((a._soa.n_samples >= 8).sum()) == 40
     c4a0_rust._native.close_cached_session()
+
+
+def test_dependent_launch_does_not_change_results():
+    """c4a0_engine_run_net chains k_step and k_net2 by programmatic dependent launch (C4A0_PDL=0: ordinary
+    launches).  Either way every read of a predecessor's data stands behind griddepcontrol.wait: same games."""
+    import os
+
+    import c4a0_rust
+
+    model = _model(8, 3, 2).to(torch.bfloat16)
+    reqs = [c4a0_rust.GameMetadata(i, 0, 0) for i in range(300)]
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["C4A0_PDL"] = flag
+        try:
+            out[flag] = c4a0_rust.play_games(reqs, 256 + 256, 48, 6.6, 0.01, model)
+        finally:
+            os.environ.pop("C4A0_PDL", None)
+    c4a0_rust._native.close_cached_session()
+    assert out["1"]._run_info.report["ticks"] > 0
+    for f in ("n_samples", "mask", "value", "policy", "q_penalty", "q_no_penalty"):
+        assert np.array_equal(getattr(out["1"]._soa, f), getattr(out["0"]._soa, f)), f
