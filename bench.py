@@ -6,10 +6,13 @@ A *step* is one whole self-play job through the public API: `c4a0_rust.play_game
 HOST request objects in and HOST samples out (BASELINE.json configs[1]: 16,384 lockstep games x 600
 MCTS sims/move, default c4a0 ResNet with random init, per GPU).  From the same K steps:
   value        positions/s over the device-timed search region (CUDA events, inputs resident in HBM)
-  e2e.value    positions/s over the wall clock of the API calls (H2D of the requests, engine set-up,
-               CUDA-graph capture, search, D2H of the samples)
+  e2e.value    positions/s over the wall clock of the API calls (H2D of the requests, weight folding, search,
+               D2H of the samples; at N > 1 the NCCL weight broadcast and the packed sample gather to rank 0)
   roofline     the tree kernel `k_step` (apply + select): algorithmic bytes per launch / its average
-               device time, sampled with CUDA events on ticks inside the timed region
+               device time, sampled with CUDA events on ticks inside the timed region; `traffic` = DRAM bytes of
+               that kernel's launches in this job from the round's ncu capture (profiles/rNN_kernel_counters.json)
+  nn_roofline  the network kernel `k_net2` against the measured dense bf16 peak, with the tensor-pipe utilisation
+               ncu measured for it
   cpu_baseline the oracle's threaded restatement of rust/src/self_play.rs on the host cores
                (rank 0, N=1 only), network evaluated through the numpy callback on cuda:0 as the
                reference does

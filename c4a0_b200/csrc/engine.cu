@@ -21,9 +21,10 @@
 //     simulation order — the reference's accumulation order.
 //   * Re-rooting keeps the chosen child's subtree and drops the siblings.  Nothing is copied while
 //     the arena has room (root_block simply becomes the child's block); when a half fills up, one
-//     CTA per game copies the live subtree breadth-first into the other half.  Memory per
-//     game is 2 * arena_blocks * 160 B, with arena_blocks >= n_iterations + 2.  (The copy runs as
-//     k_tail.)
+//     CTA copies the live subtree breadth-first into the other half: a CTA of k_step that is done
+//     with its own games takes the arena off an epoch-tagged list while slower CTAs still run
+//     (work stealing), long backlogs go to k_tail.  Memory per game is 2 * arena_blocks * 160 B,
+//     with arena_blocks >= n_iterations + 2.
 //   * The network batch is dense and de-duplicated, like the reference's NN thread builds it
 //     (self_play.rs:203-220: HashSet<Pos> per model).  As soon as a game knows its next leaf it
 //     inserts (position, model) into an epoch-tagged hash table; the first game to claim a key
@@ -36,10 +37,16 @@
 //     expanded, whose answers land in the same table before selection gets to them.  Both assume an
 //     evaluator that is a pure function of (model, position); game records do not change.
 //
+//   * Optionally (c4a0_config.dirichlet_*) root priors get Dirichlet noise; the reference has none, and
+//     the default kernel k_step<false> contains none of that code.
+//
 // One tick = k_step, then the network on rows [0, n_rows).  The last CTA of k_step to finish closes
-// the tick: it compacts the (few) arenas that filled up and publishes the tick's status (n_rows,
-// finished games) to mapped host memory.  Only a burst of compactions is handed to a second kernel,
-// k_tail (one CTA per arena), which the host launches when the status word asks for it.
+// the tick: it compacts the (few) arenas still on the list and publishes the tick's status (n_rows,
+// finished games) to mapped host memory.  Only a long backlog of compactions is handed to a second
+// kernel, k_tail (one CTA per arena), which the host launches when the status word asks for it.
+// The host loop (c4a0_engine_run / c4a0_engine_run_net at the end of this file) keeps one tick queued
+// ahead of the GPU; with the library's own network kernel (net.cu) the two kernels of a tick are chained
+// by programmatic dependent launch.
 // No CPU fallback exists: every entry point that computes needs the GPU and fails loudly.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

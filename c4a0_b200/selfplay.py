@@ -1,22 +1,25 @@
-"""Lockstep self-play driver: the engine's tree kernels + a PyTorch network on CUDA streams.
+"""Lockstep self-play driver: the engine's tree kernels + the network on CUDA streams.
 
 This is the B200 replacement for the thread/channel machinery of rust/src/self_play.rs:39-246
 (`self_play`, `NNThread`).  There the NN thread collects leaf positions from a queue, de-duplicates
 them, builds a numpy batch, calls Python, and fans results back through another queue; here a
 *tick* is
 
-    network(planes[:B]) -> logits, q_penalty, q_no_penalty     (PyTorch, bf16 or fp32, CUDA graph)
-    engine tick         -> expand + backup + move + select + dedup/pack the next planes (our kernels)
+    network(planes[:B]) -> logits, q_penalty, q_no_penalty
+    engine tick         -> expand + backup + move + select + dedup/pack the next planes (k_step)
 
-on the same device buffers.  The network is captured once per batch-size bucket into CUDA graphs;
-the C++ host loop (`c4a0_engine_run`) then alternates tree ticks and the smallest graph that covers
-the tick's live rows until every game has finished — no Python in the loop.  With `n_lanes=2` the
-games are split over two engines on two streams, so one half's tree tick hides under the other
-half's network.
+on the same device buffers, driven by the C++ host loop until every game has finished — no Python in
+the loop.  The network is either
+  * the library's own kernel (`native_net.NativeEvaluator`, csrc/net.cu: bf16, one launch per tick that
+    reads the batch size on the device; `c4a0_engine_run_net` launches both kernels of a tick, chained by
+    programmatic dependent launch) — the default for a bf16 `ConnectFourNet`; or
+  * a PyTorch callable captured once per batch-size bucket into CUDA graphs (`c4a0_engine_run` picks the
+    smallest graph that covers the tick's rows): fp32 networks, several models in one batch, anything else.
+With `n_lanes=2` the games are split over two engines on two streams (measured: no gain).
 
-Two evaluator contracts are supported:
-  * device evaluators (fast path): `fn(planes: cuda Tensor[B, stride]) -> (policy[B,7], qp[B], qn[B])`
-    cuda tensors — `DeviceEvaluator.from_model(ConnectFourNet)` builds the GEMM-folded form;
+Evaluator contracts:
+  * device evaluators (fast path): `NativeEvaluator`, or `fn(planes: cuda Tensor[B, stride]) ->
+    (policy[B,7], qp[B], qn[B])` cuda tensors — `DeviceEvaluator.from_model(ConnectFourNet)` picks the form;
   * the reference's numpy callback `cb(model_id, ndarray[B,2,6,7]) -> (policy, qp, qn)`
     (rust/src/pybridge.rs:161-199), served by `play_callback` with host copies every tick.
 """
