@@ -213,7 +213,8 @@ def cpu_sample(args, budget_s: float, rate_hint: float = 0.0) -> dict:
     reference's NN batch size): the first `budget` simulations of the job.  Returns the raw run."""
     nn_device = _nn_device(args)
     if rate_hint <= 0.0:
-        probe = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=150_000)
+        cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=100_000)  # warm-up: threads, CUDA context
+        probe = cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=400_000)
         rate_hint = probe["sims"] / probe["seconds"]
     budget = int(max(300_000, rate_hint * budget_s))
     return cpu_reference_run(CPU_GAMES, args.sims, args.width, nn_device, max_sims=budget)
