@@ -170,3 +170,42 @@ def test_bulk_cbor_codec_equals_the_python_codec_byte_for_byte():
     assert again.to_cbor() == res.to_cbor()
     empty = R.PlayGamesResult()
     assert R.PlayGamesResult.from_cbor(empty.to_cbor()).to_cbor() == empty.to_cbor() == _cbor.dumps({"results": []})
+
+
+def test_cbor_bytes_of_a_hand_encoded_document():
+    """A document small enough to encode by hand from RFC 8949 and serde's data model (structs = maps keyed by
+    field name in declaration order: pybridge.rs:60-63, types.rs:36-48, 65-71, 105-110, c4r.rs:14-17; integers with the
+    shortest head; f32 as a half float where that is lossless).  No codec is involved in producing the expectation."""
+    from c4a0_b200.engine import GameSamples
+
+    def text(s):
+        assert len(s) < 24
+        return bytes([0x60 | len(s)]) + s.encode()
+
+    half = {0.5: b"\xf9\x38\x00", -1.0: b"\xf9\xbc\x00", 0.25: b"\xf9\x34\x00", 0.0: b"\xf9\x00\x00"}
+    third = b"\xfa" + np.float32(1 / 3).tobytes()[::-1]  # not representable as a half: stays a single
+    want = (
+        b"\xa1" + text("results") + b"\x81"                                   # {results: [ one game
+        + b"\xa2" + text("metadata") + b"\xa3" + text("game_id") + b"\x18\x2a" + text("player0_id") + b"\x00"
+        + text("player1_id") + b"\x1b" + (2 ** 40).to_bytes(8, "big")          # u64 that needs the 8-byte head
+        + text("samples") + b"\x82"                                            # two samples
+        + b"\xa4" + text("pos") + b"\xa2" + text("mask") + b"\x01" + text("value") + b"\x00"
+        + text("policy") + b"\x87" + half[0.5] * 6 + third
+        + text("q_penalty") + half[-1.0] + text("q_no_penalty") + half[0.25]
+        + b"\xa4" + text("pos") + b"\xa2" + text("mask") + b"\x19\x01\x81" + text("value") + b"\x18\x80"
+        + text("policy") + b"\x87" + half[0.0] * 7
+        + text("q_penalty") + half[0.0] + text("q_no_penalty") + half[0.5]
+    )
+    M = 43
+    soa = GameSamples(np.array([2], np.uint32), np.zeros((1, M), np.uint64), np.zeros((1, M), np.uint64),
+                      np.zeros((1, M, 7), np.float32), np.zeros((1, M), np.float32), np.zeros((1, M), np.float32))
+    soa.mask[0, :2] = [1, 0x181]
+    soa.value[0, :2] = [0, 0x80]
+    soa.policy[0, 0] = [0.5] * 6 + [np.float32(1 / 3)]
+    soa.q_penalty[0, :2] = [-1.0, 0.0]
+    soa.q_no_penalty[0, :2] = [0.25, 0.5]
+    res = R.PlayGamesResult._from_soa(np.array([[42, 0, 2 ** 40]], np.uint64), soa)
+    assert res.to_cbor() == want
+    back = R.PlayGamesResult.from_cbor(want)
+    assert back.results[0].metadata.player1_id == 2 ** 40 and len(back.results[0].samples) == 2
+    assert back.to_cbor() == want
