@@ -993,13 +993,19 @@ __device__ __forceinline__ void push_mover(const Dev& D, uint32_t slot, uint32_t
   const uint32_t i = atomicAdd(&D.g->n_movers, 1u);
   atomicExch(D.movers + i, ((unsigned long long)epoch << 32) | slot);
 }
+constexpr uint32_t NO_MOVER = 0xffffffffu;
 __device__ __forceinline__ uint32_t mover_slot(const Dev& D, uint32_t m, uint32_t epoch) {
-  unsigned long long v;
-  do {  // the entry is written right after the counter was advanced
-    v = *reinterpret_cast<volatile unsigned long long*>(D.movers + m);
-  } while ((uint32_t)(v >> 32) != epoch);
-  __threadfence();
-  return (uint32_t)v;
+  // the entry is written right after the counter was advanced: a handful of polls at most.  Bounded all the
+  // same — a wait that long is a protocol bug, and a bug must surface as C4A0_E_ENGINE, never as a hung GPU
+  for (uint32_t spin = 0; spin < (1u << 22); spin++) {
+    const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(D.movers + m);
+    if ((uint32_t)(v >> 32) == epoch) {
+      __threadfence();
+      return (uint32_t)v;
+    }
+  }
+  D.g->error = C4A0_E_ENGINE;
+  return NO_MOVER;
 }
 
 constexpr uint32_t STEAL_BACKLOG_MAX = 16;   // k_step's CTAs take compactions off the list while at most this many wait
@@ -1012,6 +1018,7 @@ constexpr uint32_t INLINE_COMPACTIONS = 4;  // up to this many, k_step's last CT
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void compact_one(const Dev& D, uint32_t slot) {
   __shared__ uint32_t sh_next, sh_head;
+  if (slot >= D.n_slots) return;  // NO_MOVER (CTA-uniform): see mover_slot
   Slot* S = D.slots + slot;
   const uint32_t half = S->half;
   const uint32_t src_root = S->root_block;
