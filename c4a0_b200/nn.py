@@ -205,8 +205,9 @@ class FoldedNet(nn.Module):
     @classmethod
     @torch.no_grad()
     def _fold(cls, model: ConnectFourNet):
-        """float64 folded weights {buffer name: tensor} + structure (n_blocks, joint_first, n_p, n_v)."""
-        model = model.eval()
+        """float64 folded weights {buffer name: tensor} + structure (n_blocks, joint_first, n_p, n_v).  The fold is
+        the eval-mode function (BatchNorm with its running statistics); only parameters and buffers are read, the
+        module's training flag is left as found."""
         F = model.fc_size
         out = {}
         layers = list(model.conv.children())

@@ -77,7 +77,9 @@ class DeviceEvaluator:
         self.dtype = dtype
         self.plane_stride = plane_stride  # elements per row of the buffer the engine writes planes into
         self.plane_offset = plane_offset  # first plane element of a row (the buffer may hold more)
-        if isinstance(module_or_fn, torch.nn.Module):
+        if isinstance(module_or_fn, torch.nn.Module) and module_or_fn.training:
+            # a module evaluated as it is (no folding): self-play needs inference behaviour (BatchNorm running
+            # statistics, no dropout).  FoldedNet / FusedNet / NativeEvaluator never touch the caller's module.
             module_or_fn.eval()
 
     @classmethod

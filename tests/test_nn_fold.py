@@ -100,3 +100,22 @@ def test_fused_form_equals_module_and_refreshes_in_place():
         for a, b in zip(f(buf), model2(x)):
             assert torch.allclose(a.double(), b, atol=1e-6)
     assert not FusedNet.supports(ConnectFourNet(ModelConfig(n_residual_blocks=2, conv_filter_size=2, n_policy_layers=2, n_value_layers=2)))
+
+
+def test_folding_leaves_the_callers_module_alone():
+    """handing a module that is being trained to the engine must not flip it to eval mode.  The fold
+    reads parameters and running statistics only, so it is the same in either mode."""
+    from c4a0_b200.nn import ConnectFourNet, FoldedNet, ModelConfig
+
+    torch.manual_seed(5)
+    m = ConnectFourNet(ModelConfig(n_residual_blocks=1, conv_filter_size=4, n_policy_layers=2, n_value_layers=2))
+    for mod in m.modules():
+        if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 1.5)
+    m.train()
+    a, meta_a = FoldedNet._fold(m)
+    assert m.training and all(mod.training for mod in m.modules())
+    m.eval()
+    b, meta_b = FoldedNet._fold(m)
+    assert meta_a == meta_b and all(torch.equal(a[k], b[k]) for k in a)
