@@ -442,8 +442,13 @@ def run_ours(args):
                 checksum += float(gp[:, 12].view(np.float32).sum())
         return time.perf_counter() - t0, res._run_info, n_pos, checksum
 
-    for _ in range(args.warmup):
+    first_call_s = None
+    for i in range(args.warmup):
+        t_first = time.perf_counter()
         one_step()
+        if i == 0:  # engine creation (arenas, cache, network buffers), first launches: what the session cache hides later
+            torch.cuda.synchronize()
+            first_call_s = time.perf_counter() - t_first
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -528,6 +533,9 @@ def run_ours(args):
                                    else int(52 * positions_all / max(1, args.steps)) + 28 * G * world),
             "sims_per_s": sims_all / e2e_s_max, "api": "c4a0_rust.play_games(list[GameMetadata], ...) -> PlayGamesResult",
             "wall_ms_per_step": 1e3 * wall_max / max(1, args.steps),
+            # the very first call of the process (untimed warm-up step 1): device allocations of the engine, the
+            # evaluation cache and the network, first kernel launches; later calls reuse the cached session
+            "first_call_ms": None if first_call_s is None else 1e3 * first_call_s,
         },
         # our kernels inside the timed region: k_step once per tick, k_tail where a tick needed it,
         # k_init_globals + k_init + k_tail per call, k_sum_counters per call, and k_head_epilogue (the
