@@ -638,49 +638,95 @@ constexpr unsigned long long TAG_DYING = 1ull << 32;
 // The game's freshly selected, non-terminal leaf: answered from the cache (-> true, values in
 // x/vq/vn) or not.  On a miss lane 0 may claim the entry for the answer the network will deliver
 // next tick (G.cache_own), or mark a readable entry of another key for replacement.
+// The table is 2-way set associative: the two 64-byte entries of a 128-byte line form a set (one memory
+// transaction serves both).  Measured on the bench job with one way: in the last 500 ticks of a job EVERY miss
+// of a live game was a collision (the wanted position's entry held another live key), and each collision costs
+// two network round trips (mark dying, ask uncached, claim on the next request).
+struct WayState {
+  unsigned long long tag;
+  bool mine, dying, old, same;
+};
+__device__ __forceinline__ WayState way_state(const uint4 a, const uint64_t emodel, uint64_t key, uint64_t model, uint32_t job,
+                                              uint32_t epoch) {
+  WayState s;
+  const uint64_t ekey = (uint64_t)a.x | ((uint64_t)a.y << 32);
+  s.tag = (unsigned long long)a.z | ((unsigned long long)a.w << 32);
+  s.mine = (uint32_t)(s.tag >> 33) == job;
+  s.dying = (s.tag & TAG_DYING) != 0ull;
+  s.old = (uint32_t)s.tag < epoch;  // the last state change happened in an earlier tick
+  s.same = ekey == key && emodel == model;
+  return s;
+}
+// way to claim for a key that has no entry in the set: an empty / stale way first, else one whose entry has been
+// dying since an earlier tick; -1 = both ways hold live entries
+__device__ __forceinline__ int claimable_way(const WayState& s0, const WayState& s1) {
+  if (!s0.mine) return 0;
+  if (!s1.mine) return 1;
+  if (s0.dying && s0.old) return 0;
+  if (s1.dying && s1.old) return 1;
+  return -1;
+}
+
 __device__ __forceinline__ bool cache_lookup(const Dev& D, const Lanes& L, Game& G, bool pred, Pos leaf, uint64_t model,
                                              uint32_t epoch, float& x, float& vq, float& vn) {
   const uint64_t key = pos_key(leaf);
-  const uint32_t h = (uint32_t)splitmix64(key ^ (model * 0x9E3779B97F4A7C15ULL)) & D.cache_mask;
+  const uint32_t h0 = (uint32_t)splitmix64(key ^ (model * 0x9E3779B97F4A7C15ULL)) & D.cache_mask & ~1u;
   bool hit = false;
   if (pred) {
-    EvalEntry* E = D.cache + h;
-    const uint4 a = *reinterpret_cast<const uint4*>(E);        // key, tag
-    const uint4 b = *(reinterpret_cast<const uint4*>(E) + 1);  // model, qp, qn
-    const float lg = E->logit[L.l < 7 ? L.l : 6];
-    const uint64_t ekey = (uint64_t)a.x | ((uint64_t)a.y << 32);
-    const unsigned long long tag = (unsigned long long)a.z | ((unsigned long long)a.w << 32);
-    const uint64_t emodel = (uint64_t)b.x | ((uint64_t)b.y << 32);
-    const bool mine = (uint32_t)(tag >> 33) == D.job;
-    const bool dying = (tag & TAG_DYING) != 0ull;
-    const bool old = (uint32_t)tag < epoch;  // the last state change happened in an earlier tick
-    const bool same = ekey == key && emodel == model;
-    hit = mine && !dying && old && same;
+    EvalEntry* E = D.cache + h0;  // ways E[0], E[1]
+    const int li = L.l < 7 ? L.l : 6;
+    const uint4 a0 = *reinterpret_cast<const uint4*>(E), b0 = *(reinterpret_cast<const uint4*>(E) + 1);          // key, tag | model, qp, qn
+    const uint4 a1 = *reinterpret_cast<const uint4*>(E + 1), b1 = *(reinterpret_cast<const uint4*>(E + 1) + 1);
+    const float lg0 = E[0].logit[li], lg1 = E[1].logit[li];
+    const WayState s0 = way_state(a0, (uint64_t)b0.x | ((uint64_t)b0.y << 32), key, model, D.job, epoch);
+    const WayState s1 = way_state(a1, (uint64_t)b1.x | ((uint64_t)b1.y << 32), key, model, D.job, epoch);
+    const bool hit0 = s0.mine && !s0.dying && s0.old && s0.same, hit1 = s1.mine && !s1.dying && s1.old && s1.same;
     // claimed during the last tick with a known row: that row of the last batch holds the answer
-    const uint32_t frow = (mine && !dying && same && (uint32_t)tag == epoch) ? E->row : 0u;
-    if (hit) {
-      x = lg;
-      vq = __uint_as_float(b.z);
-      vn = __uint_as_float(b.w);
+    uint32_t frow = 0u;
+    if (!hit0 && !hit1) {
+      if (s0.mine && !s0.dying && s0.same && (uint32_t)s0.tag == epoch) frow = E[0].row;
+      else if (s1.mine && !s1.dying && s1.same && (uint32_t)s1.tag == epoch) frow = E[1].row;
+    }
+    if (hit0 || hit1) {
+      hit = true;
+      x = hit0 ? lg0 : lg1;
+      vq = __uint_as_float(hit0 ? b0.z : b1.z);
+      vn = __uint_as_float(hit0 ? b0.w : b1.w);
       G.hits++;
     } else if (frow) {
       hit = true;
-      x = D.logits[(size_t)(frow - 1u) * 7 + (L.l < 7 ? L.l : 6)];
+      x = D.logits[(size_t)(frow - 1u) * 7 + li];
       vq = D.qp[frow - 1u];
       vn = D.qn[frow - 1u];
       G.hits++;
     } else if (L.l == 0) {
       const unsigned long long jb = (unsigned long long)D.job << 33;
-      if (!mine || (dying && old)) {
-        if (atomicCAS(&E->tag, tag, jb | (unsigned long long)(epoch + 1u)) == tag) {
-          E->key = key;
-          E->model = model;
-          E->row = 0u;  // set by publish_leaf() if this game also leads the key
-          G.cache_own = h + 1u;
+      const bool here0 = s0.mine && s0.same, here1 = s1.mine && s1.same;  // the key has an entry, not readable (yet)
+      int w = -1;
+      if (here0 || here1) {
+        const WayState& s = here0 ? s0 : s1;
+        if (s.dying && s.old) w = here0 ? 0 : 1;  // its own dying copy may be claimed again
+      } else {
+        w = claimable_way(s0, s1);
+      }
+      if (w >= 0) {
+        EvalEntry* Ew = E + w;
+        const unsigned long long tag = w ? s1.tag : s0.tag;
+        if (atomicCAS(&Ew->tag, tag, jb | (unsigned long long)(epoch + 1u)) == tag) {
+          Ew->key = key;
+          Ew->model = model;
+          Ew->row = 0u;  // set by publish_leaf() if this game also leads the key
+          G.cache_own = h0 + (uint32_t)w + 1u;
           G.claims++;
         }
-      } else if (!dying && old && !same) {
-        atomicCAS(&E->tag, tag, jb | TAG_DYING | (unsigned long long)epoch);
+      } else if (!here0 && !here1) {
+        // both ways hold other live keys: retire the readable one that changed longest ago (claimable next tick)
+        const bool r0 = !s0.dying && s0.old, r1 = !s1.dying && s1.old;
+        int k = -1;
+        if (r0 && r1) k = (uint32_t)s0.tag <= (uint32_t)s1.tag ? 0 : 1;
+        else if (r0) k = 0;
+        else if (r1) k = 1;
+        if (k >= 0) atomicCAS(&E[k].tag, k ? s1.tag : s0.tag, jb | TAG_DYING | (unsigned long long)epoch);
       }
     }
   }
@@ -704,29 +750,34 @@ __device__ __forceinline__ uint64_t model_to_play(const Dev& D, const Game& G, P
 __device__ __forceinline__ bool spec_request(const Dev& D, const Game& G, Pos pos, uint32_t epoch, uint32_t budget) {
   const uint64_t model = model_to_play(D, G, pos);
   const uint64_t key = pos_key(pos);
-  const uint32_t h = (uint32_t)splitmix64(key ^ (model * 0x9E3779B97F4A7C15ULL)) & D.cache_mask;
-  EvalEntry* E = D.cache + h;
-  const unsigned long long tag = *reinterpret_cast<volatile unsigned long long*>(&E->tag);
-  const bool mine = (uint32_t)(tag >> 33) == D.job;
-  const bool dying = (tag & TAG_DYING) != 0ull;
-  const bool old = (uint32_t)tag < epoch;
-  if (mine && !(dying && old)) return true;  // cached, on its way, or another position lives here (never evicted for a guess)
+  const uint32_t h0 = (uint32_t)splitmix64(key ^ (model * 0x9E3779B97F4A7C15ULL)) & D.cache_mask & ~1u;
+  EvalEntry* E = D.cache + h0;
+  // (L2 loads: other SMs claim entries during the tick, and a stale L1 line would only cost a failed CAS)
+  const uint4 a0 = __ldcg(reinterpret_cast<const uint4*>(E)), a1 = __ldcg(reinterpret_cast<const uint4*>(E + 1));
+  const WayState s0 = way_state(a0, __ldcg(reinterpret_cast<const unsigned long long*>(&E[0].model)), key, model, D.job, epoch);
+  const WayState s1 = way_state(a1, __ldcg(reinterpret_cast<const unsigned long long*>(&E[1].model)), key, model, D.job, epoch);
+  // cached or on its way already
+  if ((s0.mine && s0.same && !(s0.dying && s0.old)) || (s1.mine && s1.same && !(s1.dying && s1.old))) return true;
+  const int w = claimable_way(s0, s1);
+  if (w < 0) return true;  // both ways hold live entries: a guess never evicts
   Globals* g = D.g;
   const uint32_t s = atomicAdd(&g->spec_acc, 1u);
   if (s >= budget) return false;
   uint2 item = make_uint2(0xffffffffu, 0u);
-  if (atomicCAS(&E->tag, tag, ((unsigned long long)D.job << 33) | (unsigned long long)(epoch + 1u)) == tag) {
-    E->key = key;
-    E->model = model;
+  EvalEntry* Ew = E + w;
+  const unsigned long long tag = w ? s1.tag : s0.tag;
+  if (atomicCAS(&Ew->tag, tag, ((unsigned long long)D.job << 33) | (unsigned long long)(epoch + 1u)) == tag) {
+    Ew->key = key;
+    Ew->model = model;
     const uint32_t row = atomicAdd(&g->rows_acc, 1u);
     atomicAdd(&g->spec_ok, 1u);
-    E->row = row + 1u;
+    Ew->row = row + 1u;
     D.row_slot[row] = 0xffffffffu;
     D.row_model[row] = model;
     D.row_mask[row] = pos.mask;
     D.row_value[row] = pos.value;
     write_planes(D, row, pos);
-    item = make_uint2(row, h);
+    item = make_uint2(row, h0 + (uint32_t)w);
   }
   D.spec_list[(size_t)(epoch & 1u) * D.spec_cap + s] = item;
   return true;
