@@ -1,5 +1,5 @@
 # in-kernel simulation budget while speculating = C4A0_INLINE_SPEC_MULT x max_inline_sims (default 4 x 3)
-for m in 1 2 3 4 6; do
+for m in ${MULTS:-1 2 3 4 6}; do
 C4A0_INLINE_SPEC_MULT=$m python bench.py --steps 2 --warmup 2 --no-ablation --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
