@@ -438,7 +438,8 @@ def run_ours(args):
             gm, gc, gp = D.gather_session_samples(c4a0_rust._native._SESSION["sess"], meta, packed_result=True)
             if rank == 0:  # host arrays: per game its id and sample count, per valid sample 52 bytes
                 state["gathered"] = int(gc.sum())
-                assert state["gathered"] >= n_pos and len(gm) == G * world and gp.shape == (state["gathered"], D.PACK_WORDS)
+                n_all = (args.total_games or args.games) if args.scaling == "strong" else G * world
+                assert state["gathered"] >= n_pos and len(gm) == n_all and gp.shape == (state["gathered"], D.PACK_WORDS)
                 checksum += float(gp[:, 12].view(np.float32).sum())
         return time.perf_counter() - t0, res._run_info, n_pos, checksum
 
