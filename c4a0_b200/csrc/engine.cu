@@ -31,7 +31,7 @@
 //     draws the next row number from an atomic counter and writes the input planes of that row,
 //     later games with the same key just remember who leads it.  Rows are dense, 0..n_rows-1.
 //   * Optionally (C4A0_FLAG_EVAL_CACHE) every answer of the network is kept, for the duration of a
-//     job, in a direct-mapped table keyed by (position, model): a leaf the job has evaluated before
+//     job, in a 2-way set-associative table keyed by (position, model): a leaf the job has evaluated before
 //     is answered inside the tick and the game goes on to its next simulation.  On top of that
 //     (C4A0_FLAG_SPECULATE) small batches are topped up with the children of the leaves being
 //     expanded, whose answers land in the same table before selection gets to them.  Both assume an
@@ -87,7 +87,8 @@ struct __align__(32) Block {
 };
 static_assert(sizeof(Block) == 160, "block must be ten 16-byte vectors");
 
-// Evaluation cache (C4A0_FLAG_EVAL_CACHE): one network answer per 64-byte entry, direct mapped.
+// Evaluation cache (C4A0_FLAG_EVAL_CACHE): one network answer per 64-byte entry; the two entries of a 128-byte
+// line form a set (2-way set associative, see cache_lookup).
 //   tag = job << 33 | dying << 32 | tick.  `job` counts set_requests() calls, so entries of earlier
 //   jobs are simply stale.  An entry is READABLE in tick e iff job matches, dying == 0 and tick < e.
 //   State changes go through one atomicCAS on the tag and never touch a payload that a reader of
